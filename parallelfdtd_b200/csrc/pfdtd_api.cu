@@ -1,0 +1,1131 @@
+// pfdtd_api.cu -- the C ABI (include/pfdtd.h): domain container, z-slab partitioning, halo
+// exchange and the step loop.  Host-side replacement of the reference's CudaMesh
+// (src/kernels/cudaMesh.{h,cu}) and launchFDTD3d* drivers (src/kernels/kernels3d.cu:31-482).
+#include "pfdtd_internal.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+
+namespace pfdtd {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+// ---- NCCL, loaded lazily so that single-GPU use has no NCCL dependency ---------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, ...) = nullptr;   // (ncclComm_t*, int nranks, ncclUniqueId by value, int rank)
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId { char bytes[128]; };   // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES 128)
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.lib) return PFDTD_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  PF_CHECK(h != nullptr, PFDTD_ERR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, ...))dlsym(h, "ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclSend");
+  g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclRecv");
+  g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  PF_CHECK(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd,
+           PFDTD_ERR_COMM, "libnccl is missing required symbols");
+  g_nccl.lib = h;
+  return PFDTD_OK;
+}
+#define PF_NCCL(call)                                                                               \
+  do {                                                                                              \
+    int r__ = (call);                                                                               \
+    if (r__ != 0) {                                                                                 \
+      pfdtd::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,                            \
+                       g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error");           \
+      return PFDTD_ERR_COMM;                                                                        \
+    }                                                                                               \
+  } while (0)
+
+// ---- containers -------------------------------------------------------------------------------------
+struct Partition {
+  int device = 0;
+  int64_t first = 0, size = 0;          // slices held: [first, first+size) in the local volume
+  uint8_t* pos = nullptr;
+  uint8_t* mat = nullptr;
+  bool owns_nodes = true;
+  void* P[2] = {nullptr, nullptr};
+  void* materials = nullptr;
+  cudaStream_t s_main = nullptr, s_edge = nullptr;
+  cudaEvent_t ev_src = nullptr, ev_int = nullptr, ev_edge = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  bool use_tma = false;
+  TmaMaps maps[2];                      // maps[c]: current field = P[c], overwritten field = P[1-c]
+  TmaConfig cfg_full{0, 1}, cfg_int{0, 1}, cfg_edge{0, 1};
+  int* d_step = nullptr;                // [0] step counter, [1] first recordable step
+  // sources / receivers that live in this partition
+  int n_src = 0, n_rec = 0;
+  int64_t* d_src_elem = nullptr; int32_t* d_src_type = nullptr; int32_t* d_src_slot = nullptr;
+  int64_t* d_rec_elem = nullptr; int32_t* d_rec_slot = nullptr;
+  void* d_src_samples = nullptr;        // [n_src_total][src_steps]
+  void* d_rec_out = nullptr;            // [n_rec_total][rec_cap]
+  std::vector<int32_t> rec_slots;       // host copy of owned receiver slots
+  std::vector<cudaEvent_t> kev;         // kernel timing events (pairs)
+};
+
+}  // namespace pfdtd
+
+using namespace pfdtd;
+
+struct pfdtd_solver {
+  // options
+  int64_t opt_matidx_as_written = 1, opt_soft_accumulate = 0, opt_kernel = KERNEL_AUTO, opt_global_z_first = 0,
+          opt_global_z_dim = 0, opt_double_pad = 0, opt_use_graph = 1, opt_overlap = 1, opt_tma_chunk = 0, opt_tma_tile = 0,
+          opt_time_kernels = 0;
+  int dtype = PFDTD_F32;
+  int element_type = 0;
+  int scheme = SCH_FORWARD;
+  uint32_t X = 0, Y = 0, Z = 0;          // padded dims of the local volume
+  uint32_t bx = 32, by = 4, bz = 1;
+  double params[4] = {0, 0, 0, 0};
+  std::vector<unsigned char> materials_host;   // [n_unique][20] of dtype
+  uint32_t n_unique = 0;
+  uint64_t n_air = 0, n_boundary = 0;
+  bool mesh_ready = false;
+  int stage_device = 0;
+  uint8_t* d_pos0 = nullptr;             // padded + translated node volumes before partitioning
+  uint8_t* d_mat0 = nullptr;
+  std::vector<Partition> parts;
+  int cur = 0;                           // index of the current field in Partition::P
+  int past_direction = 1;                // launchFDTD3dStep's static (kernels3d.cu:386)
+  // sources / receivers (host copies)
+  std::vector<int32_t> src_xyz, src_type, rec_xyz;
+  std::vector<unsigned char> src_samples;   // [n_src][src_steps] of dtype
+  uint32_t n_src = 0, n_rec = 0, src_steps = 0, rec_cap = 0;
+  bool srcrec_dirty = true;
+  // comm
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
+  cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;
+  float last_total_ms = 0, last_kernel_ms = 0, last_halo_ms = 0;
+  uint32_t last_kernel_launches = 0;
+  uint64_t launch_count = 0;
+  // graph
+  cudaGraphExec_t graph_exec = nullptr;
+  uint32_t graph_steps = 0;
+};
+
+namespace pfdtd {
+
+static size_t esize(const pfdtd_solver* s) { return s->dtype == PFDTD_F32 ? 4 : 8; }
+
+static void partition_indexing(uint32_t dim, uint32_t n, std::vector<int64_t>& first, std::vector<int64_t>& size) {
+  // CudaMesh::getPartitionIndexing, src/kernels/cudaMesh.h:280-307
+  first.resize(n);
+  size.resize(n);
+  int64_t ps = dim / n;
+  for (uint32_t i = 0; i < n; i++) {
+    int64_t s_inc = (i == 0) ? 0 : 1, e_inc = (i == n - 1) ? 0 : 1;
+    int64_t cs = ps + s_inc + e_inc;
+    if (i != 0 && i == n - 1) cs += (int64_t)dim - (int64_t)(i + 1) * ps;
+    first[i] = (int64_t)i * ps - s_inc;
+    size[i] = cs;
+  }
+}
+
+static int free_partitions(pfdtd_solver* s) {
+  if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+  for (auto& p : s->parts) {
+    cudaSetDevice(p.device);
+    if (p.s_main) cudaStreamSynchronize(p.s_main);
+    if (p.s_edge) cudaStreamSynchronize(p.s_edge);
+    if (p.owns_nodes) { cudaFree(p.pos); cudaFree(p.mat); }
+    cudaFree(p.P[0]); cudaFree(p.P[1]); cudaFree(p.materials); cudaFree(p.d_step);
+    cudaFree(p.d_src_elem); cudaFree(p.d_src_type); cudaFree(p.d_src_slot); cudaFree(p.d_rec_elem); cudaFree(p.d_rec_slot);
+    cudaFree(p.d_src_samples); cudaFree(p.d_rec_out);
+    if (p.s_main) cudaStreamDestroy(p.s_main);
+    if (p.s_edge) cudaStreamDestroy(p.s_edge);
+    for (cudaEvent_t e : {p.ev_src, p.ev_int, p.ev_edge, p.ev_t0, p.ev_t1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : p.kev) cudaEventDestroy(e);
+  }
+  s->parts.clear();
+  return PFDTD_OK;
+}
+
+static bool has_lower_ext(const pfdtd_solver* s) { return s->comm && s->rank > 0; }
+static bool has_upper_ext(const pfdtd_solver* s) { return s->comm && s->rank < s->nranks - 1; }
+
+// ---- per-partition source / receiver tables ----------------------------------------------------------
+static int prepare_srcrec(pfdtd_solver* s) {
+  if (!s->srcrec_dirty) return PFDTD_OK;
+  PF_CHECK(!s->parts.empty(), PFDTD_ERR_INVALID, "make_partition must be called first");
+  const int64_t XY = (int64_t)s->X * s->Y;
+  const int64_t zoff = s->opt_global_z_first;
+  if (s->rec_cap < s->src_steps) s->rec_cap = s->src_steps;
+  if (s->rec_cap == 0) s->rec_cap = 1;
+  for (size_t k = 0; k < s->parts.size(); k++) {
+    Partition& p = s->parts[k];
+    PF_CUDA(cudaSetDevice(p.device));
+    for (void* q : {(void*)p.d_src_elem, (void*)p.d_src_type, (void*)p.d_src_slot, (void*)p.d_rec_elem, (void*)p.d_rec_slot,
+                    p.d_src_samples, p.d_rec_out})
+      cudaFree(q);
+    p.d_src_elem = nullptr; p.d_src_type = nullptr; p.d_src_slot = nullptr; p.d_rec_elem = nullptr; p.d_rec_slot = nullptr;
+    p.d_src_samples = nullptr; p.d_rec_out = nullptr;
+    std::vector<int64_t> se, re;
+    std::vector<int32_t> st, ss, rs;
+    // sources: every partition that holds the slice, halo copies included (cudaMesh.h:321-338)
+    for (uint32_t i = 0; i < s->n_src; i++) {
+      int64_t z = (int64_t)s->src_xyz[3 * i + 2] - zoff;
+      if (z < p.first || z > p.first + p.size - 1) continue;
+      se.push_back((z - p.first) * XY + (int64_t)s->src_xyz[3 * i + 1] * s->X + s->src_xyz[3 * i]);
+      st.push_back(s->src_type[i]);
+      ss.push_back((int32_t)i);
+    }
+    // receivers: first partition containing the slice (cudaMesh.h:251-266); across processes the
+    // lower process owns the two shared slices
+    for (uint32_t i = 0; i < s->n_rec; i++) {
+      int64_t z = (int64_t)s->rec_xyz[3 * i + 2] - zoff;
+      if (z < p.first || z > p.first + p.size - 1) continue;
+      if (k > 0 && z <= s->parts[k - 1].first + s->parts[k - 1].size - 1) continue;
+      if (k == 0 && zoff > 0 && z <= 1) continue;
+      re.push_back((z - p.first) * XY + (int64_t)s->rec_xyz[3 * i + 1] * s->X + s->rec_xyz[3 * i]);
+      rs.push_back((int32_t)i);
+    }
+    p.n_src = (int)se.size();
+    p.n_rec = (int)re.size();
+    p.rec_slots = rs;
+    auto up = [&](void** d, const void* h, size_t bytes) -> int {
+      if (bytes == 0) return PFDTD_OK;
+      PF_CUDA(cudaMalloc(d, bytes));
+      PF_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+      return PFDTD_OK;
+    };
+    PF_TRY(up((void**)&p.d_src_elem, se.data(), se.size() * 8));
+    PF_TRY(up((void**)&p.d_src_type, st.data(), st.size() * 4));
+    PF_TRY(up((void**)&p.d_src_slot, ss.data(), ss.size() * 4));
+    PF_TRY(up((void**)&p.d_rec_elem, re.data(), re.size() * 8));
+    PF_TRY(up((void**)&p.d_rec_slot, rs.data(), rs.size() * 4));
+    if (p.n_src) PF_TRY(up(&p.d_src_samples, s->src_samples.data(), s->src_samples.size()));
+    if (s->n_rec) {
+      size_t bytes = (size_t)s->n_rec * s->rec_cap * esize(s);
+      PF_CUDA(cudaMalloc(&p.d_rec_out, bytes));
+      PF_CUDA(cudaMemset(p.d_rec_out, 0, bytes));
+    }
+  }
+  s->srcrec_dirty = false;
+  if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+  return PFDTD_OK;
+}
+
+static UpdateArgs make_update_args(pfdtd_solver* s, Partition& p, int z_begin, int z_end, cudaStream_t st) {
+  UpdateArgs a{};
+  a.dtype = s->dtype;
+  a.scheme = s->scheme;
+  a.pos = p.pos;
+  a.mat = p.mat;
+  a.P = p.P[s->cur];
+  a.Pn = p.P[1 - s->cur];
+  a.materials = p.materials;
+  a.n_coefs = s->n_unique * 20;
+  for (int i = 0; i < 4; i++) a.params[i] = s->params[i];
+  a.matidx_as_written = (int)s->opt_matidx_as_written;
+  a.X = (int)s->X;
+  a.Y = (int)s->Y;
+  a.z_begin = z_begin;
+  a.z_end = z_end;
+  a.stream = st;
+  return a;
+}
+
+static int launch_update(pfdtd_solver* s, Partition& p, int z_begin, int z_end, const TmaConfig& cfg, cudaStream_t st,
+                         bool timed) {
+  if (z_end <= z_begin) return PFDTD_OK;
+  UpdateArgs a = make_update_args(s, p, z_begin, z_end, st);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed) {
+    PF_CUDA(cudaEventCreate(&e0));
+    PF_CUDA(cudaEventCreate(&e1));
+    p.kev.push_back(e0);
+    p.kev.push_back(e1);
+    PF_CUDA(cudaEventRecord(e0, st));
+  }
+  if (p.use_tma) PF_TRY(launch_update_tma(a, p.maps[s->cur], cfg));
+  else PF_TRY(launch_update_plain(a));
+  if (timed) PF_CUDA(cudaEventRecord(e1, st));
+  s->launch_count++;
+  return PFDTD_OK;
+}
+
+static int launch_srcrec_for(pfdtd_solver* s, Partition& p, cudaStream_t st, int record, int inject, int advance) {
+  if (p.n_src == 0 && p.n_rec == 0 && !advance) return PFDTD_OK;
+  SrcRecArgs a{};
+  a.dtype = s->dtype;
+  a.P = p.P[s->cur];
+  a.n_rec = p.n_rec; a.rec_elem = p.d_rec_elem; a.rec_slot = p.d_rec_slot; a.rec_out = p.d_rec_out; a.rec_stride = s->rec_cap;
+  a.n_src = p.n_src; a.src_elem = p.d_src_elem; a.src_type = p.d_src_type; a.src_slot = p.d_src_slot;
+  a.src_samples = p.d_src_samples; a.src_stride = s->src_steps;
+  a.d_step = p.d_step;
+  a.do_record = record; a.do_inject = inject; a.soft_accumulate = (int)s->opt_soft_accumulate; a.advance = advance;
+  a.stream = st;
+  PF_TRY(launch_srcrec(a));
+  s->launch_count++;
+  return PFDTD_OK;
+}
+
+// Halo exchange of field index `b` for every interface this process touches, enqueued on the edge
+// streams (CudaMesh::switchHalos, cudaMesh.h:432-463: slab_i[last-1] -> slab_{i+1}[0],
+// slab_{i+1}[1] -> slab_i[last]).  Local interfaces: peer copies.  Process boundaries: NCCL send/recv.
+static int enqueue_halo_local_up(pfdtd_solver* s, size_t k, int b) {   // copies issued by partition k towards k+1 ... and k+1 -> k
+  Partition& lo = s->parts[k];
+  Partition& hi = s->parts[k + 1];
+  const size_t plane = (size_t)s->X * s->Y * esize(s);
+  char* src1 = (char*)lo.P[b] + (size_t)(lo.size - 2) * plane;
+  char* dst1 = (char*)hi.P[b];
+  PF_CUDA(cudaSetDevice(lo.device));
+  PF_CUDA(cudaMemcpyPeerAsync(dst1, hi.device, src1, lo.device, plane, lo.s_edge));
+  return PFDTD_OK;
+}
+static int enqueue_halo_local_down(pfdtd_solver* s, size_t k, int b) {  // partition k+1's plane 1 -> partition k's last plane
+  Partition& lo = s->parts[k];
+  Partition& hi = s->parts[k + 1];
+  const size_t plane = (size_t)s->X * s->Y * esize(s);
+  char* src2 = (char*)hi.P[b] + plane;
+  char* dst2 = (char*)lo.P[b] + (size_t)(lo.size - 1) * plane;
+  PF_CUDA(cudaSetDevice(hi.device));
+  PF_CUDA(cudaMemcpyPeerAsync(dst2, lo.device, src2, hi.device, plane, hi.s_edge));
+  return PFDTD_OK;
+}
+static int enqueue_halo_external(pfdtd_solver* s, int b) {
+  if (!s->comm) return PFDTD_OK;
+  const size_t plane = (size_t)s->X * s->Y * esize(s);
+  const bool lo_ext = has_lower_ext(s), hi_ext = has_upper_ext(s);
+  if (!lo_ext && !hi_ext) return PFDTD_OK;
+  Partition& pb = s->parts.front();
+  Partition& pt = s->parts.back();
+  // bottom and top partitions may differ; each side's traffic goes on its own edge stream
+  if (lo_ext) {
+    PF_CUDA(cudaSetDevice(pb.device));
+    PF_NCCL(g_nccl.GroupStart());
+    PF_NCCL(g_nccl.Send((char*)pb.P[b] + plane, plane, 1 /*ncclUint8*/, s->rank - 1, s->comm, pb.s_edge));
+    PF_NCCL(g_nccl.Recv((char*)pb.P[b], plane, 1, s->rank - 1, s->comm, pb.s_edge));
+    if (hi_ext && &pb == &pt) {
+      PF_NCCL(g_nccl.Send((char*)pt.P[b] + (size_t)(pt.size - 2) * plane, plane, 1, s->rank + 1, s->comm, pt.s_edge));
+      PF_NCCL(g_nccl.Recv((char*)pt.P[b] + (size_t)(pt.size - 1) * plane, plane, 1, s->rank + 1, s->comm, pt.s_edge));
+    }
+    PF_NCCL(g_nccl.GroupEnd());
+  }
+  if (hi_ext && !(lo_ext && &pb == &pt)) {
+    PF_CUDA(cudaSetDevice(pt.device));
+    PF_NCCL(g_nccl.GroupStart());
+    PF_NCCL(g_nccl.Send((char*)pt.P[b] + (size_t)(pt.size - 2) * plane, plane, 1, s->rank + 1, s->comm, pt.s_edge));
+    PF_NCCL(g_nccl.Recv((char*)pt.P[b] + (size_t)(pt.size - 1) * plane, plane, 1, s->rank + 1, s->comm, pt.s_edge));
+    PF_NCCL(g_nccl.GroupEnd());
+  }
+  return PFDTD_OK;
+}
+
+// One time step for all partitions: source(n) -> update -> flip -> halo, receiver(n) is recorded by the
+// next step's srcrec launch (or the final flush).  Edge planes are computed first on the edge stream,
+// their halo transfer overlaps the interior update on the main stream.
+static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
+  const size_t np = s->parts.size();
+  const int c = s->cur;
+  const bool single = (np == 1 && !s->comm);
+  if (single) {
+    Partition& p = s->parts[0];
+    PF_CUDA(cudaSetDevice(p.device));
+    PF_TRY(launch_srcrec_for(s, p, p.s_main, 1, 1, 1));
+    PF_TRY(launch_update(s, p, 1, (int)p.size - 1, p.cfg_full, p.s_main, timed));
+    s->cur = 1 - c;
+    return PFDTD_OK;
+  }
+  // phase 1: sources/receivers + edge planes on the edge stream
+  for (size_t k = 0; k < np; k++) {
+    Partition& p = s->parts[k];
+    PF_CUDA(cudaSetDevice(p.device));
+    // wait for last step's interior of this partition and the neighbours' edge work (halo arrival + WAR)
+    PF_CUDA(cudaStreamWaitEvent(p.s_edge, p.ev_int, 0));
+    if (k > 0) PF_CUDA(cudaStreamWaitEvent(p.s_edge, s->parts[k - 1].ev_edge, 0));
+    if (k + 1 < np) PF_CUDA(cudaStreamWaitEvent(p.s_edge, s->parts[k + 1].ev_edge, 0));
+    PF_TRY(launch_srcrec_for(s, p, p.s_edge, 1, 1, 1));
+    PF_CUDA(cudaEventRecord(p.ev_src, p.s_edge));
+  }
+  for (size_t k = 0; k < np; k++) {
+    Partition& p = s->parts[k];
+    PF_CUDA(cudaSetDevice(p.device));
+    const bool lo_nb = (k > 0) || has_lower_ext(s);
+    const bool hi_nb = (k + 1 < np) || has_upper_ext(s);
+    const int zb = 1, ze = (int)p.size - 1;   // updated planes [zb, ze)
+    int ib = zb, ie = ze;
+    const bool split = s->opt_overlap && (ze - zb) >= 4;
+    if (split) {
+      if (lo_nb) { PF_TRY(launch_update(s, p, zb, zb + 1, p.cfg_edge, p.s_edge, timed)); ib = zb + 1; }
+      if (hi_nb) { PF_TRY(launch_update(s, p, ze - 1, ze, p.cfg_edge, p.s_edge, timed)); ie = ze - 1; }
+      // interior on the main stream, concurrently with the halo traffic below
+      PF_CUDA(cudaStreamWaitEvent(p.s_main, p.ev_src, 0));
+      PF_TRY(launch_update(s, p, ib, ie, p.cfg_int, p.s_main, timed));
+      PF_CUDA(cudaEventRecord(p.ev_int, p.s_main));
+    } else {
+      PF_TRY(launch_update(s, p, zb, ze, p.cfg_full, p.s_edge, timed));
+      PF_CUDA(cudaEventRecord(p.ev_int, p.s_edge));
+    }
+  }
+  // phase 2: halo traffic of the new field (index 1-c) on the edge streams
+  if (time_halo && s->ev_h0) { PF_CUDA(cudaSetDevice(s->parts[0].device)); PF_CUDA(cudaEventRecord(s->ev_h0, s->parts[0].s_edge)); }
+  for (size_t k = 0; k + 1 < np; k++) {
+    PF_TRY(enqueue_halo_local_up(s, k, 1 - c));
+    PF_TRY(enqueue_halo_local_down(s, k, 1 - c));
+  }
+  PF_TRY(enqueue_halo_external(s, 1 - c));
+  if (time_halo && s->ev_h1) { PF_CUDA(cudaSetDevice(s->parts[0].device)); PF_CUDA(cudaEventRecord(s->ev_h1, s->parts[0].s_edge)); }
+  for (size_t k = 0; k < np; k++) {
+    Partition& p = s->parts[k];
+    PF_CUDA(cudaSetDevice(p.device));
+    PF_CUDA(cudaEventRecord(p.ev_edge, p.s_edge));
+  }
+  s->cur = 1 - c;
+  return PFDTD_OK;
+}
+
+static int set_step_counters(pfdtd_solver* s, int step, int first_recordable) {
+  int h[2] = {step, first_recordable};
+  for (auto& p : s->parts) {
+    PF_CUDA(cudaSetDevice(p.device));
+    cudaStream_t st = (s->parts.size() == 1 && !s->comm) ? p.s_main : p.s_edge;
+    PF_CUDA(cudaMemcpyAsync(p.d_step, h, sizeof(h), cudaMemcpyHostToDevice, st));
+  }
+  return PFDTD_OK;
+}
+
+static int sync_all(pfdtd_solver* s) {
+  for (auto& p : s->parts) {
+    PF_CUDA(cudaSetDevice(p.device));
+    PF_CUDA(cudaStreamSynchronize(p.s_edge));
+    PF_CUDA(cudaStreamSynchronize(p.s_main));
+  }
+  return PFDTD_OK;
+}
+
+static int elem_of(pfdtd_solver* s, uint32_t x, uint32_t y, int64_t zl, size_t k, int64_t* e) {
+  PF_CHECK(x < s->X && y < s->Y, PFDTD_ERR_RANGE, "coordinate (%u,%u) outside mesh %ux%u", x, y, s->X, s->Y);
+  *e = (zl - s->parts[k].first) * (int64_t)s->X * s->Y + (int64_t)y * s->X + x;
+  return PFDTD_OK;
+}
+
+}  // namespace pfdtd
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+const char* pfdtd_last_error(void) { return g_last_error.c_str(); }
+const char* pfdtd_version(void) { return "pfdtd-b200 0.1 (sm_100a)"; }
+
+int pfdtd_device_count(int* out_count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    *out_count = 0;
+    return PFDTD_ERR_NO_DEVICE;
+  }
+  *out_count = n;
+  return PFDTD_OK;
+}
+
+int pfdtd_device_mem_mb(int device, int* out_total_mb, int* out_free_mb) {
+  PF_CUDA(cudaSetDevice(device));
+  size_t f = 0, t = 0;
+  PF_CUDA(cudaMemGetInfo(&f, &t));
+  if (out_total_mb) *out_total_mb = (int)(t >> 20);
+  if (out_free_mb) *out_free_mb = (int)(f >> 20);
+  return PFDTD_OK;
+}
+
+int pfdtd_create(pfdtd_solver** out) {
+  PF_CHECK(out != nullptr, PFDTD_ERR_INVALID, "null out pointer");
+  *out = new pfdtd_solver();
+  return PFDTD_OK;
+}
+
+int pfdtd_destroy(pfdtd_solver* s) {
+  if (!s) return PFDTD_OK;
+  free_partitions(s);
+  if (s->d_pos0) { cudaSetDevice(s->stage_device); cudaFree(s->d_pos0); cudaFree(s->d_mat0); }
+  if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+  if (s->ev_h0) cudaEventDestroy(s->ev_h0);
+  if (s->ev_h1) cudaEventDestroy(s->ev_h1);
+  delete s;
+  return PFDTD_OK;
+}
+
+static int64_t* option_slot(pfdtd_solver* s, int option) {
+  switch (option) {
+    case PFDTD_OPT_MATIDX_AS_WRITTEN: return &s->opt_matidx_as_written;
+    case PFDTD_OPT_SOFT_ACCUMULATE: return &s->opt_soft_accumulate;
+    case PFDTD_OPT_KERNEL: return &s->opt_kernel;
+    case PFDTD_OPT_GLOBAL_Z_FIRST: return &s->opt_global_z_first;
+    case PFDTD_OPT_GLOBAL_Z_DIM: return &s->opt_global_z_dim;
+    case PFDTD_OPT_DOUBLE_PAD_AS_WRITTEN: return &s->opt_double_pad;
+    case PFDTD_OPT_USE_GRAPH: return &s->opt_use_graph;
+    case PFDTD_OPT_OVERLAP: return &s->opt_overlap;
+    case PFDTD_OPT_TMA_CHUNK: return &s->opt_tma_chunk;
+    case PFDTD_OPT_TMA_TILE: return &s->opt_tma_tile;
+    case PFDTD_OPT_TIME_KERNELS: return &s->opt_time_kernels;
+  }
+  return nullptr;
+}
+
+int pfdtd_set_option(pfdtd_solver* s, int option, int64_t value) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  int64_t* slot = option_slot(s, option);
+  PF_CHECK(slot, PFDTD_ERR_INVALID, "unknown option %d", option);
+  *slot = value;
+  if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+  return PFDTD_OK;
+}
+
+int pfdtd_get_option(pfdtd_solver* s, int option, int64_t* value) {
+  PF_CHECK(s && value, PFDTD_ERR_INVALID, "null argument");
+  int64_t* slot = option_slot(s, option);
+  PF_CHECK(slot, PFDTD_ERR_INVALID, "unknown option %d", option);
+  *value = *slot;
+  return PFDTD_OK;
+}
+
+int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t* d_mat, uint32_t vx, uint32_t vy, uint32_t vz,
+                            uint32_t block_x, uint32_t block_y, uint32_t block_z, uint32_t element_type, int dtype,
+                            const void* params, const void* material_coefs, uint32_t n_unique_materials) {
+  PF_CHECK(s && d_bid && d_mat && params && material_coefs, PFDTD_ERR_INVALID, "null argument");
+  PF_CHECK(dtype == PFDTD_F32 || dtype == PFDTD_F64, PFDTD_ERR_INVALID, "bad dtype %d", dtype);
+  PF_CHECK(vx && vy && vz && block_x && block_y && block_z, PFDTD_ERR_INVALID, "zero dimension");
+  PF_CHECK(n_unique_materials >= 1, PFDTD_ERR_INVALID, "at least one material is required");
+  PF_CHECK(element_type <= PFDTD_SRL, PFDTD_ERR_INVALID,
+           "update type %u: the interpolated IISO/IWB schemes are not available in this build", element_type);
+  free_partitions(s);
+  PF_CUDA(cudaSetDevice(device));
+  if (s->d_pos0) { cudaFree(s->d_pos0); cudaFree(s->d_mat0); s->d_pos0 = s->d_mat0 = nullptr; }
+  s->dtype = dtype;
+  s->element_type = (int)element_type;
+  // scheme choice as in setupMesh: types 0,1,(3) -> Bilbao/forward, else Kowalczyk/centred (cudaMesh.cu:70-73,134-137)
+  s->scheme = (element_type == 0 || element_type == 1) ? SCH_FORWARD : SCH_CENTRED;
+  s->bx = block_x; s->by = block_y; s->bz = block_z;
+  // padWithZeros (cudaMesh.cu:253-304); setupMeshDouble pads y with block.x (cudaMesh.cu:106-111) when asked to
+  uint32_t pby = (dtype == PFDTD_F64 && s->opt_double_pad) ? block_x : block_y;
+  auto padded = [](uint32_t d, uint32_t b) { return d % b ? d + (b - d % b) : d; };
+  const uint32_t nx = padded(vx, block_x), ny = padded(vy, pby), nz = padded(vz, block_z);
+  const uint64_t n_new = (uint64_t)nx * ny * nz;
+  uint8_t *np = nullptr, *nm = nullptr;
+  unsigned long long* d_counts = nullptr;
+  PF_CUDA(cudaMalloc(&np, n_new));
+  PF_CUDA(cudaMalloc(&nm, n_new));
+  PF_CUDA(cudaMalloc(&d_counts, 2 * sizeof(unsigned long long)));
+  PF_CUDA(cudaMemset(d_counts, 0, 2 * sizeof(unsigned long long)));
+  const int skip_z0 = (s->opt_global_z_first == 0);   // only the global z=0 plane is dropped by the reference's copy
+  PF_TRY(launch_pad_with_zeros(d_bid, np, vx, vy, vz, nx, ny, nz, skip_z0, 0));
+  PF_TRY(launch_pad_with_zeros(d_mat, nm, vx, vy, vz, nx, ny, nz, skip_z0, 0));
+  PF_TRY(launch_translate_nodes(np, nm, n_new, s->scheme == SCH_CENTRED, d_counts, 0));
+  s->launch_count += 3;
+  unsigned long long h_counts[2] = {0, 0};
+  PF_CUDA(cudaMemcpy(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost));
+  PF_CUDA(cudaFree(d_counts));
+  PF_CUDA(cudaFree(d_bid));   // adopted, like the reference (cudaMesh.cu:290-291)
+  PF_CUDA(cudaFree(d_mat));
+  s->d_pos0 = np; s->d_mat0 = nm;
+  s->stage_device = device;
+  s->X = nx; s->Y = ny; s->Z = nz;
+  s->n_air = h_counts[0]; s->n_boundary = h_counts[1];
+  if (dtype == PFDTD_F32) for (int i = 0; i < 4; i++) s->params[i] = (double)((const float*)params)[i];
+  else for (int i = 0; i < 4; i++) s->params[i] = ((const double*)params)[i];
+  s->n_unique = n_unique_materials;
+  s->materials_host.assign((const unsigned char*)material_coefs,
+                           (const unsigned char*)material_coefs + (size_t)n_unique_materials * 20 * esize(s));
+  s->mesh_ready = true;
+  s->cur = 0;
+  s->past_direction = 1;
+  s->srcrec_dirty = true;
+  return PFDTD_OK;
+}
+
+int pfdtd_setup_mesh(pfdtd_solver* s, const uint8_t* h_bid, const uint8_t* h_mat, uint32_t vx, uint32_t vy, uint32_t vz,
+                     uint32_t block_x, uint32_t block_y, uint32_t block_z, uint32_t element_type, int dtype, const void* params,
+                     const void* material_coefs, uint32_t n_unique_materials) {
+  PF_CHECK(s && h_bid && h_mat, PFDTD_ERR_INVALID, "null argument");
+  int ndev = 0;
+  PF_TRY(pfdtd_device_count(&ndev));
+  PF_CHECK(ndev > 0, PFDTD_ERR_NO_DEVICE, "no CUDA device: libpfdtd_b200 has no CPU fallback");
+  int device = 0;
+  PF_CUDA(cudaGetDevice(&device));
+  const size_t n = (size_t)vx * vy * vz;
+  uint8_t *db = nullptr, *dm = nullptr;
+  PF_CUDA(cudaMalloc(&db, n));
+  PF_CUDA(cudaMalloc(&dm, n));
+  PF_CUDA(cudaMemcpy(db, h_bid, n, cudaMemcpyHostToDevice));
+  PF_CUDA(cudaMemcpy(dm, h_mat, n, cudaMemcpyHostToDevice));
+  return pfdtd_setup_mesh_device(s, device, db, dm, vx, vy, vz, block_x, block_y, block_z, element_type, dtype, params,
+                                 material_coefs, n_unique_materials);
+}
+
+int pfdtd_partition_indexing(uint32_t dim_z, uint32_t n_partitions, uint32_t* first_slice, uint32_t* n_slices) {
+  PF_CHECK(n_partitions >= 1 && first_slice && n_slices, PFDTD_ERR_INVALID, "bad argument");
+  std::vector<int64_t> f, sz;
+  partition_indexing(dim_z, n_partitions, f, sz);
+  for (uint32_t i = 0; i < n_partitions; i++) { first_slice[i] = (uint32_t)f[i]; n_slices[i] = (uint32_t)sz[i]; }
+  return PFDTD_OK;
+}
+
+int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t* device_list) {
+  PF_CHECK(s && s->mesh_ready, PFDTD_ERR_INVALID, "setup_mesh must be called before make_partition");
+  PF_CHECK(n_partitions >= 1, PFDTD_ERR_INVALID, "need at least one partition");
+  PF_CHECK(s->Z / n_partitions >= 1, PFDTD_ERR_INVALID, "more partitions (%u) than slices (%u)", n_partitions, s->Z);
+  free_partitions(s);
+  int ndev = 0;
+  PF_TRY(pfdtd_device_count(&ndev));
+  std::vector<int64_t> first, size;
+  partition_indexing(s->Z, n_partitions, first, size);
+  const size_t XY = (size_t)s->X * s->Y;
+  const size_t es = esize(s);
+  s->parts.resize(n_partitions);
+  for (uint32_t k = 0; k < n_partitions; k++) {
+    Partition& p = s->parts[k];
+    p.device = device_list ? (int)device_list[k] : (int)k;
+    PF_CHECK(p.device < ndev, PFDTD_ERR_INVALID, "partition %u wants device %d but only %d devices exist", k, p.device, ndev);
+    p.first = first[k];
+    p.size = size[k];
+  }
+  // peer access between devices that share an interface (NVLink P2P; the reference never enables it)
+  for (uint32_t k = 0; k + 1 < n_partitions; k++) {
+    int a = s->parts[k].device, b = s->parts[k + 1].device;
+    if (a == b) continue;
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, a, b);
+    if (can) {
+      cudaSetDevice(a); cudaError_t e = cudaDeviceEnablePeerAccess(b, 0); if (e != cudaSuccess) cudaGetLastError();
+      cudaSetDevice(b); e = cudaDeviceEnablePeerAccess(a, 0); if (e != cudaSuccess) cudaGetLastError();
+    }
+  }
+  for (uint32_t k = 0; k < n_partitions; k++) {
+    Partition& p = s->parts[k];
+    PF_CUDA(cudaSetDevice(p.device));
+    const size_t nelem = (size_t)p.size * XY;
+    if (n_partitions == 1 && p.device == s->stage_device) {
+      p.pos = s->d_pos0; p.mat = s->d_mat0; p.owns_nodes = true;   // adopt (cudaMesh.h:697-700)
+      s->d_pos0 = s->d_mat0 = nullptr;
+    } else {
+      PF_CUDA(cudaMalloc(&p.pos, nelem));
+      PF_CUDA(cudaMalloc(&p.mat, nelem));
+      PF_CUDA(cudaMemcpyPeer(p.pos, p.device, s->d_pos0 + (size_t)p.first * XY, s->stage_device, nelem));
+      PF_CUDA(cudaMemcpyPeer(p.mat, p.device, s->d_mat0 + (size_t)p.first * XY, s->stage_device, nelem));
+    }
+    for (int b = 0; b < 2; b++) {
+      PF_CUDA(cudaMalloc(&p.P[b], nelem * es));
+      PF_CUDA(cudaMemset(p.P[b], 0, nelem * es));
+    }
+    PF_CUDA(cudaMalloc(&p.materials, s->materials_host.size()));
+    PF_CUDA(cudaMemcpy(p.materials, s->materials_host.data(), s->materials_host.size(), cudaMemcpyHostToDevice));
+    PF_CUDA(cudaMalloc(&p.d_step, 2 * sizeof(int)));
+    PF_CUDA(cudaMemset(p.d_step, 0, 2 * sizeof(int)));
+    int lo_pri = 0, hi_pri = 0;
+    PF_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    PF_CUDA(cudaStreamCreateWithPriority(&p.s_main, cudaStreamNonBlocking, lo_pri));
+    PF_CUDA(cudaStreamCreateWithPriority(&p.s_edge, cudaStreamNonBlocking, hi_pri));
+    for (cudaEvent_t* e : {&p.ev_src, &p.ev_int, &p.ev_edge}) PF_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    PF_CUDA(cudaEventCreate(&p.ev_t0));
+    PF_CUDA(cudaEventCreate(&p.ev_t1));
+    // prime the cross-stream events so the first step's waits are satisfied
+    PF_CUDA(cudaEventRecord(p.ev_int, p.s_main));
+    PF_CUDA(cudaEventRecord(p.ev_edge, p.s_edge));
+    // kernel choice
+    const int nplanes = (int)p.size - 2;
+    p.use_tma = (s->opt_kernel != KERNEL_PLAIN) && tma_supported((int)s->X, (int)s->Y, s->dtype) && nplanes >= 1;
+    PF_CHECK(!(s->opt_kernel == KERNEL_TMA && !p.use_tma), PFDTD_ERR_INVALID,
+             "TMA kernel requested but mesh %ux%u (slab of %lld slices) is not supported by it", s->X, s->Y, (long long)p.size);
+    if (p.use_tma) {
+      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->X, (int)s->Y, nplanes, p.device, s->opt_tma_tile, s->opt_tma_chunk,
+                             &p.cfg_full));
+      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->X, (int)s->Y, std::max(1, nplanes - 2), p.device,
+                             p.cfg_full.tile + 1, s->opt_tma_chunk, &p.cfg_int));
+      p.cfg_edge = TmaConfig{p.cfg_full.tile, 1};
+      for (int c = 0; c < 2; c++)
+        PF_TRY(tma_encode_maps(&p.maps[c], s->dtype, p.cfg_full.tile, p.P[c], p.P[1 - c], p.pos, (int)s->X, (int)s->Y, (int)p.size));
+    }
+  }
+  if (s->d_pos0) {   // free the staging volumes (cudaMesh.h:704-707)
+    PF_CUDA(cudaSetDevice(s->stage_device));
+    PF_CUDA(cudaFree(s->d_pos0));
+    PF_CUDA(cudaFree(s->d_mat0));
+    s->d_pos0 = s->d_mat0 = nullptr;
+  }
+  s->mesh_ready = false;   // staging consumed; setup_mesh again before re-partitioning
+  s->cur = 0;
+  s->srcrec_dirty = true;
+  return PFDTD_OK;
+}
+
+int pfdtd_get_dims(pfdtd_solver* s, uint32_t* dim_x, uint32_t* dim_y, uint32_t* dim_z) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  if (dim_x) *dim_x = s->X;
+  if (dim_y) *dim_y = s->Y;
+  if (dim_z) *dim_z = s->Z;
+  return PFDTD_OK;
+}
+
+int pfdtd_get_counts(pfdtd_solver* s, uint64_t* n_elements, uint64_t* n_air, uint64_t* n_boundary) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  if (n_elements) *n_elements = (uint64_t)s->X * s->Y * s->Z;
+  if (n_air) *n_air = s->n_air;
+  if (n_boundary) *n_boundary = s->n_boundary;
+  return PFDTD_OK;
+}
+
+int pfdtd_get_num_partitions(pfdtd_solver* s, uint32_t* n) {
+  PF_CHECK(s && n, PFDTD_ERR_INVALID, "null argument");
+  *n = (uint32_t)s->parts.size();
+  return PFDTD_OK;
+}
+
+int pfdtd_get_partition(pfdtd_solver* s, uint32_t k, uint32_t* first_slice, uint32_t* n_slices, uint32_t* device) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  PF_CHECK(k < s->parts.size(), PFDTD_ERR_RANGE, "partition %u out of range (%zu)", k, s->parts.size());
+  if (first_slice) *first_slice = (uint32_t)s->parts[k].first;
+  if (n_slices) *n_slices = (uint32_t)s->parts[k].size;
+  if (device) *device = (uint32_t)s->parts[k].device;
+  return PFDTD_OK;
+}
+
+int pfdtd_get_element_idx_and_partition(pfdtd_solver* s, uint32_t x, uint32_t y, uint32_t z, int* partition, int64_t* element) {
+  PF_CHECK(s && partition && element, PFDTD_ERR_INVALID, "null argument");
+  *partition = -1;
+  *element = -1;
+  for (size_t k = 0; k < s->parts.size(); k++) {
+    const Partition& p = s->parts[k];
+    if ((int64_t)z > p.first + p.size - 1) continue;
+    if ((int64_t)z < p.first) break;
+    *element = ((int64_t)z - p.first) * (int64_t)s->X * s->Y + (int64_t)y * s->X + x;
+    *partition = (int)k;
+    break;
+  }
+  return PFDTD_OK;
+}
+
+int pfdtd_export_partition_nodes(pfdtd_solver* s, uint32_t k, uint8_t* h_pos, uint8_t* h_mat) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  PF_CHECK(k < s->parts.size(), PFDTD_ERR_RANGE, "partition %u out of range", k);
+  Partition& p = s->parts[k];
+  PF_CUDA(cudaSetDevice(p.device));
+  const size_t n = (size_t)p.size * s->X * s->Y;
+  if (h_pos) PF_CUDA(cudaMemcpy(h_pos, p.pos, n, cudaMemcpyDeviceToHost));
+  if (h_mat) PF_CUDA(cudaMemcpy(h_mat, p.mat, n, cudaMemcpyDeviceToHost));
+  return PFDTD_OK;
+}
+
+int pfdtd_export_partition_pressure(pfdtd_solver* s, uint32_t k, int which, void* h_out) {
+  PF_CHECK(s && h_out, PFDTD_ERR_INVALID, "null argument");
+  PF_CHECK(k < s->parts.size(), PFDTD_ERR_RANGE, "partition %u out of range", k);
+  PF_TRY(sync_all(s));
+  Partition& p = s->parts[k];
+  PF_CUDA(cudaSetDevice(p.device));
+  const size_t n = (size_t)p.size * s->X * s->Y * esize(s);
+  PF_CUDA(cudaMemcpy(h_out, p.P[which ? 1 - s->cur : s->cur], n, cudaMemcpyDeviceToHost));
+  return PFDTD_OK;
+}
+
+// ---- single samples --------------------------------------------------------------------------------------
+static int write_sample(pfdtd_solver* s, size_t k, int64_t e, double value, bool add) {
+  Partition& p = s->parts[k];
+  PF_CUDA(cudaSetDevice(p.device));
+  char* dst = (char*)p.P[s->cur] + (size_t)e * esize(s);
+  if (s->dtype == PFDTD_F32) {
+    float v = (float)value;
+    if (add && s->opt_soft_accumulate) { float c = 0; PF_CUDA(cudaMemcpy(&c, dst, 4, cudaMemcpyDeviceToHost)); v += c; }
+    PF_CUDA(cudaMemcpy(dst, &v, 4, cudaMemcpyHostToDevice));
+  } else {
+    double v = value;
+    if (add && s->opt_soft_accumulate) { double c = 0; PF_CUDA(cudaMemcpy(&c, dst, 8, cudaMemcpyDeviceToHost)); v += c; }
+    PF_CUDA(cudaMemcpy(dst, &v, 8, cudaMemcpyHostToDevice));
+  }
+  return PFDTD_OK;
+}
+
+static int set_or_add(pfdtd_solver* s, uint32_t x, uint32_t y, uint32_t z, double value, bool add) {
+  PF_CHECK(s && !s->parts.empty(), PFDTD_ERR_INVALID, "no partitions");
+  PF_TRY(sync_all(s));
+  // every partition containing the slice (cudaMesh.h:321-338 / 349-369)
+  for (size_t k = 0; k < s->parts.size(); k++) {
+    const Partition& p = s->parts[k];
+    if ((int64_t)z > p.first + p.size - 1) continue;
+    if ((int64_t)z < p.first) break;
+    int64_t e;
+    PF_TRY(elem_of(s, x, y, z, k, &e));
+    PF_TRY(write_sample(s, k, e, value, add));
+  }
+  return PFDTD_OK;
+}
+
+int pfdtd_set_sample(pfdtd_solver* s, uint32_t x, uint32_t y, uint32_t z, double value) { return set_or_add(s, x, y, z, value, false); }
+int pfdtd_add_sample(pfdtd_solver* s, uint32_t x, uint32_t y, uint32_t z, double value) { return set_or_add(s, x, y, z, value, true); }
+
+static int read_sample(pfdtd_solver* s, size_t k, int64_t e, double* value) {
+  Partition& p = s->parts[k];
+  PF_CUDA(cudaSetDevice(p.device));
+  const char* src = (const char*)p.P[s->cur] + (size_t)e * esize(s);
+  if (s->dtype == PFDTD_F32) { float v = 0; PF_CUDA(cudaMemcpy(&v, src, 4, cudaMemcpyDeviceToHost)); *value = v; }
+  else { PF_CUDA(cudaMemcpy(value, src, 8, cudaMemcpyDeviceToHost)); }
+  return PFDTD_OK;
+}
+
+int pfdtd_get_sample(pfdtd_solver* s, uint32_t x, uint32_t y, uint32_t z, double* value) {
+  PF_CHECK(s && value && !s->parts.empty(), PFDTD_ERR_INVALID, "bad argument");
+  PF_TRY(sync_all(s));
+  *value = 0.0;
+  int k = -1;
+  int64_t e = -1;
+  PF_TRY(pfdtd_get_element_idx_and_partition(s, x, y, z, &k, &e));
+  if (k < 0) return PFDTD_OK;   // the reference returns 0 for a slice nobody holds (cudaMesh.h:387-404)
+  PF_CHECK(x < s->X && y < s->Y, PFDTD_ERR_RANGE, "coordinate outside mesh");
+  return read_sample(s, (size_t)k, e, value);
+}
+
+int pfdtd_set_sample_at(pfdtd_solver* s, uint32_t x, uint32_t y, uint32_t local_z, uint32_t partition, double value) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  PF_CHECK(partition < s->parts.size(), PFDTD_ERR_RANGE, "partition %u out of range", partition);
+  PF_CHECK(x < s->X && y < s->Y && (int64_t)local_z < s->parts[partition].size, PFDTD_ERR_RANGE, "coordinate outside partition");
+  PF_TRY(sync_all(s));
+  return write_sample(s, partition, (int64_t)local_z * s->X * s->Y + (int64_t)y * s->X + x, value, false);
+}
+
+int pfdtd_get_sample_at(pfdtd_solver* s, uint32_t x, uint32_t y, uint32_t local_z, uint32_t partition, double* value) {
+  PF_CHECK(s && value, PFDTD_ERR_INVALID, "null argument");
+  PF_CHECK(partition < s->parts.size(), PFDTD_ERR_RANGE, "partition %u out of range", partition);
+  PF_CHECK(x < s->X && y < s->Y && (int64_t)local_z < s->parts[partition].size, PFDTD_ERR_RANGE, "coordinate outside partition");
+  PF_TRY(sync_all(s));
+  return read_sample(s, partition, (int64_t)local_z * s->X * s->Y + (int64_t)y * s->X + x, value);
+}
+
+int pfdtd_switch_halos(pfdtd_solver* s) {
+  PF_CHECK(s && !s->parts.empty(), PFDTD_ERR_INVALID, "no partitions");
+  PF_TRY(sync_all(s));
+  for (size_t k = 0; k + 1 < s->parts.size(); k++) {
+    PF_TRY(enqueue_halo_local_up(s, k, s->cur));
+    PF_TRY(enqueue_halo_local_down(s, k, s->cur));
+  }
+  PF_TRY(enqueue_halo_external(s, s->cur));
+  return sync_all(s);
+}
+
+int pfdtd_flip_pressure_pointers(pfdtd_solver* s) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  s->cur = 1 - s->cur;
+  return PFDTD_OK;
+}
+
+int pfdtd_reset_pressures(pfdtd_solver* s) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  PF_TRY(sync_all(s));
+  for (auto& p : s->parts) {
+    PF_CUDA(cudaSetDevice(p.device));
+    const size_t n = (size_t)p.size * s->X * s->Y * esize(s);
+    PF_CUDA(cudaMemset(p.P[0], 0, n));
+    PF_CUDA(cudaMemset(p.P[1], 0, n));
+  }
+  return PFDTD_OK;
+}
+
+// ---- sources / receivers ----------------------------------------------------------------------------------
+int pfdtd_set_sources(pfdtd_solver* s, uint32_t n, const int32_t* xyz, const int32_t* src_types, const void* samples,
+                      uint32_t n_steps) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  PF_CHECK(n == 0 || (xyz && src_types && samples), PFDTD_ERR_INVALID, "null source arrays");
+  for (uint32_t i = 0; i < n; i++)
+    PF_CHECK(xyz[3 * i] >= 0 && xyz[3 * i + 1] >= 0 && xyz[3 * i + 2] >= 0 &&
+                 (s->X == 0 || ((uint32_t)xyz[3 * i] < s->X && (uint32_t)xyz[3 * i + 1] < s->Y)),
+             PFDTD_ERR_RANGE, "source %u at (%d,%d,%d) is outside the mesh", i, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  s->n_src = n;
+  s->src_steps = n_steps;
+  s->src_xyz.assign(xyz, xyz + 3 * (size_t)n);
+  s->src_type.assign(src_types, src_types + n);
+  s->src_samples.assign((const unsigned char*)samples, (const unsigned char*)samples + (size_t)n * n_steps * esize(s));
+  s->srcrec_dirty = true;
+  return PFDTD_OK;
+}
+
+int pfdtd_set_receivers(pfdtd_solver* s, uint32_t n, const int32_t* xyz) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  PF_CHECK(n == 0 || xyz, PFDTD_ERR_INVALID, "null receiver array");
+  for (uint32_t i = 0; i < n; i++)
+    PF_CHECK(xyz[3 * i] >= 0 && xyz[3 * i + 1] >= 0 && xyz[3 * i + 2] >= 0 &&
+                 (s->X == 0 || ((uint32_t)xyz[3 * i] < s->X && (uint32_t)xyz[3 * i + 1] < s->Y)),
+             PFDTD_ERR_RANGE, "receiver %u at (%d,%d,%d) is outside the mesh", i, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  s->n_rec = n;
+  s->rec_xyz.assign(xyz, xyz + 3 * (size_t)n);
+  s->srcrec_dirty = true;
+  return PFDTD_OK;
+}
+
+int pfdtd_reserve_steps(pfdtd_solver* s, uint32_t n_steps) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  if (n_steps > s->rec_cap) { s->rec_cap = n_steps; s->srcrec_dirty = true; }
+  return PFDTD_OK;
+}
+
+// ---- stepping ----------------------------------------------------------------------------------------------
+int pfdtd_enqueue_steps(pfdtd_solver* s, uint32_t first_step, uint32_t n_steps) {
+  PF_CHECK(s && !s->parts.empty(), PFDTD_ERR_INVALID, "make_partition must be called before stepping");
+  if (first_step + n_steps > s->rec_cap) PF_TRY(pfdtd_reserve_steps(s, first_step + n_steps));
+  PF_TRY(prepare_srcrec(s));
+  const bool single = (s->parts.size() == 1 && !s->comm);
+  const bool timed = s->opt_time_kernels != 0;
+  for (auto& p : s->parts) {
+    for (cudaEvent_t e : p.kev) cudaEventDestroy(e);
+    p.kev.clear();
+  }
+  if (s->comm && !s->ev_h0) {
+    PF_CUDA(cudaSetDevice(s->parts[0].device));
+    PF_CUDA(cudaEventCreate(&s->ev_h0));
+    PF_CUDA(cudaEventCreate(&s->ev_h1));
+  }
+  PF_TRY(set_step_counters(s, (int)first_step, (int)first_step));
+  for (auto& p : s->parts) {
+    PF_CUDA(cudaSetDevice(p.device));
+    cudaStream_t lead = single ? p.s_main : p.s_edge;
+    PF_CUDA(cudaEventRecord(p.ev_t0, lead));
+  }
+  uint32_t done = 0;
+  // CUDA-graph replay of two-step blocks (single partition, untimed): the launch-bound regime of small meshes
+  if (single && s->opt_use_graph && !timed && n_steps >= 8) {
+    Partition& p = s->parts[0];
+    PF_CUDA(cudaSetDevice(p.device));
+    if (s->cur != 0) { PF_TRY(enqueue_one_step(s, false, false)); done++; }
+    if (!s->graph_exec) {
+      cudaGraph_t g = nullptr;
+      PF_CUDA(cudaStreamBeginCapture(p.s_main, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue_one_step(s, false, false);
+      if (rc == PFDTD_OK) rc = enqueue_one_step(s, false, false);
+      cudaError_t ce = cudaStreamEndCapture(p.s_main, &g);
+      s->launch_count -= 4;   // capture recorded, nothing ran
+      if (rc != PFDTD_OK) { if (g) cudaGraphDestroy(g); return rc; }
+      PF_CUDA(ce);
+      PF_CUDA(cudaGraphInstantiate(&s->graph_exec, g, 0));
+      PF_CUDA(cudaGraphDestroy(g));
+    }
+    while (n_steps - done >= 2) {
+      PF_CUDA(cudaGraphLaunch(s->graph_exec, p.s_main));
+      s->launch_count += 4;
+      done += 2;
+    }
+  }
+  for (; done < n_steps; done++) PF_TRY(enqueue_one_step(s, timed, s->comm != nullptr && done + 1 == n_steps));
+  // flush: record the receivers of the last step
+  for (auto& p : s->parts) {
+    PF_CUDA(cudaSetDevice(p.device));
+    if (single) {
+      PF_TRY(launch_srcrec_for(s, p, p.s_main, 1, 0, 0));
+      PF_CUDA(cudaEventRecord(p.ev_t1, p.s_main));
+    } else {
+      // the last step's interior, and the neighbours' halo copies into this partition's end planes
+      PF_CUDA(cudaStreamWaitEvent(p.s_edge, p.ev_int, 0));
+      const size_t k = (size_t)(&p - &s->parts[0]);
+      if (k > 0) PF_CUDA(cudaStreamWaitEvent(p.s_edge, s->parts[k - 1].ev_edge, 0));
+      if (k + 1 < s->parts.size()) PF_CUDA(cudaStreamWaitEvent(p.s_edge, s->parts[k + 1].ev_edge, 0));
+      PF_TRY(launch_srcrec_for(s, p, p.s_edge, 1, 0, 0));
+      PF_CUDA(cudaEventRecord(p.ev_t1, p.s_edge));
+    }
+  }
+  return PFDTD_OK;
+}
+
+int pfdtd_sync(pfdtd_solver* s) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  PF_TRY(sync_all(s));
+  float total = 0, kern = 0;
+  uint32_t nk = 0;
+  for (auto& p : s->parts) {
+    PF_CUDA(cudaSetDevice(p.device));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.ev_t0, p.ev_t1) == cudaSuccess) total = std::max(total, ms);
+    else cudaGetLastError();
+    float ksum = 0;
+    for (size_t i = 0; i + 1 < p.kev.size(); i += 2) {
+      float k = 0;
+      if (cudaEventElapsedTime(&k, p.kev[i], p.kev[i + 1]) == cudaSuccess) { ksum += k; nk++; }
+      else cudaGetLastError();
+    }
+    kern = std::max(kern, ksum);
+  }
+  s->last_total_ms = total;
+  s->last_kernel_ms = kern;
+  s->last_kernel_launches = nk;
+  if (s->ev_h0) {
+    float h = 0;
+    cudaSetDevice(s->parts[0].device);
+    if (cudaEventElapsedTime(&h, s->ev_h0, s->ev_h1) == cudaSuccess) s->last_halo_ms = h;
+    else cudaGetLastError();
+  }
+  return PFDTD_OK;
+}
+
+int pfdtd_last_timing(pfdtd_solver* s, float* total_ms, float* update_kernel_ms, uint32_t* n_update_launches) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  if (total_ms) *total_ms = s->last_total_ms;
+  if (update_kernel_ms) *update_kernel_ms = s->last_kernel_ms;
+  if (n_update_launches) *n_update_launches = s->last_kernel_launches;
+  return PFDTD_OK;
+}
+
+int pfdtd_last_halo_ms(pfdtd_solver* s, float* halo_ms) {
+  PF_CHECK(s && halo_ms, PFDTD_ERR_INVALID, "null argument");
+  *halo_ms = s->last_halo_ms;
+  return PFDTD_OK;
+}
+
+int pfdtd_fetch_responses(pfdtd_solver* s, void* h_response, uint32_t n_steps) {
+  PF_CHECK(s && (h_response || s->n_rec == 0), PFDTD_ERR_INVALID, "null response buffer");
+  PF_CHECK(n_steps <= s->rec_cap || s->n_rec == 0, PFDTD_ERR_RANGE, "asked for %u steps but only %u were reserved", n_steps,
+           s->rec_cap);
+  PF_TRY(sync_all(s));
+  const size_t es = esize(s);
+  if (s->n_rec) memset(h_response, 0, (size_t)s->n_rec * n_steps * es);
+  for (auto& p : s->parts) {
+    if (!p.d_rec_out) continue;
+    PF_CUDA(cudaSetDevice(p.device));
+    for (int32_t slot : p.rec_slots)
+      PF_CUDA(cudaMemcpy((char*)h_response + (size_t)slot * n_steps * es, (char*)p.d_rec_out + (size_t)slot * s->rec_cap * es,
+                         (size_t)n_steps * es, cudaMemcpyDeviceToHost));
+  }
+  return PFDTD_OK;
+}
+
+int pfdtd_run(pfdtd_solver* s, uint32_t n_steps, void* h_response, pfdtd_interrupt_cb interrupt, pfdtd_progress_cb progress,
+              float* seconds_per_step) {
+  PF_CHECK(s && !s->parts.empty(), PFDTD_ERR_INVALID, "make_partition must be called before run");
+  auto t0 = std::chrono::steady_clock::now();
+  PF_TRY(pfdtd_reserve_steps(s, n_steps));
+  // steps are enqueued in blocks of PROGRESS_MOD (kernels3d.h:36) so the callbacks keep their cadence
+  // without a device synchronisation per step
+  const uint32_t block = 100;
+  uint32_t done = 0;
+  bool interrupted = false;
+  auto tb = t0;
+  while (done < n_steps) {
+    if (interrupt && interrupt()) { interrupted = true; break; }
+    uint32_t nb = std::min(block, n_steps - done);
+    PF_TRY(pfdtd_enqueue_steps(s, done, nb));
+    if (progress) {
+      PF_TRY(sync_all(s));
+      auto tn = std::chrono::steady_clock::now();
+      progress((int)done, (int)n_steps, (float)(std::chrono::duration<double>(tn - tb).count() / nb));
+      tb = tn;
+    }
+    done += nb;
+  }
+  PF_TRY(pfdtd_sync(s));
+  if (h_response && s->n_rec) PF_TRY(pfdtd_fetch_responses(s, h_response, n_steps));
+  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (seconds_per_step) *seconds_per_step = (float)(secs / std::max(1u, done));
+  if (interrupted) { set_error("interrupted at step %u", done); return PFDTD_ERR_INTERRUPTED; }
+  return PFDTD_OK;
+}
+
+int pfdtd_step(pfdtd_solver* s, uint32_t step, int direction, void* h_response, uint32_t n_steps_total) {
+  PF_CHECK(s && !s->parts.empty(), PFDTD_ERR_INVALID, "make_partition must be called before step");
+  PF_TRY(prepare_srcrec(s));
+  PF_TRY(sync_all(s));
+  PF_TRY(set_step_counters(s, (int)step, 0x7fffffff));
+  const bool single = (s->parts.size() == 1 && !s->comm);
+  for (auto& p : s->parts) {
+    PF_CUDA(cudaSetDevice(p.device));
+    cudaStream_t st = single ? p.s_main : p.s_edge;
+    PF_TRY(launch_srcrec_for(s, p, st, 0, 1, 0));
+    PF_TRY(launch_update(s, p, 1, (int)p.size - 1, p.cfg_full, st, false));
+  }
+  PF_TRY(sync_all(s));
+  // time-reversal rule of launchFDTD3dStep (kernels3d.cu:462-465)
+  if (s->past_direction == direction) s->cur = 1 - s->cur;
+  s->past_direction = direction;
+  PF_TRY(pfdtd_switch_halos(s));
+  if (h_response) {
+    for (uint32_t r = 0; r < s->n_rec; r++) {
+      double v = 0;
+      int64_t z = (int64_t)s->rec_xyz[3 * r + 2] - s->opt_global_z_first;
+      if (z >= 0) PF_TRY(pfdtd_get_sample(s, (uint32_t)s->rec_xyz[3 * r], (uint32_t)s->rec_xyz[3 * r + 1], (uint32_t)z, &v));
+      if (s->dtype == PFDTD_F32) ((float*)h_response)[(size_t)r * n_steps_total + step] = (float)v;
+      else ((double*)h_response)[(size_t)r * n_steps_total + step] = v;
+    }
+  }
+  return PFDTD_OK;
+}
+
+// ---- multi-process ------------------------------------------------------------------------------------------
+int pfdtd_comm_unique_id(uint8_t* out_id128) {
+  PF_CHECK(out_id128, PFDTD_ERR_INVALID, "null argument");
+  PF_TRY(nccl_load());
+  NcclId id;
+  memset(&id, 0, sizeof(id));
+  PF_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(out_id128, id.bytes, 128);
+  return PFDTD_OK;
+}
+
+int pfdtd_comm_init(pfdtd_solver* s, const uint8_t* id128, int rank, int nranks) {
+  PF_CHECK(s && id128, PFDTD_ERR_INVALID, "null argument");
+  PF_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, PFDTD_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+  PF_CHECK(!s->parts.empty(), PFDTD_ERR_INVALID, "make_partition must be called before comm_init");
+  PF_TRY(nccl_load());
+  NcclId id;
+  memcpy(id.bytes, id128, 128);
+  PF_CUDA(cudaSetDevice(s->parts[0].device));
+  void* comm = nullptr;
+  PF_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+  s->comm = comm;
+  s->rank = rank;
+  s->nranks = nranks;
+  s->srcrec_dirty = true;
+  if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+  return PFDTD_OK;
+}
+
+// ---- introspection --------------------------------------------------------------------------------------------
+int pfdtd_kernel_name(pfdtd_solver* s, char* buf, size_t buflen) {
+  PF_CHECK(s && buf && buflen > 0, PFDTD_ERR_INVALID, "bad argument");
+  if (s->parts.empty()) { snprintf(buf, buflen, "none"); return PFDTD_OK; }
+  const Partition& p = s->parts[0];
+  if (p.use_tma)
+    snprintf(buf, buflen, "fdtd_update_tma<%s,%s> tile %s chunk %d", s->dtype == PFDTD_F32 ? "f32" : "f64",
+             s->scheme == SCH_CENTRED ? "centred" : "forward", tma_tile_name(s->dtype, p.cfg_full.tile), p.cfg_full.chunk);
+  else
+    snprintf(buf, buflen, "fdtd_update_plain<%s,%s>", s->dtype == PFDTD_F32 ? "f32" : "f64",
+             s->scheme == SCH_CENTRED ? "centred" : "forward");
+  return PFDTD_OK;
+}
+
+int pfdtd_launch_count(pfdtd_solver* s, uint64_t* n) {
+  PF_CHECK(s && n, PFDTD_ERR_INVALID, "null argument");
+  *n = s->launch_count;
+  return PFDTD_OK;
+}
+
+}  // extern "C"

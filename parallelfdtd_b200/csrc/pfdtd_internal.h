@@ -1,0 +1,97 @@
+// pfdtd_internal.h -- internal declarations shared by the translation units of libpfdtd_b200.so
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "../../include/pfdtd.h"
+
+namespace pfdtd {
+
+void set_error(const char* fmt, ...);
+
+// equation families: the reference's SRL_FORWARD and SHARED share the forward-difference boundary
+// (kernels3d.cu:485-606), SRL uses the centred-difference boundary (:608-665)
+enum : int { SCH_FORWARD = 0, SCH_CENTRED = 2 };
+
+#define PF_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      pfdtd::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return PFDTD_ERR_CUDA;                                                                   \
+    }                                                                                          \
+  } while (0)
+
+#define PF_CHECK(cond, code, ...)          \
+  do {                                     \
+    if (!(cond)) {                         \
+      pfdtd::set_error(__VA_ARGS__);       \
+      return (code);                       \
+    }                                      \
+  } while (0)
+
+#define PF_TRY(expr)              \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != PFDTD_OK) return rc__; \
+  } while (0)
+
+// ---- mesh preparation kernels (mesh_kernels.cu) ------------------------------------------------
+// padWithZeros + toBilbao/toKowalczyk + calcBoundaries of the reference, on `stream`.
+int launch_pad_with_zeros(const uint8_t* d_old, uint8_t* d_new, uint32_t dx, uint32_t dy, uint32_t dz,
+                          uint32_t nx, uint32_t ny, uint32_t nz, int skip_z0, cudaStream_t stream);
+int launch_translate_nodes(uint8_t* d_pos, uint8_t* d_mat, uint64_t n, int centred, unsigned long long* d_counts2,
+                           cudaStream_t stream);
+
+// ---- update kernels (update_kernels.cu) ---------------------------------------------------------
+struct TmaMaps {           // tensor maps of one partition for one (cur,new) buffer assignment
+  CUtensorMap p_halo;      // P (current field), box with x/y halo
+  CUtensorMap p_old;       // field that is overwritten (past -> next), box without halo
+  CUtensorMap pos;         // node byte, box without halo
+};
+
+struct UpdateArgs {
+  int dtype;               // PFDTD_F32 / PFDTD_F64
+  int scheme;              // 0 forward equations, 2 centred equations
+  const uint8_t* pos;
+  const uint8_t* mat;
+  const void* P;           // current field (slab base)
+  void* Pn;                // past field, overwritten with the next field
+  const void* materials;   // device [n_coefs]
+  uint32_t n_coefs;
+  double params[4];        // lambda, lambda^2, 1/3, octave  (already rounded to the dtype)
+  int matidx_as_written;
+  int X, Y;
+  int z_begin, z_end;      // local planes [z_begin, z_end) are updated
+  void* peer_lo;           // optional: base of the neighbour slab plane that receives plane z_begin (or null)
+  void* peer_hi;           // optional: ... receives plane z_end-1
+  cudaStream_t stream;
+};
+
+enum { KERNEL_AUTO = 0, KERNEL_TMA = 1, KERNEL_PLAIN = 2 };
+
+struct TmaConfig { int tile; int chunk; };
+
+bool tma_supported(int X, int Y, int dtype);
+int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void* Pold, const uint8_t* pos, int X, int Y, int nz);
+int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk, TmaConfig* out);
+int launch_update_tma(const UpdateArgs& a, const TmaMaps& maps, const TmaConfig& cfg);
+int launch_update_plain(const UpdateArgs& a);
+const char* tma_tile_name(int dtype, int tile);
+
+// ---- source / receiver kernel (srcrec_kernels.cu) -------------------------------------------------
+struct SrcRecArgs {
+  int dtype;
+  void* P;                       // current field of the partition
+  int n_rec; const int64_t* rec_elem; const int32_t* rec_slot; void* rec_out; int64_t rec_stride;
+  int n_src; const int64_t* src_elem; const int32_t* src_type; const int32_t* src_slot; const void* src_samples; int64_t src_stride;
+  int* d_step;                   // device step counter n: record slot n-1 (if n>0 && do_record), inject sample n (if do_inject)
+  int do_record, do_inject, soft_accumulate, advance;
+  cudaStream_t stream;
+};
+int launch_srcrec(const SrcRecArgs& a);
+
+}  // namespace pfdtd

@@ -1,0 +1,460 @@
+// update_kernels.cu -- the leapfrog pressure update (the hot path).
+//
+// Replaces fdtd3dStdMaterials / fdtd3dSliced / fdtd3dStdKowalczykMaterials
+// (reference src/kernels/kernels3d.cu:485-665).  Two implementations of the same arithmetic
+// (update_math.cuh):
+//
+//  * fdtd_update_tma  -- the product kernel.  Each CTA owns a 128 x TY xy-tile and marches a chunk of
+//    z-planes.  A producer warp streams, per plane, three TMA boxes into a ring of shared-memory
+//    stages (mbarrier full/empty pipeline): the current field with a one-voxel xy halo, the field
+//    being overwritten, and the node byte.  Consumer warps keep z-1 / z / z+1 of their four
+//    x-adjacent voxels in registers, take y-neighbours from the shared tile, x-neighbours by warp
+//    shuffle (halo column from the tile), and write the result with one 128-bit store per four
+//    voxels.  The boundary term (admittance / direction flags from the node byte, material byte
+//    fetched for boundary nodes only) is evaluated in the same pass.  HBM traffic per voxel update:
+//    read P 4(8) B once, read P_old 4(8) B, write 4(8) B, node byte 1 B = 13 B fp32 / 25 B fp64.
+//
+//  * fdtd_update_plain -- one thread per voxel, neighbour reads through L1/L2; used for dimensions the
+//    TMA path does not cover and as an on-device cross-check.
+#include "pfdtd_internal.h"
+#include "update_math.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+namespace pfdtd {
+
+// =====================================================================================================
+// plain kernel
+// =====================================================================================================
+template <typename T, int SCHEME>
+__global__ void __launch_bounds__(128) fdtd_update_plain(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ mat,
+                                                         const T* __restrict__ P, T* __restrict__ Pn, UpdConst<T> c, int X,
+                                                         int Y, int z_begin) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int z = z_begin + blockIdx.z;
+  if (x >= X || y >= Y) return;
+  const int64_t XY = (int64_t)X * Y;
+  const int64_t cur = (int64_t)z * XY + (int64_t)y * X + x;
+  const uint32_t ps = pos[cur];
+  // neighbour indexing identical to the reference: linear offsets, rows/slices wrap (kernels3d.cu:516-523)
+  T zp = P[cur + XY], zm = P[cur - XY], yp = P[cur + X], ym = P[cur - X], xp = P[cur + 1], xm = P[cur - 1];
+  T p = P[cur], p_old = Pn[cur];
+  Pn[cur] = voxel_update<T, SCHEME>(ps, mat + cur, p, zp, zm, yp, ym, xp, xm, p_old, c);
+}
+
+template <typename T>
+static UpdConst<T> make_const(const UpdateArgs& a) {
+  UpdConst<T> c;
+  c.lam = (T)a.params[0];
+  c.lam2 = (T)a.params[1];
+  c.octave = (T)a.params[3];
+  // computed on the host with the same single-rounding fma the device would use
+  if (a.scheme == SCH_CENTRED) c.a_air = (T)std::fma((T)a.params[1], (T)-6, (T)2);
+  else c.a_air = (T)std::fma((T)6, -(T)a.params[1], (T)2);
+  c.materials = (const T*)a.materials;
+  c.n_coefs = a.n_coefs;
+  c.matidx_as_written = a.matidx_as_written;
+  return c;
+}
+
+template <typename T, int SCHEME>
+static int launch_plain_t(const UpdateArgs& a) {
+  dim3 block(32, 4, 1);
+  dim3 grid((a.X + 31) / 32, (a.Y + 3) / 4, a.z_end - a.z_begin);
+  fdtd_update_plain<T, SCHEME><<<grid, block, 0, a.stream>>>(a.pos, a.mat, (const T*)a.P, (T*)a.Pn, make_const<T>(a), a.X,
+                                                             a.Y, a.z_begin);
+  PF_CUDA(cudaGetLastError());
+  return PFDTD_OK;
+}
+
+int launch_update_plain(const UpdateArgs& a) {
+  if (a.z_end <= a.z_begin) return PFDTD_OK;
+  if (a.dtype == PFDTD_F32) return a.scheme == SCH_CENTRED ? launch_plain_t<float, SCH_CENTRED>(a) : launch_plain_t<float, SCH_FORWARD>(a);
+  return a.scheme == SCH_CENTRED ? launch_plain_t<double, SCH_CENTRED>(a) : launch_plain_t<double, SCH_FORWARD>(a);
+}
+
+// =====================================================================================================
+// TMA z-march kernel
+// =====================================================================================================
+namespace {
+
+constexpr int TX = 128;  // voxels per tile row: 32 lanes x 4 voxels
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <typename T> struct V4 { T v[4]; };
+
+__device__ __forceinline__ void lds4(const float* p, V4<float>& o) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  o.v[0] = t.x; o.v[1] = t.y; o.v[2] = t.z; o.v[3] = t.w;
+}
+__device__ __forceinline__ void lds4(const double* p, V4<double>& o) {
+  double2 a = *reinterpret_cast<const double2*>(p);
+  double2 b = *reinterpret_cast<const double2*>(p + 2);
+  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = b.x; o.v[3] = b.y;
+}
+__device__ __forceinline__ void stg4(float* p, const V4<float>& o) {
+  *reinterpret_cast<float4*>(p) = make_float4(o.v[0], o.v[1], o.v[2], o.v[3]);
+}
+__device__ __forceinline__ void stg4(double* p, const V4<double>& o) {
+  *reinterpret_cast<double2*>(p) = make_double2(o.v[0], o.v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(o.v[2], o.v[3]);
+}
+
+constexpr int align128(int x) { return (x + 127) & ~127; }
+
+template <typename T, int TY>
+struct TileGeom {
+  static constexpr int HX = 16 / (int)sizeof(T);           // x halo columns each side (16 B keeps rows 16-B aligned)
+  static constexpr int PW = TX + 2 * HX;                    // halo tile row pitch (elements)
+  static constexpr int PT_BYTES = (TY + 2) * PW * (int)sizeof(T);
+  static constexpr int PO_BYTES = TY * TX * (int)sizeof(T);
+  static constexpr int PS_BYTES = TY * TX;
+  static constexpr int PT_OFF = 0;
+  static constexpr int PO_OFF = align128(PT_BYTES);
+  static constexpr int PS_OFF = PO_OFF + align128(PO_BYTES);
+  static constexpr int STAGE_BYTES = PS_OFF + align128(PS_BYTES);
+};
+
+}  // namespace
+
+// grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: (TY/RPW + 1) warps (last warp = TMA producer)
+template <typename T, int SCHEME, int TY, int RPW, int NST>
+__global__ void __launch_bounds__((TY / RPW + 1) * 32)
+    fdtd_update_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
+                    const __grid_constant__ CUtensorMap tm_pos, const uint8_t* __restrict__ mat, T* __restrict__ Pn,
+                    UpdConst<T> c, int X, int Y, int z_begin, int z_end, int chunk) {
+  using G = TileGeom<T, TY>;
+  constexpr int NW = TY / RPW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[NST];
+  __shared__ __align__(8) uint64_t bar_empty[NST];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * TX;
+  const int y0 = blockIdx.y * TY;
+  const int z_lo = z_begin + blockIdx.z * chunk;
+  const int z_hi = min(z_lo + chunk, z_end);
+  const int n = z_hi - z_lo;              // planes this CTA computes
+  if (n <= 0) return;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; s++) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // ------------------------------- producer -------------------------------------------------
+    if (lane == 0) {
+      // load i brings P(z_lo-1+i) with halo and, from i >= 2, P_old / node byte of plane z_lo+i-2
+      for (int i = 0; i < n + 2; i++) {
+        const int slot = i % NST;
+        const uint32_t round = (uint32_t)(i / NST);
+        mbar_wait(&bar_empty[slot], (round & 1u) ^ 1u);
+        unsigned char* st = smem_raw + (size_t)slot * G::STAGE_BYTES;
+        const uint32_t bytes = (i >= 2) ? (uint32_t)(G::PT_BYTES + G::PO_BYTES + G::PS_BYTES) : (uint32_t)G::PT_BYTES;
+        mbar_expect_tx(&bar_full[slot], bytes);
+        tma_load_3d(st + G::PT_OFF, &tm_p, x0 - G::HX, y0 - 1, z_lo - 1 + i, &bar_full[slot]);
+        if (i >= 2) {
+          tma_load_3d(st + G::PO_OFF, &tm_old, x0, y0, z_lo + i - 2, &bar_full[slot]);
+          tma_load_3d(st + G::PS_OFF, &tm_pos, x0, y0, z_lo + i - 2, &bar_full[slot]);
+        }
+      }
+    }
+    return;
+  }
+
+  // --------------------------------- consumers ---------------------------------------------------
+  const int r0 = warp * RPW;                 // first tile row of this warp
+  const int xl = 4 * lane;                   // x offset inside the tile
+  const int gx = x0 + xl;
+  const bool x_ok = gx < X;                  // X is a multiple of 4 on this path
+  const int64_t XY = (int64_t)X * Y;
+
+  V4<T> down[RPW], cur[RPW], up[RPW];
+
+  // prologue: plane z_lo-1 (centre only), then plane z_lo (kept resident for its xy-neighbours)
+  {
+    mbar_wait(&bar_full[0], 0);
+    const T* pt = reinterpret_cast<const T*>(smem_raw + G::PT_OFF);
+#pragma unroll
+    for (int k = 0; k < RPW; k++) lds4(pt + (r0 + k + 1) * G::PW + G::HX + xl, down[k]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_empty[0]);
+    mbar_wait(&bar_full[1 % NST], (uint32_t)((1 / NST) & 1));
+    const T* pt1 = reinterpret_cast<const T*>(smem_raw + (size_t)(1 % NST) * G::STAGE_BYTES + G::PT_OFF);
+#pragma unroll
+    for (int k = 0; k < RPW; k++) lds4(pt1 + (r0 + k + 1) * G::PW + G::HX + xl, cur[k]);
+  }
+
+  for (int j = 0; j < n; j++) {
+    const int i2 = j + 2;
+    const int s2 = i2 % NST;
+    const int s1 = (j + 1) % NST;
+    mbar_wait(&bar_full[s2], (uint32_t)((i2 / NST) & 1));
+    const unsigned char* st2 = smem_raw + (size_t)s2 * G::STAGE_BYTES;
+    const T* pt2 = reinterpret_cast<const T*>(st2 + G::PT_OFF);
+    const T* po2 = reinterpret_cast<const T*>(st2 + G::PO_OFF);
+    const unsigned char* ps2 = st2 + G::PS_OFF;
+    const T* pt1 = reinterpret_cast<const T*>(smem_raw + (size_t)s1 * G::STAGE_BYTES + G::PT_OFF);
+    const int z = z_lo + j;
+
+    V4<T> old[RPW];
+    uint32_t pw[RPW];
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+      lds4(pt2 + (r0 + k + 1) * G::PW + G::HX + xl, up[k]);
+      lds4(po2 + (r0 + k) * TX + xl, old[k]);
+      pw[k] = *reinterpret_cast<const uint32_t*>(ps2 + (r0 + k) * TX + xl);
+    }
+    V4<T> ym0, yp1;   // y-1 of the warp's first row, y+1 of its last row: from the shared tile of plane z
+    lds4(pt1 + (r0) * G::PW + G::HX + xl, ym0);
+    lds4(pt1 + (r0 + RPW + 1) * G::PW + G::HX + xl, yp1);
+
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+      const V4<T>& cc = cur[k];
+      T xm_edge = __shfl_up_sync(0xffffffffu, cc.v[3], 1);
+      T xp_edge = __shfl_down_sync(0xffffffffu, cc.v[0], 1);
+      if (lane == 0) xm_edge = pt1[(r0 + k + 1) * G::PW + G::HX - 1];
+      if (lane == 31) xp_edge = pt1[(r0 + k + 1) * G::PW + G::HX + TX];
+      const int gy = y0 + r0 + k;
+      if (x_ok && gy < Y) {
+        const V4<T>& ym = (k == 0) ? ym0 : cur[k - 1 < 0 ? 0 : k - 1];
+        const V4<T>& yp = (k == RPW - 1) ? yp1 : cur[k + 1 >= RPW ? RPW - 1 : k + 1];
+        const int64_t e = (int64_t)z * XY + (int64_t)gy * X + gx;
+        V4<T> res;
+        const uint32_t air4 = (SCHEME == SCH_CENTRED) ? 0x80808080u : 0x86868686u;
+        if (pw[k] == air4) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            T xm = (q == 0) ? xm_edge : cc.v[q - 1 < 0 ? 0 : q - 1];
+            T xp = (q == 3) ? xp_edge : cc.v[q + 1 > 3 ? 3 : q + 1];
+            res.v[q] = voxel_update<T, SCHEME>(air4 & 0xffu, nullptr, cc.v[q], up[k].v[q], down[k].v[q], yp.v[q], ym.v[q],
+                                               xp, xm, old[k].v[q], c);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            T xm = (q == 0) ? xm_edge : cc.v[q - 1 < 0 ? 0 : q - 1];
+            T xp = (q == 3) ? xp_edge : cc.v[q + 1 > 3 ? 3 : q + 1];
+            res.v[q] = voxel_update<T, SCHEME>((pw[k] >> (8 * q)) & 0xffu, mat + e + q, cc.v[q], up[k].v[q], down[k].v[q],
+                                               yp.v[q], ym.v[q], xp, xm, old[k].v[q], c);
+          }
+        }
+        stg4(Pn + e, res);
+      }
+    }
+    // every read of stage s1 (plane z tile, plus P_old/node bytes of plane z-1 read last iteration) is done
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_empty[s1]);
+#pragma unroll
+    for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side of the TMA path
+// ------------------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+int encode3d(CUtensorMap* out, CUtensorMapDataType dt, int esize, const void* base, int X, int Y, int nz, int bx, int by) {
+  EncodeTiledFn fn = get_encode_fn();
+  PF_CHECK(fn != nullptr, PFDTD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)nz};
+  cuuint64_t strides[2] = {(cuuint64_t)X * esize, (cuuint64_t)X * Y * esize};
+  cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PF_CHECK(r == CUDA_SUCCESS, PFDTD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) X=%d Y=%d nz=%d box=%dx%d esize=%d", (int)r, X,
+           Y, nz, bx, by, esize);
+  return PFDTD_OK;
+}
+
+// tile variants: index -> (TY, RPW, NST)
+struct TileDef { int ty, rpw, nst; const char* name; };
+const TileDef kTiles[] = {
+    {8, 1, 4, "128x8 r1 s4"},
+    {16, 2, 4, "128x16 r2 s4"},
+    {16, 1, 4, "128x16 r1 s4"},
+    {8, 1, 6, "128x8 r1 s6"},
+    {16, 2, 3, "128x16 r2 s3"},
+    {32, 2, 3, "128x32 r2 s3"},
+};
+constexpr int kNumTiles = (int)(sizeof(kTiles) / sizeof(kTiles[0]));
+
+template <typename T, int TY>
+constexpr int stage_bytes() { return TileGeom<T, TY>::STAGE_BYTES; }
+
+template <typename T, int SCHEME, int TY, int RPW, int NST>
+int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupancy_out) {
+  auto kern = fdtd_update_tma<T, SCHEME, TY, RPW, NST>;
+  const int smem = NST * stage_bytes<T, TY>();
+  static bool attr_set[64] = {false};   // per device
+  int dev = 0;
+  PF_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[dev] = true;
+  }
+  const int threads = (TY / RPW + 1) * 32;
+  if (occupancy_out) {
+    PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy_out, kern, threads, smem));
+    return PFDTD_OK;
+  }
+  const int nplanes = a.z_end - a.z_begin;
+  dim3 grid((a.X + TX - 1) / TX, (a.Y + TY - 1) / TY, (nplanes + chunk - 1) / chunk);
+  kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.pos, a.mat, (T*)a.Pn, make_const<T>(a), a.X, a.Y, a.z_begin,
+                                          a.z_end, chunk);
+  PF_CUDA(cudaGetLastError());
+  return PFDTD_OK;
+}
+
+template <typename T, int SCHEME>
+int dispatch_tile(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
+  switch (tile) {
+    case 0: return launch_tma_t<T, SCHEME, 8, 1, 4>(a, m, chunk, occ);
+    case 1: return launch_tma_t<T, SCHEME, 16, 2, 4>(a, m, chunk, occ);
+    case 2: return launch_tma_t<T, SCHEME, 16, 1, 4>(a, m, chunk, occ);
+    case 3: return launch_tma_t<T, SCHEME, 8, 1, 6>(a, m, chunk, occ);
+    case 4: return launch_tma_t<T, SCHEME, 16, 2, 3>(a, m, chunk, occ);
+    case 5: return launch_tma_t<T, SCHEME, 32, 2, 3>(a, m, chunk, occ);
+  }
+  set_error("unknown TMA tile variant %d", tile);
+  return PFDTD_ERR_INVALID;
+}
+
+int dispatch(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
+  if (a.dtype == PFDTD_F32)
+    return a.scheme == SCH_CENTRED ? dispatch_tile<float, SCH_CENTRED>(a, m, tile, chunk, occ)
+                                   : dispatch_tile<float, SCH_FORWARD>(a, m, tile, chunk, occ);
+  return a.scheme == SCH_CENTRED ? dispatch_tile<double, SCH_CENTRED>(a, m, tile, chunk, occ)
+                                 : dispatch_tile<double, SCH_FORWARD>(a, m, tile, chunk, occ);
+}
+
+}  // namespace
+
+bool tma_supported(int X, int Y, int dtype) {
+  (void)dtype;
+  // rows must be 16-byte multiples for the tensor map strides and the 128-bit stores
+  return X % 16 == 0 && X >= 16 && Y >= 1 && get_encode_fn() != nullptr;
+}
+
+const char* tma_tile_name(int dtype, int tile) {
+  (void)dtype;
+  return (tile >= 0 && tile < kNumTiles) ? kTiles[tile].name : "?";
+}
+
+int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void* Pold, const uint8_t* pos, int X, int Y, int nz) {
+  PF_CHECK(tile >= 0 && tile < kNumTiles, PFDTD_ERR_INVALID, "bad tile variant %d", tile);
+  const int ty = kTiles[tile].ty;
+  const int esize = dtype == PFDTD_F32 ? 4 : 8;
+  const CUtensorMapDataType dt = dtype == PFDTD_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+  const int hx = 16 / esize;
+  PF_TRY(encode3d(&out->p_halo, dt, esize, P, X, Y, nz, TX + 2 * hx, ty + 2));
+  PF_TRY(encode3d(&out->p_old, dt, esize, Pold, X, Y, nz, TX, ty));
+  PF_TRY(encode3d(&out->pos, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pos, X, Y, nz, TX, ty));
+  return PFDTD_OK;
+}
+
+int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk,
+                    TmaConfig* out) {
+  int tile = (opt_tile > 0 && opt_tile <= kNumTiles) ? (int)opt_tile - 1 : (dtype == PFDTD_F32 ? 1 : 0);
+  if (Y <= 8 && kTiles[tile].ty > 8) tile = 0;
+  UpdateArgs probe{};
+  probe.dtype = dtype;
+  probe.scheme = scheme;
+  TmaMaps dummy{};
+  int occ = 0;
+  PF_TRY(dispatch(probe, dummy, tile, 1, &occ));
+  PF_CHECK(occ >= 1, PFDTD_ERR_CUDA, "TMA kernel variant %d does not fit on an SM", tile);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int64_t resident = (int64_t)occ * sms;
+  const int64_t tiles = (int64_t)((X + TX - 1) / TX) * ((Y + kTiles[tile].ty - 1) / kTiles[tile].ty);
+  int chunk = 0;
+  if (opt_chunk > 0) {
+    chunk = (int)opt_chunk;
+  } else {
+    // choose the number of z-chunks that best fills whole waves, charging 2 extra plane loads per chunk
+    double best = -1;
+    for (int gz = 1; gz <= nplanes; gz++) {
+      int ch = (nplanes + gz - 1) / gz;
+      if (ch < 8 && gz > 1) break;
+      int gz_eff = (nplanes + ch - 1) / ch;
+      int64_t total = tiles * gz_eff;
+      int64_t waves = (total + resident - 1) / resident;
+      double fill = (double)total / (double)(waves * resident);
+      double eff = fill * (double)ch / (double)(ch + 2);
+      if (eff > best + 1e-9) { best = eff; chunk = ch; }
+    }
+    if (chunk <= 0) chunk = nplanes;
+  }
+  out->tile = tile;
+  out->chunk = std::max(1, std::min(chunk, std::max(nplanes, 1)));
+  return PFDTD_OK;
+}
+
+int launch_update_tma(const UpdateArgs& a, const TmaMaps& maps, const TmaConfig& cfg) {
+  if (a.z_end <= a.z_begin) return PFDTD_OK;
+  return dispatch(a, maps, cfg.tile, cfg.chunk, nullptr);
+}
+
+}  // namespace pfdtd

@@ -1,0 +1,124 @@
+// update_math.cuh -- per-voxel update arithmetic shared by every update kernel.
+//
+// One device function per scheme, used by the plain kernel, the TMA z-march kernel, the edge
+// launches and the interior launches alike, so a voxel's result never depends on which kernel or
+// how many partitions computed it (reference invariant: tests/CudaMeshTest.cpp:508-518).
+//
+// The operation order and the FMA contraction reproduce what nvcc emits for the reference
+// kernels (src/kernels/kernels3d.cu:485-529 and :608-665) when built for sm_100 -- every op is an
+// explicit round-to-nearest intrinsic, so the compiler cannot re-associate or re-contract.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pfdtd {
+
+template <typename T> struct Ar;
+template <> struct Ar<float> {
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float rcp(float a) { return __frcp_rn(a); }   // == 1.f/a (IEEE)
+};
+template <> struct Ar<double> {
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double rcp(double a) { return __drcp_rn(a); }  // == 1.0/a (IEEE)
+};
+
+
+// Per-launch constants. params = [lambda, lambda^2, 1/3, octave] (SimulationParameters.cpp:379-396).
+template <typename T>
+struct UpdConst {
+  T lam;          // params[0]
+  T lam2;         // params[1]
+  T octave;       // params[3]
+  T a_air;        // forward:  fma(6, -lam2, 2)     centred: fma(lam2, -6, 2)
+  const T* materials;      // [n_unique][20] admittances on this device
+  uint32_t n_coefs;        // entries in `materials` (index is clamped; the reference would read out of bounds)
+  int matidx_as_written;   // forward kernel only, kernels3d.cu:513
+};
+
+template <typename T>
+__device__ __forceinline__ T load_coef(const UpdConst<T>& c, uint32_t idx) {
+  idx = idx < c.n_coefs ? idx : c.n_coefs - 1;
+  return __ldg(c.materials + idx);
+}
+
+// ---- SRL_FORWARD (kernels3d.cu:508-528) --------------------------------------------------------
+// S is summed as ((((z+ + z-) + y+) + y-) + x+) + x-.
+template <typename T>
+__device__ __forceinline__ T sum6_forward(T zp, T zm, T yp, T ym, T xp, T xm) {
+  T S = Ar<T>::add(zp, zm);
+  S = Ar<T>::add(S, yp);
+  S = Ar<T>::add(S, ym);
+  S = Ar<T>::add(S, xp);
+  S = Ar<T>::add(S, xm);
+  return S;
+}
+
+template <typename T>
+__device__ __forceinline__ T voxel_forward(uint32_t pos, const uint8_t* mat_ptr, T p, T S, T p_old, const UpdConst<T>& c) {
+  if (pos == 0x86u) {  // air: K=6, beta=0 -> identical bits to the general expression
+    T inner = Ar<T>::fma(S, c.lam2, Ar<T>::mul(p, c.a_air));
+    return Ar<T>::fma(p_old, (T)-1, inner);
+  }
+  T K = (T)(pos & 0x7Fu);
+  T sw = (T)(pos >> 7);
+  uint32_t m = (pos != 0u) ? (uint32_t)(*mat_ptr) : 0u;   // solid nodes always carry material 0 (cudaMesh.cu:332-336)
+  uint32_t idx = c.matidx_as_written ? (uint32_t)Ar<T>::mul((T)(m * 20u), c.octave)
+                                     : m * 20u + (uint32_t)c.octave;
+  T coef = load_coef(c, idx);
+  T t = Ar<T>::mul(Ar<T>::mul(coef, Ar<T>::add((T)6, -K)), c.lam);
+  T one_p_beta = Ar<T>::fma(t, (T)0.5, (T)1);
+  T one_m_beta = Ar<T>::fma(t, (T)-0.5, (T)1);
+  T a = Ar<T>::fma(K, -c.lam2, (T)2);
+  T inner = Ar<T>::fma(S, c.lam2, Ar<T>::mul(p, a));
+  inner = Ar<T>::fma(p_old, -one_m_beta, inner);
+  return Ar<T>::mul(Ar<T>::mul(sw, Ar<T>::rcp(one_p_beta)), inner);
+}
+
+// ---- SRL centred (kernels3d.cu:632-663) ----------------------------------------------------------
+// sum = (((((x- + x+) + y-) + y+) + z+) + z-) + S_boundary
+template <typename T>
+__device__ __forceinline__ T voxel_centred(uint32_t pos, const uint8_t* mat_ptr, T p, T zp, T zm, T yp, T ym, T xp, T xm,
+                                           T p_old, const UpdConst<T>& c) {
+  T S = Ar<T>::add(xm, xp);
+  S = Ar<T>::add(S, ym);
+  S = Ar<T>::add(S, yp);
+  S = Ar<T>::add(S, zp);
+  S = Ar<T>::add(S, zm);
+  T q = Ar<T>::mul(p, c.a_air);
+  if (pos == 0x80u) {  // air: no direction flags, beta = 0
+    S = Ar<T>::add(S, (T)0);
+    T inner = Ar<T>::fma(S, c.lam2, -q);
+    return Ar<T>::fma(p_old, (T)-1, inner);
+  }
+  T sw = (T)(pos >> 7);
+  T dir_x = (T)(pos & 1u), dir_y = (T)((pos >> 1) & 1u), dir_z = (T)((pos >> 2) & 1u);
+  T dsum = (T)((pos & 1u) + ((pos >> 1) & 1u) + ((pos >> 2) & 1u));
+  uint32_t m = (pos != 0u) ? (uint32_t)(*mat_ptr) : 0u;
+  uint32_t idx = (uint32_t)Ar<T>::add((T)(m * 20u), c.octave);
+  T cl = Ar<T>::mul(load_coef(c, idx), c.lam);
+  T one_p_beta = Ar<T>::fma(cl, dsum, (T)1);
+  T beta_m_one = Ar<T>::fma(cl, dsum, (T)-1);
+  T sx = (pos & 0x10u) ? xp : xm;   // p_x[sign_x], SIGN_X selects x+1
+  T sy = (pos & 0x20u) ? yp : ym;   // p_y[sign_y]
+  T sz = (pos & 0x40u) ? zm : zp;   // p_z[sign_z], SIGN_Z selects z-1 (kernels3d.cu:643-644)
+  // dir_* are 0/1: products exact, so only the grouping of the two adds matters
+  T Sb = Ar<T>::add(Ar<T>::add(Ar<T>::mul(sx, dir_x), Ar<T>::mul(sy, dir_y)), Ar<T>::mul(sz, dir_z));
+  S = Ar<T>::add(S, Sb);
+  T inner = Ar<T>::fma(S, c.lam2, -q);
+  inner = Ar<T>::fma(p_old, beta_m_one, inner);
+  return Ar<T>::mul(Ar<T>::mul(sw, inner), Ar<T>::rcp(one_p_beta));
+}
+
+template <typename T, int SCHEME>
+__device__ __forceinline__ T voxel_update(uint32_t pos, const uint8_t* mat_ptr, T p, T zp, T zm, T yp, T ym, T xp, T xm,
+                                          T p_old, const UpdConst<T>& c) {
+  if (SCHEME == SCH_CENTRED) return voxel_centred<T>(pos, mat_ptr, p, zp, zm, yp, ym, xp, xm, p_old, c);
+  return voxel_forward<T>(pos, mat_ptr, p, sum6_forward<T>(zp, zm, yp, ym, xp, xm), p_old, c);
+}
+
+}  // namespace pfdtd
