@@ -23,94 +23,28 @@ os.makedirs(os.path.join(OUT, "golden"), exist_ok=True)
 LAM = 1.0 / np.sqrt(3.0)
 
 
-def make_case(name, dims, update_type, double, steps, n_mat, n_parts, sources, receivers, geometry="shoebox", octave=0,
-              input_data=()):
-    if geometry == "shoebox":
-        bid, mat = synth.shoebox(dims, n_mat)
-    else:
-        bid, mat = synth.hall(dims, n_mat)
-    refl = [0.9] if n_mat == 1 else list(np.linspace(0.99, 0.5, n_mat))
-    tab = synth.material_table(refl) * (1 + 0.01 * np.arange(20, dtype=np.float32))[None, :]   # octave slots differ
-    return dict(name=name, bid=bid, mat=mat, block=(32, 4, 1), update_type=update_type, double=double, steps=steps,
-                octave=octave, n_parts=n_parts, devices=[0] * n_parts, materials=tab.astype(np.float32),
-                sources=sources, receivers=receivers, input_data=list(input_data))
-
-
-def source_table(case):
-    steps = case["steps"]
-    dt = np.float64 if case["double"] else np.float32
-    tab = np.zeros((len(case["sources"]), steps), dtype=dt)
-    for i, s in enumerate(case["sources"]):
-        data = case["input_data"][s[5]] if s[4] == 3 else None
-        tab[i] = oracle.source_samples(s[4], steps, 7000, data, case["double"])
-    return tab
-
-
-def run_oracle(case, n_parts=None, matidx=1):
-    pos, mat, air, bnd = oracle.setup_mesh(case["bid"], case["mat"], case["block"], case["update_type"], case["double"])
-    prm = oracle.params(LAM, case["octave"], case["double"])
-    src = np.asarray(case["sources"], dtype=np.int32).reshape(-1, 6)
-    scheme = 2 if case["update_type"] == 2 else 0
-    r, secs = oracle.run(pos, mat, scheme, prm, case["materials"], src[:, :3], src[:, 3], source_table(case),
-                         case["receivers"], case["steps"], n_parts or case["n_parts"], matidx)
-    return r, (pos, mat, air, bnd), secs
+from tests.fdtd_cases import (make_case, parity_cases, source_table, run_oracle, rel_l2, node_checksum)  # noqa: E402
+from tests import fdtd_cases as fc  # noqa: E402
 
 
 def run_ours(case, n_parts=None, kernel=capi.KERNEL_AUTO, matidx=1, opts=()):
-    s = capi.Solver()
-    s.set_option(capi.OPT_KERNEL, kernel)
-    s.set_option(capi.OPT_MATIDX_AS_WRITTEN, matidx)
-    for k, v in opts:
-        s.set_option(k, v)
-    dt = capi.F64 if case["double"] else capi.F32
-    prm = oracle.params(LAM, case["octave"], case["double"])
-    s.setup_mesh(case["bid"], case["mat"], case["block"], case["update_type"], dt, prm, case["materials"])
-    n = n_parts or case["n_parts"]
-    s.make_partition(n, [0] * n)
-    src = np.asarray(case["sources"], dtype=np.int32).reshape(-1, 6)
-    s.set_sources(src[:, :3], src[:, 3], source_table(case))
-    s.set_receivers(case["receivers"])
-    t0 = time.time()
-    r, sps = s.run(case["steps"])
-    wall = time.time() - t0
-    nodes = [s.export_partition_nodes(k) for k in range(n)]
-    info = dict(kernel=s.kernel_name(), wall=wall, counts=s.counts(), dims=s.dims(), launches=s.launch_count())
-    s.close()
-    return r, nodes, info
-
-
-def rel_l2(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
-    d = np.linalg.norm(b)
-    return float(np.linalg.norm(a - b) / d) if d > 0 else float(np.linalg.norm(a - b))
+    return fc.run_ours(capi, case, n_parts=n_parts, kernel=kernel, matidx=matidx, opts=opts)
 
 
 def main():
     results = []
     have_ref = casefile.ref_available()
     print("devices:", capi.device_count(), "ref:", have_ref, flush=True)
-    cases = [
-        make_case("c1_shoebox64_fwd_f32", (64, 64, 64), 0, False, 500, 1, 1, [(32, 32, 32, 0, 0, 0)], [(40, 36, 28)]),
-        make_case("shoebox64_fwd_f64", (64, 64, 64), 0, True, 300, 1, 1, [(32, 32, 32, 0, 0, 0)], [(40, 36, 28)]),
-        make_case("shoebox_48x40x49_ctr_f32_6mat_2parts", (48, 40, 49), 2, False, 300, 6, 2,
-                  [(10, 10, 3, 0, 0, 0), (10, 12, 23, 0, 1, 0), (11, 10, 40, 1, 3, 0)], [(20, 12, 5), (20, 12, 24), (20, 12, 42)],
-                  input_data=[np.sin(np.arange(64) * 0.3)]),
-        make_case("shoebox_48x40x49_ctr_f64_6mat_5parts", (48, 40, 49), 2, True, 300, 6, 5,
-                  [(10, 10, 3, 0, 0, 0), (10, 12, 23, 0, 1, 0), (11, 10, 40, 1, 3, 0)], [(20, 12, 5), (20, 12, 24), (20, 12, 42)],
-                  input_data=[np.sin(np.arange(64) * 0.3)]),
-        make_case("hall_96x128x64_fwd_f32_5mat_oct1", (96, 128, 64), 0, False, 200, 5, 1, [(40, 20, 20, 0, 0, 0)],
-                  [(50, 60, 30), (20, 100, 40)], geometry="hall", octave=1),
-        make_case("hall_96x128x64_ctr_f32_5mat", (96, 128, 64), 2, False, 200, 5, 2, [(40, 20, 20, 0, 0, 0)],
-                  [(50, 60, 30), (20, 100, 40)], geometry="hall"),
-    ]
+    cases = parity_cases()
     for case in cases:
         name = case["name"]
         t0 = time.time()
         r_or, (pos, mat, air, bnd), osecs = run_oracle(case)
         rec = dict(case=name, oracle_s=round(time.time() - t0, 2))
+        r_ref = None
         if have_ref:
-            ref = casefile.run_reference(case, os.path.join(OUT, "ref_" + name), dump_nodes=True)
+          try:
+            ref = casefile.run_reference(case, os.path.join("/tmp/pfdtd_ref", name), dump_nodes=True)
             r_ref = ref["responses"]
             rec["ref_vs_oracle_bitexact"] = bool(np.array_equal(r_ref, r_or))
             rec["ref_vs_oracle_rel_l2"] = rel_l2(r_or, r_ref)
@@ -124,8 +58,12 @@ def main():
             np.savez_compressed(os.path.join(OUT, "golden", name + ".npz"), responses=r_ref, dims=np.asarray(ref["dims"]),
                                 n_air=ref["n_air"], n_boundary=ref["n_boundary"],
                                 partitions=np.asarray(ref["partitions"]),
-                                pos_crc=np.asarray([int(np.sum(p[0].astype(np.uint64) * (1 + np.arange(p[0].size, dtype=np.uint64) % 251))) for p in ref["nodes"]], dtype=np.uint64),
-                                mat_crc=np.asarray([int(np.sum(p[1].astype(np.uint64) * (1 + np.arange(p[1].size, dtype=np.uint64) % 251))) for p in ref["nodes"]], dtype=np.uint64))
+                                pos_crc=np.asarray([node_checksum(p[0]) for p in ref["nodes"]], dtype=np.uint64),
+                                mat_crc=np.asarray([node_checksum(p[1]) for p in ref["nodes"]], dtype=np.uint64),
+                                **{f"pos_{k}": p[0] for k, p in enumerate(ref["nodes"])},
+                                **{f"mat_{k}": p[1] for k, p in enumerate(ref["nodes"])})
+          except Exception as e:  # noqa: BLE001
+            rec["ref_error"] = repr(e)
         for kname, kern in (("plain", capi.KERNEL_PLAIN), ("tma", capi.KERNEL_TMA)):
             try:
                 r, nodes, info = run_ours(case, kernel=kern)
@@ -137,7 +75,7 @@ def main():
                           for k in range(case["n_parts"]))
                 rec[kname + "_nodes_bitexact"] = bool(okn)
                 rec[kname + "_counts"] = list(info["counts"])
-                if have_ref:
+                if r_ref is not None:
                     rec[kname + "_vs_ref_bitexact"] = bool(np.array_equal(r, r_ref))
                 # partition invariance
                 inv = True
@@ -194,7 +132,7 @@ def main():
                     case = dict(bid=bid, mat=mat, block=(32, 4, 1), update_type=ut, double=dbl, steps=steps, octave=0, n_parts=1,
                                 devices=[0], materials=tab, sources=[(dims[0] // 2,) * 3 + (0, 0, 0)],
                                 receivers=[(dims[0] // 2 + 5, dims[0] // 2, dims[0] // 2)], input_data=[])
-                    ref = casefile.run_reference(case, os.path.join(OUT, "ref_bench"))
+                    ref = casefile.run_reference(case, "/tmp/pfdtd_ref/bench")
                     print(json.dumps(dict(bench=dims, ref=True, update_type=ut, double=dbl, wall=ref["wall_seconds"],
                                           mvox_s=dims[0] * dims[1] * dims[2] * steps / ref["wall_seconds"] / 1e6,
                                           stdout=ref["stdout"].strip())), flush=True)
