@@ -72,7 +72,10 @@ enum {
   PFDTD_OPT_TMA_TILE = 10,
   /* bracket every update-kernel launch of pfdtd_enqueue_steps with CUDA events so that
    * pfdtd_last_timing can report the kernels' own device time (disables graph replay) */
-  PFDTD_OPT_TIME_KERNELS = 11
+  PFDTD_OPT_TIME_KERNELS = 11,
+  /* L2 cache hints on the TMA loads: bit0 = evict_first for operands read once per step (P_old,
+   * node bytes), bit1 = evict_last for P (shared with neighbouring tiles).  Default 0. */
+  PFDTD_OPT_TMA_HINTS = 12
 };
 
 typedef int (*pfdtd_interrupt_cb)(void);                      /* kernels3d.h: bool (*)(void) */

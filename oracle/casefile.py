@@ -59,7 +59,7 @@ def read_result(path, with_nodes=False):
     with open(path, "rb") as f:
         assert f.read(8) == b"PFDTDOUT"
         X, Y, Z, n_parts, n_rec, steps, is_double, n_air, n_bnd = struct.unpack("<9I", f.read(36))
-        t_ret, wall = struct.unpack("<2d", f.read(16))
+        t_ret, wall, wall_e2e = struct.unpack("<3d", f.read(24))
         parts = [struct.unpack("<2I", f.read(8)) for _ in range(n_parts)]
         resp = np.frombuffer(f.read(8 * n_rec * steps), dtype=np.float64).reshape(n_rec, steps).copy()
         nodes = []
@@ -72,16 +72,16 @@ def read_result(path, with_nodes=False):
     if not is_double:
         resp = resp.astype(np.float32)
     return dict(dims=(X, Y, Z), n_parts=n_parts, steps=steps, double=bool(is_double), n_air=n_air, n_boundary=n_bnd,
-                time_per_step_returned=t_ret, wall_seconds=wall, partitions=parts, responses=resp, nodes=nodes)
+                time_per_step_returned=t_ret, wall_seconds=wall, wall_e2e_seconds=wall_e2e, partitions=parts, responses=resp, nodes=nodes)
 
 
-def run_reference(case, workdir, dump_nodes=False, timeout=600):
+def run_reference(case, workdir, dump_nodes=False, timeout=600, warmup_steps=0):
     """Run the reference's own CUDA hot path (needs a GPU). Returns read_result(...)."""
     os.makedirs(workdir, exist_ok=True)
     cp = os.path.join(workdir, "case.bin")
     op = os.path.join(workdir, "out.bin")
     write_case(cp, case)
-    r = subprocess.run([REF_BIN, cp, op, "1" if dump_nodes else "0"], cwd=workdir, capture_output=True, text=True, timeout=timeout)
+    r = subprocess.run([REF_BIN, cp, op, "1" if dump_nodes else "0", str(int(warmup_steps))], cwd=workdir, capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"ref_fdtd failed ({r.returncode}): {r.stdout}\n{r.stderr}")
     res = read_result(op, with_nodes=dump_nodes)

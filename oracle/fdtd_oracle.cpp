@@ -116,6 +116,30 @@ inline T update_centred(uint8_t pos, uint8_t mat, const T* P, int64_t cur, int64
   return (sw * inner) * rcp;
 }
 
+// One launch of the update kernel over a slab: local slices 1..nz-2 of `Q` (the past field) are
+// overwritten with the next field (kernels3d.cu:109-153: grid.z = slab slices - 2, pointers offset
+// by one slice).  pos/mat point at the slab's first slice.
+template <typename T>
+void update_slab(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int64_t nz, int scheme, const T* params,
+                 const T* materials, int matidx_mode, const T* P, T* Q) {
+  const int64_t XY = X * Y;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int64_t z = 1; z < nz - 1; z++) {
+    for (int64_t y = 0; y < Y; y++) {
+      const int64_t row = z * XY + y * X;
+      const uint8_t* prow = pos + row;
+      const uint8_t* mrow = mat + row;
+      if (scheme == 2) {
+        for (int64_t x = 0; x < X; x++)
+          Q[row + x] = update_centred<T>(prow[x], mrow[x], P, row + x, X, XY, Q[row + x], params, materials);
+      } else {
+        for (int64_t x = 0; x < X; x++)
+          Q[row + x] = update_forward<T>(prow[x], mrow[x], P, row + x, X, XY, Q[row + x], params, materials, matidx_mode);
+      }
+    }
+  }
+}
+
 // src/kernels/kernels3d.cu:31-203 / 205-374 : launchFDTD3d / launchFDTD3dDouble.
 // Emulates N partitions with halo slices exactly as CudaMesh holds them
 // (cudaMesh.h:648-751), setSample/addSample semantics (cudaMesh.h:321-369),
@@ -153,27 +177,9 @@ double run_sim(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int
       }
     }
     // (2) update local slices 1..size-2 of every slab (kernels3d.cu:109-153)
-    for (int k = 0; k < n_parts; k++) {
-      const T* P = cur[k];
-      T* Q = past[k];
-      const int64_t zoff = slabs[k].first;
-      const int64_t nz = slabs[k].size;
-#pragma omp parallel for collapse(2) schedule(static)
-      for (int64_t z = 1; z < nz - 1; z++) {
-        for (int64_t y = 0; y < Y; y++) {
-          const int64_t row = z * XY + y * X;
-          const uint8_t* prow = pos + (zoff + z) * XY + y * X;
-          const uint8_t* mrow = mat + (zoff + z) * XY + y * X;
-          if (scheme == 2) {
-            for (int64_t x = 0; x < X; x++)
-              Q[row + x] = update_centred<T>(prow[x], mrow[x], P, row + x, X, XY, Q[row + x], params, materials);
-          } else {
-            for (int64_t x = 0; x < X; x++)
-              Q[row + x] = update_forward<T>(prow[x], mrow[x], P, row + x, X, XY, Q[row + x], params, materials, matidx_mode);
-          }
-        }
-      }
-    }
+    for (int k = 0; k < n_parts; k++)
+      update_slab<T>(pos + slabs[k].first * XY, mat + slabs[k].first * XY, X, Y, slabs[k].size, scheme, params, materials,
+                     matidx_mode, cur[k], past[k]);
     // (3) flip (kernels3d.cu:160)
     for (int k = 0; k < n_parts; k++) std::swap(cur[k], past[k]);
     // (4) halos (kernels3d.cu:161, cudaMesh.h:432-463)
@@ -299,6 +305,18 @@ double pfo_run_f64(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y,
                    const int32_t* rec_xyz, int64_t steps, double* out, int timed_from_step) {
   return run_sim<double>(pos, mat, X, Y, Z, scheme, params, materials, matidx_mode, soft_mode, n_parts, n_src, src_xyz,
                          src_type, src_samples, n_rec, rec_xyz, steps, out, timed_from_step);
+}
+
+// One update launch on a single slab whose end planes are halos (multi-process emulation in
+// tests/test_slabs_gloo.py).  cur/past: [nz][Y][X] with X+1 elements of slack NOT required: the x=0 /
+// x=X-1 taps that wrap rows stay inside the slab because planes 0 and nz-1 are never updated.
+void pfo_step_slab_f32(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int64_t nz, int scheme, const float* params,
+                       const float* materials, int matidx_mode, const float* cur, float* past) {
+  update_slab<float>(pos, mat, X, Y, nz, scheme, params, materials, matidx_mode, cur, past);
+}
+void pfo_step_slab_f64(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int64_t nz, int scheme, const double* params,
+                       const double* materials, int matidx_mode, const double* cur, double* past) {
+  update_slab<double>(pos, mat, X, Y, nz, scheme, params, materials, matidx_mode, cur, past);
 }
 
 // ---- host-side pieces of the path -------------------------------------------

@@ -117,6 +117,20 @@ def run(pos, mat, scheme, params_v, materials, src_xyz, src_type, src_samples, r
     return out, secs
 
 
+def step_slab(pos, mat, scheme, params_v, materials, cur, past, matidx_as_written=1):
+    """One update launch over a slab [nz][Y][X] (planes 0 and nz-1 are halos): returns the next field."""
+    double = params_v.dtype == np.float64
+    dt = np.float64 if double else np.float32
+    nz, Y, X = pos.shape
+    materials = np.ascontiguousarray(materials, dtype=dt)
+    cur = np.ascontiguousarray(cur, dtype=dt)
+    new = np.array(past, dtype=dt, order="C", copy=True)
+    fn = lib().pfo_step_slab_f64 if double else lib().pfo_step_slab_f32
+    fn(_p(np.ascontiguousarray(pos)), _p(np.ascontiguousarray(mat)), C.c_int64(X), C.c_int64(Y), C.c_int64(nz), C.c_int(scheme),
+       _p(params_v), _p(materials), C.c_int(matidx_as_written), _p(cur), _p(new))
+    return new
+
+
 def source_samples(input_type, steps, fs=7000, data=None, double=False, transparent=False, grid_ir=None):
     """SimulationParameters::getSourceSample[Double] for steps 0..steps-1."""
     dt = np.float64 if double else np.float32

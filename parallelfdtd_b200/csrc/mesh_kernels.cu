@@ -97,4 +97,47 @@ int launch_translate_nodes(uint8_t* d_pos, uint8_t* d_mat, uint64_t n, int centr
   return PFDTD_OK;
 }
 
+// ---- node classes ---------------------------------------------------------------------------------
+// key = pos | mat << 8; air nodes are normalised to material 0 (their admittance term vanishes:
+// 6-K = 0 in the forward scheme, no direction flags in the centred one), solid nodes already carry 0.
+__device__ __forceinline__ uint32_t class_key(uint32_t pos, uint32_t mat, uint32_t air_code) {
+  return (pos == air_code || pos == 0u) ? pos : (pos | (mat << 8));
+}
+
+__global__ void mark_classes_kernel(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ mat, uint64_t n, uint32_t air_code,
+                                    uint8_t* __restrict__ flags) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t p = pos[i];
+    if (p == air_code || p == 0u) continue;      // classes 0 and 1 always exist
+    flags[class_key(p, mat[i], air_code)] = 1;    // benign race: every writer stores 1
+  }
+}
+
+__global__ void assign_classes_kernel(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ mat, uint64_t n, uint32_t air_code,
+                                      const uint8_t* __restrict__ lut, uint8_t* __restrict__ cls) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t p = pos[i];
+    cls[i] = (p == 0u) ? (uint8_t)0 : (p == air_code) ? (uint8_t)1 : lut[class_key(p, mat[i], air_code)];
+  }
+}
+
+int launch_mark_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_code, uint8_t* d_flags, cudaStream_t stream) {
+  int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
+  if (blocks < 1) blocks = 1;
+  mark_classes_kernel<<<blocks, 256, 0, stream>>>(d_pos, d_mat, n, air_code, d_flags);
+  PF_CUDA(cudaGetLastError());
+  return PFDTD_OK;
+}
+
+int launch_assign_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_code, const uint8_t* d_lut,
+                          uint8_t* d_cls, cudaStream_t stream) {
+  int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
+  if (blocks < 1) blocks = 1;
+  assign_classes_kernel<<<blocks, 256, 0, stream>>>(d_pos, d_mat, n, air_code, d_lut, d_cls);
+  PF_CUDA(cudaGetLastError());
+  return PFDTD_OK;
+}
+
 }  // namespace pfdtd

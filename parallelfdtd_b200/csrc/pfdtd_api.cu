@@ -77,6 +77,9 @@ struct Partition {
   int64_t first = 0, size = 0;          // slices held: [first, first+size) in the local volume
   uint8_t* pos = nullptr;
   uint8_t* mat = nullptr;
+  uint8_t* cls = nullptr;               // node class byte (what the TMA kernel reads instead of pos + mat)
+  void* class_table = nullptr;          // ClassEntry<T>[n_classes]
+  uint16_t* d_class_keys = nullptr;
   bool owns_nodes = true;
   void* P[2] = {nullptr, nullptr};
   void* materials = nullptr;
@@ -104,7 +107,7 @@ struct pfdtd_solver {
   // options
   int64_t opt_matidx_as_written = 1, opt_soft_accumulate = 0, opt_kernel = KERNEL_AUTO, opt_global_z_first = 0,
           opt_global_z_dim = 0, opt_double_pad = 0, opt_use_graph = 1, opt_overlap = 1, opt_tma_chunk = 0, opt_tma_tile = 0,
-          opt_time_kernels = 0;
+          opt_time_kernels = 0, opt_tma_hints = 0;
   int dtype = PFDTD_F32;
   int element_type = 0;
   int scheme = SCH_FORWARD;
@@ -118,6 +121,9 @@ struct pfdtd_solver {
   int stage_device = 0;
   uint8_t* d_pos0 = nullptr;             // padded + translated node volumes before partitioning
   uint8_t* d_mat0 = nullptr;
+  uint8_t* d_cls0 = nullptr;             // class byte volume before partitioning (null when > 256 classes)
+  std::vector<uint16_t> class_keys;      // class id -> pos | mat << 8
+  bool tables_dirty = true;
   std::vector<Partition> parts;
   int cur = 0;                           // index of the current field in Partition::P
   int past_direction = 1;                // launchFDTD3dStep's static (kernels3d.cu:386)
@@ -162,7 +168,8 @@ static int free_partitions(pfdtd_solver* s) {
     cudaSetDevice(p.device);
     if (p.s_main) cudaStreamSynchronize(p.s_main);
     if (p.s_edge) cudaStreamSynchronize(p.s_edge);
-    if (p.owns_nodes) { cudaFree(p.pos); cudaFree(p.mat); }
+    if (p.owns_nodes) { cudaFree(p.pos); cudaFree(p.mat); cudaFree(p.cls); }
+    cudaFree(p.class_table); cudaFree(p.d_class_keys);
     cudaFree(p.P[0]); cudaFree(p.P[1]); cudaFree(p.materials); cudaFree(p.d_step);
     cudaFree(p.d_src_elem); cudaFree(p.d_src_type); cudaFree(p.d_src_slot); cudaFree(p.d_rec_elem); cudaFree(p.d_rec_slot);
     cudaFree(p.d_src_samples); cudaFree(p.d_rec_out);
@@ -246,6 +253,10 @@ static UpdateArgs make_update_args(pfdtd_solver* s, Partition& p, int z_begin, i
   a.scheme = s->scheme;
   a.pos = p.pos;
   a.mat = p.mat;
+  a.cls = p.cls;
+  a.class_table = p.class_table;
+  a.n_classes = (int)s->class_keys.size();
+  a.tma_hints = (int)s->opt_tma_hints;
   a.P = p.P[s->cur];
   a.Pn = p.P[1 - s->cur];
   a.materials = p.materials;
@@ -258,6 +269,21 @@ static UpdateArgs make_update_args(pfdtd_solver* s, Partition& p, int z_begin, i
   a.z_end = z_end;
   a.stream = st;
   return a;
+}
+
+// (Re)build the per-class coefficient tables: they depend on params, materials and the material-index option.
+static int ensure_class_tables(pfdtd_solver* s) {
+  if (!s->tables_dirty) return PFDTD_OK;
+  for (auto& p : s->parts) {
+    if (!p.class_table) continue;
+    PF_CUDA(cudaSetDevice(p.device));
+    UpdateArgs a = make_update_args(s, p, 0, 0, p.s_main);
+    PF_TRY(build_class_table(a, p.d_class_keys, (int)s->class_keys.size(), p.class_table));
+    PF_CUDA(cudaStreamSynchronize(p.s_main));
+    s->launch_count++;
+  }
+  s->tables_dirty = false;
+  return PFDTD_OK;
 }
 
 static int launch_update(pfdtd_solver* s, Partition& p, int z_begin, int z_end, const TmaConfig& cfg, cudaStream_t st,
@@ -475,7 +501,7 @@ int pfdtd_create(pfdtd_solver** out) {
 int pfdtd_destroy(pfdtd_solver* s) {
   if (!s) return PFDTD_OK;
   free_partitions(s);
-  if (s->d_pos0) { cudaSetDevice(s->stage_device); cudaFree(s->d_pos0); cudaFree(s->d_mat0); }
+  if (s->d_pos0) { cudaSetDevice(s->stage_device); cudaFree(s->d_pos0); cudaFree(s->d_mat0); cudaFree(s->d_cls0); }
   if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
   if (s->ev_h0) cudaEventDestroy(s->ev_h0);
   if (s->ev_h1) cudaEventDestroy(s->ev_h1);
@@ -496,6 +522,7 @@ static int64_t* option_slot(pfdtd_solver* s, int option) {
     case PFDTD_OPT_TMA_CHUNK: return &s->opt_tma_chunk;
     case PFDTD_OPT_TMA_TILE: return &s->opt_tma_tile;
     case PFDTD_OPT_TIME_KERNELS: return &s->opt_time_kernels;
+    case PFDTD_OPT_TMA_HINTS: return &s->opt_tma_hints;
   }
   return nullptr;
 }
@@ -505,6 +532,7 @@ int pfdtd_set_option(pfdtd_solver* s, int option, int64_t value) {
   int64_t* slot = option_slot(s, option);
   PF_CHECK(slot, PFDTD_ERR_INVALID, "unknown option %d", option);
   *slot = value;
+  s->tables_dirty = true;
   if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
   return PFDTD_OK;
 }
@@ -528,7 +556,7 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
            "update type %u: the interpolated IISO/IWB schemes are not available in this build", element_type);
   free_partitions(s);
   PF_CUDA(cudaSetDevice(device));
-  if (s->d_pos0) { cudaFree(s->d_pos0); cudaFree(s->d_mat0); s->d_pos0 = s->d_mat0 = nullptr; }
+  if (s->d_pos0) { cudaFree(s->d_pos0); cudaFree(s->d_mat0); cudaFree(s->d_cls0); s->d_pos0 = s->d_mat0 = s->d_cls0 = nullptr; }
   s->dtype = dtype;
   s->element_type = (int)element_type;
   // scheme choice as in setupMesh: types 0,1,(3) -> Bilbao/forward, else Kowalczyk/centred (cudaMesh.cu:70-73,134-137)
@@ -555,6 +583,32 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
   PF_CUDA(cudaFree(d_counts));
   PF_CUDA(cudaFree(d_bid));   // adopted, like the reference (cudaMesh.cu:290-291)
   PF_CUDA(cudaFree(d_mat));
+  // node classes: distinct (position byte, material byte) pairs -> one class byte per voxel
+  {
+    const uint32_t air_code = s->scheme == SCH_CENTRED ? 0x80u : 0x86u;
+    uint8_t* d_flags = nullptr;
+    PF_CUDA(cudaMalloc(&d_flags, 65536));
+    PF_CUDA(cudaMemset(d_flags, 0, 65536));
+    PF_TRY(launch_mark_classes(np, nm, n_new, air_code, d_flags, 0));
+    std::vector<uint8_t> flags(65536);
+    PF_CUDA(cudaMemcpy(flags.data(), d_flags, 65536, cudaMemcpyDeviceToHost));
+    s->class_keys.clear();
+    s->class_keys.push_back(0);                    // class 0: solid
+    s->class_keys.push_back((uint16_t)air_code);   // class 1: air
+    for (uint32_t k = 0; k < 65536; k++)
+      if (flags[k] && k != 0 && k != air_code) s->class_keys.push_back((uint16_t)k);
+    s->d_cls0 = nullptr;
+    if (s->class_keys.size() <= 256) {
+      std::vector<uint8_t> lut(65536, 0);
+      for (size_t c = 0; c < s->class_keys.size(); c++) lut[s->class_keys[c]] = (uint8_t)c;
+      PF_CUDA(cudaMemcpy(d_flags, lut.data(), 65536, cudaMemcpyHostToDevice));
+      PF_CUDA(cudaMalloc(&s->d_cls0, n_new));
+      PF_TRY(launch_assign_classes(np, nm, n_new, air_code, d_flags, s->d_cls0, 0));
+      PF_CUDA(cudaDeviceSynchronize());
+      s->launch_count += 2;
+    }
+    PF_CUDA(cudaFree(d_flags));
+  }
   s->d_pos0 = np; s->d_mat0 = nm;
   s->stage_device = device;
   s->X = nx; s->Y = ny; s->Z = nz;
@@ -633,13 +687,23 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
     PF_CUDA(cudaSetDevice(p.device));
     const size_t nelem = (size_t)p.size * XY;
     if (n_partitions == 1 && p.device == s->stage_device) {
-      p.pos = s->d_pos0; p.mat = s->d_mat0; p.owns_nodes = true;   // adopt (cudaMesh.h:697-700)
-      s->d_pos0 = s->d_mat0 = nullptr;
+      p.pos = s->d_pos0; p.mat = s->d_mat0; p.cls = s->d_cls0; p.owns_nodes = true;   // adopt (cudaMesh.h:697-700)
+      s->d_pos0 = s->d_mat0 = s->d_cls0 = nullptr;
     } else {
       PF_CUDA(cudaMalloc(&p.pos, nelem));
       PF_CUDA(cudaMalloc(&p.mat, nelem));
       PF_CUDA(cudaMemcpyPeer(p.pos, p.device, s->d_pos0 + (size_t)p.first * XY, s->stage_device, nelem));
       PF_CUDA(cudaMemcpyPeer(p.mat, p.device, s->d_mat0 + (size_t)p.first * XY, s->stage_device, nelem));
+      if (s->d_cls0) {
+        PF_CUDA(cudaMalloc(&p.cls, nelem));
+        PF_CUDA(cudaMemcpyPeer(p.cls, p.device, s->d_cls0 + (size_t)p.first * XY, s->stage_device, nelem));
+      }
+    }
+    if (p.cls) {
+      const size_t nc = s->class_keys.size();
+      PF_CUDA(cudaMalloc(&p.class_table, nc * class_entry_bytes(s->dtype)));
+      PF_CUDA(cudaMalloc(&p.d_class_keys, nc * sizeof(uint16_t)));
+      PF_CUDA(cudaMemcpy(p.d_class_keys, s->class_keys.data(), nc * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
     for (int b = 0; b < 2; b++) {
       PF_CUDA(cudaMalloc(&p.P[b], nelem * es));
@@ -661,9 +725,10 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
     PF_CUDA(cudaEventRecord(p.ev_edge, p.s_edge));
     // kernel choice
     const int nplanes = (int)p.size - 2;
-    p.use_tma = (s->opt_kernel != KERNEL_PLAIN) && tma_supported((int)s->X, (int)s->Y, s->dtype) && nplanes >= 1;
+    p.use_tma = (s->opt_kernel != KERNEL_PLAIN) && tma_supported((int)s->X, (int)s->Y, s->dtype) && nplanes >= 1 && p.cls != nullptr;
     PF_CHECK(!(s->opt_kernel == KERNEL_TMA && !p.use_tma), PFDTD_ERR_INVALID,
-             "TMA kernel requested but mesh %ux%u (slab of %lld slices) is not supported by it", s->X, s->Y, (long long)p.size);
+             "TMA kernel requested but mesh %ux%u (slab of %lld slices, %zu node classes) is not supported by it", s->X, s->Y,
+             (long long)p.size, s->class_keys.size());
     if (p.use_tma) {
       PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->X, (int)s->Y, nplanes, p.device, s->opt_tma_tile, s->opt_tma_chunk,
                              &p.cfg_full));
@@ -671,15 +736,17 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
                              p.cfg_full.tile + 1, s->opt_tma_chunk, &p.cfg_int));
       p.cfg_edge = TmaConfig{p.cfg_full.tile, 1};
       for (int c = 0; c < 2; c++)
-        PF_TRY(tma_encode_maps(&p.maps[c], s->dtype, p.cfg_full.tile, p.P[c], p.P[1 - c], p.pos, (int)s->X, (int)s->Y, (int)p.size));
+        PF_TRY(tma_encode_maps(&p.maps[c], s->dtype, p.cfg_full.tile, p.P[c], p.P[1 - c], p.cls, (int)s->X, (int)s->Y, (int)p.size));
     }
   }
   if (s->d_pos0) {   // free the staging volumes (cudaMesh.h:704-707)
     PF_CUDA(cudaSetDevice(s->stage_device));
     PF_CUDA(cudaFree(s->d_pos0));
     PF_CUDA(cudaFree(s->d_mat0));
-    s->d_pos0 = s->d_mat0 = nullptr;
+    PF_CUDA(cudaFree(s->d_cls0));
+    s->d_pos0 = s->d_mat0 = s->d_cls0 = nullptr;
   }
+  s->tables_dirty = true;
   s->mesh_ready = false;   // staging consumed; setup_mesh again before re-partitioning
   s->cur = 0;
   s->srcrec_dirty = true;
@@ -897,6 +964,7 @@ int pfdtd_enqueue_steps(pfdtd_solver* s, uint32_t first_step, uint32_t n_steps) 
   PF_CHECK(s && !s->parts.empty(), PFDTD_ERR_INVALID, "make_partition must be called before stepping");
   if (first_step + n_steps > s->rec_cap) PF_TRY(pfdtd_reserve_steps(s, first_step + n_steps));
   PF_TRY(prepare_srcrec(s));
+  PF_TRY(ensure_class_tables(s));
   const bool single = (s->parts.size() == 1 && !s->comm);
   const bool timed = s->opt_time_kernels != 0;
   for (auto& p : s->parts) {
@@ -1053,6 +1121,7 @@ int pfdtd_run(pfdtd_solver* s, uint32_t n_steps, void* h_response, pfdtd_interru
 int pfdtd_step(pfdtd_solver* s, uint32_t step, int direction, void* h_response, uint32_t n_steps_total) {
   PF_CHECK(s && !s->parts.empty(), PFDTD_ERR_INVALID, "make_partition must be called before step");
   PF_TRY(prepare_srcrec(s));
+  PF_TRY(ensure_class_tables(s));
   PF_TRY(sync_all(s));
   PF_TRY(set_step_counters(s, (int)step, 0x7fffffff));
   const bool single = (s->parts.size() == 1 && !s->comm);

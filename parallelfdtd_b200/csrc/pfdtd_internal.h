@@ -45,12 +45,17 @@ int launch_pad_with_zeros(const uint8_t* d_old, uint8_t* d_new, uint32_t dx, uin
                           uint32_t nx, uint32_t ny, uint32_t nz, int skip_z0, cudaStream_t stream);
 int launch_translate_nodes(uint8_t* d_pos, uint8_t* d_mat, uint64_t n, int centred, unsigned long long* d_counts2,
                            cudaStream_t stream);
+// node classes: mark which (pos, mat) pairs occur (d_flags: 65536 bytes, zeroed by the caller), then
+// write the class byte volume through a 65536-entry key -> class LUT
+int launch_mark_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_code, uint8_t* d_flags, cudaStream_t stream);
+int launch_assign_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_code, const uint8_t* d_lut,
+                          uint8_t* d_cls, cudaStream_t stream);
 
 // ---- update kernels (update_kernels.cu) ---------------------------------------------------------
 struct TmaMaps {           // tensor maps of one partition for one (cur,new) buffer assignment
   CUtensorMap p_halo;      // P (current field), box with x/y halo
   CUtensorMap p_old;       // field that is overwritten (past -> next), box without halo
-  CUtensorMap pos;         // node byte, box without halo
+  CUtensorMap cls;         // node class byte, box without halo
 };
 
 struct UpdateArgs {
@@ -58,6 +63,10 @@ struct UpdateArgs {
   int scheme;              // 0 forward equations, 2 centred equations
   const uint8_t* pos;
   const uint8_t* mat;
+  const uint8_t* cls;      // node class byte volume (TMA kernel)
+  const void* class_table; // device ClassEntry<T>[n_classes]
+  int n_classes;
+  int tma_hints;           // bit0: evict_first on once-read operands, bit1: evict_last on P
   const void* P;           // current field (slab base)
   void* Pn;                // past field, overwritten with the next field
   const void* materials;   // device [n_coefs]
@@ -76,7 +85,9 @@ enum { KERNEL_AUTO = 0, KERNEL_TMA = 1, KERNEL_PLAIN = 2 };
 struct TmaConfig { int tile; int chunk; };
 
 bool tma_supported(int X, int Y, int dtype);
-int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void* Pold, const uint8_t* pos, int X, int Y, int nz);
+int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void* Pold, const uint8_t* cls, int X, int Y, int nz);
+int build_class_table(const UpdateArgs& a, const uint16_t* d_keys, int n_classes, void* d_table);
+size_t class_entry_bytes(int dtype);
 int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk, TmaConfig* out);
 int launch_update_tma(const UpdateArgs& a, const TmaMaps& maps, const TmaConfig& cfg);
 int launch_update_plain(const UpdateArgs& a);

@@ -7,12 +7,14 @@
 //  * fdtd_update_tma  -- the product kernel.  Each CTA owns a 128 x TY xy-tile and marches a chunk of
 //    z-planes.  A producer warp streams, per plane, three TMA boxes into a ring of shared-memory
 //    stages (mbarrier full/empty pipeline): the current field with a one-voxel xy halo, the field
-//    being overwritten, and the node byte.  Consumer warps keep z-1 / z / z+1 of their four
-//    x-adjacent voxels in registers, take y-neighbours from the shared tile, x-neighbours by warp
-//    shuffle (halo column from the tile), and write the result with one 128-bit store per four
-//    voxels.  The boundary term (admittance / direction flags from the node byte, material byte
-//    fetched for boundary nodes only) is evaluated in the same pass.  HBM traffic per voxel update:
-//    read P 4(8) B once, read P_old 4(8) B, write 4(8) B, node byte 1 B = 13 B fp32 / 25 B fp64.
+//    being overwritten, and the packed node byte (the node *class*: one byte that stands for the
+//    reference's position byte AND material byte, see update_math.cuh).  Consumer warps keep
+//    z-1 / z / z+1 of their four x-adjacent voxels in registers, take y-neighbours from the shared
+//    tile, x-neighbours by warp shuffle (halo column from the tile), and write the result with one
+//    128-bit store per four voxels.  The boundary term is evaluated in the same pass from a per-class
+//    table in shared memory (no dependent global loads, no separate boundary kernel).  HBM traffic per
+//    voxel update: read P 4(8) B once, read P_old 4(8) B, write 4(8) B, node byte 1 B = 13 B fp32 /
+//    25 B fp64.
 //
 //  * fdtd_update_plain -- one thread per voxel, neighbour reads through L1/L2; used for dimensions the
 //    TMA path does not cover and as an on-device cross-check.
@@ -115,6 +117,25 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], "
+      "[%5], %6;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
 template <typename T> struct V4 { T v[4]; };
 
 __device__ __forceinline__ void lds4(const float* p, V4<float>& o) {
@@ -155,13 +176,14 @@ struct TileGeom {
 template <typename T, int SCHEME, int TY, int RPW, int NST>
 __global__ void __launch_bounds__((TY / RPW + 1) * 32)
     fdtd_update_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
-                    const __grid_constant__ CUtensorMap tm_pos, const uint8_t* __restrict__ mat, T* __restrict__ Pn,
-                    UpdConst<T> c, int X, int Y, int z_begin, int z_end, int chunk) {
+                    const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
+                    T* __restrict__ Pn, T lam2, T a_air, int X, int Y, int z_begin, int z_end, int chunk, int hints) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY / RPW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[NST];
   __shared__ __align__(8) uint64_t bar_empty[NST];
+  __shared__ ClassEntry<T> s_table[256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -180,11 +202,16 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < n_classes; i += blockDim.x) s_table[i] = g_table[i];
   __syncthreads();
 
   if (warp == NW) {
     // ------------------------------- producer -------------------------------------------------
     if (lane == 0) {
+      // P is shared with the neighbouring tiles (halo rows/columns) and re-read by the z-neighbour chunk;
+      // P_old and the node bytes are touched exactly once per step
+      const uint64_t pol_once = policy_evict_first();
+      const uint64_t pol_keep = policy_evict_last();
       // load i brings P(z_lo-1+i) with halo and, from i >= 2, P_old / node byte of plane z_lo+i-2
       for (int i = 0; i < n + 2; i++) {
         const int slot = i % NST;
@@ -193,10 +220,19 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
         unsigned char* st = smem_raw + (size_t)slot * G::STAGE_BYTES;
         const uint32_t bytes = (i >= 2) ? (uint32_t)(G::PT_BYTES + G::PO_BYTES + G::PS_BYTES) : (uint32_t)G::PT_BYTES;
         mbar_expect_tx(&bar_full[slot], bytes);
-        tma_load_3d(st + G::PT_OFF, &tm_p, x0 - G::HX, y0 - 1, z_lo - 1 + i, &bar_full[slot]);
-        if (i >= 2) {
-          tma_load_3d(st + G::PO_OFF, &tm_old, x0, y0, z_lo + i - 2, &bar_full[slot]);
-          tma_load_3d(st + G::PS_OFF, &tm_pos, x0, y0, z_lo + i - 2, &bar_full[slot]);
+        if (hints) {
+          if (hints & 2) tma_load_3d_hint(st + G::PT_OFF, &tm_p, x0 - G::HX, y0 - 1, z_lo - 1 + i, &bar_full[slot], pol_keep);
+          else tma_load_3d(st + G::PT_OFF, &tm_p, x0 - G::HX, y0 - 1, z_lo - 1 + i, &bar_full[slot]);
+          if (i >= 2) {
+            tma_load_3d_hint(st + G::PO_OFF, &tm_old, x0, y0, z_lo + i - 2, &bar_full[slot], pol_once);
+            tma_load_3d_hint(st + G::PS_OFF, &tm_cls, x0, y0, z_lo + i - 2, &bar_full[slot], pol_once);
+          }
+        } else {
+          tma_load_3d(st + G::PT_OFF, &tm_p, x0 - G::HX, y0 - 1, z_lo - 1 + i, &bar_full[slot]);
+          if (i >= 2) {
+            tma_load_3d(st + G::PO_OFF, &tm_old, x0, y0, z_lo + i - 2, &bar_full[slot]);
+            tma_load_3d(st + G::PS_OFF, &tm_cls, x0, y0, z_lo + i - 2, &bar_full[slot]);
+          }
         }
       }
     }
@@ -225,6 +261,8 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
 #pragma unroll
     for (int k = 0; k < RPW; k++) lds4(pt1 + (r0 + k + 1) * G::PW + G::HX + xl, cur[k]);
   }
+
+  constexpr uint32_t AIR4 = CLS_AIR * 0x01010101u;
 
   for (int j = 0; j < n; j++) {
     const int i2 = j + 2;
@@ -263,22 +301,33 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
         const V4<T>& yp = (k == RPW - 1) ? yp1 : cur[k + 1 >= RPW ? RPW - 1 : k + 1];
         const int64_t e = (int64_t)z * XY + (int64_t)gy * X + gx;
         V4<T> res;
-        const uint32_t air4 = (SCHEME == SCH_CENTRED) ? 0x80808080u : 0x86868686u;
-        if (pw[k] == air4) {
+        T S[4];
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            T xm = (q == 0) ? xm_edge : cc.v[q - 1 < 0 ? 0 : q - 1];
-            T xp = (q == 3) ? xp_edge : cc.v[q + 1 > 3 ? 3 : q + 1];
-            res.v[q] = voxel_update<T, SCHEME>(air4 & 0xffu, nullptr, cc.v[q], up[k].v[q], down[k].v[q], yp.v[q], ym.v[q],
-                                               xp, xm, old[k].v[q], c);
-          }
+        for (int q = 0; q < 4; q++) {
+          T xm = (q == 0) ? xm_edge : cc.v[q - 1 < 0 ? 0 : q - 1];
+          T xp = (q == 3) ? xp_edge : cc.v[q + 1 > 3 ? 3 : q + 1];
+          S[q] = (SCHEME == SCH_CENTRED) ? sum6_centred<T>(up[k].v[q], down[k].v[q], yp.v[q], ym.v[q], xp, xm)
+                                         : sum6_forward<T>(up[k].v[q], down[k].v[q], yp.v[q], ym.v[q], xp, xm);
+        }
+        if (pw[k] == AIR4) {
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            res.v[q] = (SCHEME == SCH_CENTRED) ? voxel_centred_air<T>(cc.v[q], S[q], old[k].v[q], lam2, a_air)
+                                               : voxel_forward_air<T>(cc.v[q], S[q], old[k].v[q], lam2, a_air);
         } else {
 #pragma unroll
           for (int q = 0; q < 4; q++) {
-            T xm = (q == 0) ? xm_edge : cc.v[q - 1 < 0 ? 0 : q - 1];
-            T xp = (q == 3) ? xp_edge : cc.v[q + 1 > 3 ? 3 : q + 1];
-            res.v[q] = voxel_update<T, SCHEME>((pw[k] >> (8 * q)) & 0xffu, mat + e + q, cc.v[q], up[k].v[q], down[k].v[q],
-                                               yp.v[q], ym.v[q], xp, xm, old[k].v[q], c);
+            const ClassEntry<T> ce = s_table[(pw[k] >> (8 * q)) & 0xffu];
+            if (SCHEME == SCH_CENTRED) {
+              T xm = (q == 0) ? xm_edge : cc.v[q - 1 < 0 ? 0 : q - 1];
+              T xp = (q == 3) ? xp_edge : cc.v[q + 1 > 3 ? 3 : q + 1];
+              res.v[q] = ((pw[k] >> (8 * q)) & 0xffu) == CLS_AIR
+                             ? voxel_centred_air<T>(cc.v[q], S[q], old[k].v[q], lam2, a_air)
+                             : voxel_centred_cls<T>(ce, cc.v[q], S[q], up[k].v[q], down[k].v[q], yp.v[q], ym.v[q], xp, xm,
+                                                    old[k].v[q], lam2, a_air);
+            } else {
+              res.v[q] = voxel_forward_cls<T>(ce, cc.v[q], S[q], old[k].v[q], lam2);
+            }
           }
         }
         stg4(Pn + e, res);
@@ -290,6 +339,15 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
 #pragma unroll
     for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
   }
+}
+
+// builds the per-class table with the device arithmetic of update_math.cuh (one thread per class)
+template <typename T, int SCHEME>
+__global__ void build_class_table_kernel(const uint16_t* __restrict__ keys, int n_classes, UpdConst<T> c, ClassEntry<T>* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_classes) return;
+  const uint32_t key = keys[i];
+  out[i] = make_class_entry<T, SCHEME>(key & 0xffu, key >> 8, c);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -361,8 +419,9 @@ int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupanc
   }
   const int nplanes = a.z_end - a.z_begin;
   dim3 grid((a.X + TX - 1) / TX, (a.Y + TY - 1) / TY, (nplanes + chunk - 1) / chunk);
-  kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.pos, a.mat, (T*)a.Pn, make_const<T>(a), a.X, a.Y, a.z_begin,
-                                          a.z_end, chunk);
+  const UpdConst<T> c = make_const<T>(a);
+  kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.cls, (const ClassEntry<T>*)a.class_table, a.n_classes, (T*)a.Pn,
+                                          c.lam2, c.a_air, a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }
@@ -402,7 +461,7 @@ const char* tma_tile_name(int dtype, int tile) {
   return (tile >= 0 && tile < kNumTiles) ? kTiles[tile].name : "?";
 }
 
-int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void* Pold, const uint8_t* pos, int X, int Y, int nz) {
+int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void* Pold, const uint8_t* cls, int X, int Y, int nz) {
   PF_CHECK(tile >= 0 && tile < kNumTiles, PFDTD_ERR_INVALID, "bad tile variant %d", tile);
   const int ty = kTiles[tile].ty;
   const int esize = dtype == PFDTD_F32 ? 4 : 8;
@@ -410,13 +469,13 @@ int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void
   const int hx = 16 / esize;
   PF_TRY(encode3d(&out->p_halo, dt, esize, P, X, Y, nz, TX + 2 * hx, ty + 2));
   PF_TRY(encode3d(&out->p_old, dt, esize, Pold, X, Y, nz, TX, ty));
-  PF_TRY(encode3d(&out->pos, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pos, X, Y, nz, TX, ty));
+  PF_TRY(encode3d(&out->cls, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, cls, X, Y, nz, TX, ty));
   return PFDTD_OK;
 }
 
 int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk,
                     TmaConfig* out) {
-  int tile = (opt_tile > 0 && opt_tile <= kNumTiles) ? (int)opt_tile - 1 : (dtype == PFDTD_F32 ? 1 : 0);
+  int tile = (opt_tile > 0 && opt_tile <= kNumTiles) ? (int)opt_tile - 1 : (dtype == PFDTD_F32 ? 2 : 0);
   if (Y <= 8 && kTiles[tile].ty > 8) tile = 0;
   UpdateArgs probe{};
   probe.dtype = dtype;
@@ -451,6 +510,22 @@ int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device
   out->chunk = std::max(1, std::min(chunk, std::max(nplanes, 1)));
   return PFDTD_OK;
 }
+
+int build_class_table(const UpdateArgs& a, const uint16_t* d_keys, int n_classes, void* d_table) {
+  if (n_classes <= 0) return PFDTD_OK;
+  const int th = 64, bl = (n_classes + th - 1) / th;
+  if (a.dtype == PFDTD_F32) {
+    if (a.scheme == SCH_CENTRED) build_class_table_kernel<float, SCH_CENTRED><<<bl, th, 0, a.stream>>>(d_keys, n_classes, make_const<float>(a), (ClassEntry<float>*)d_table);
+    else build_class_table_kernel<float, SCH_FORWARD><<<bl, th, 0, a.stream>>>(d_keys, n_classes, make_const<float>(a), (ClassEntry<float>*)d_table);
+  } else {
+    if (a.scheme == SCH_CENTRED) build_class_table_kernel<double, SCH_CENTRED><<<bl, th, 0, a.stream>>>(d_keys, n_classes, make_const<double>(a), (ClassEntry<double>*)d_table);
+    else build_class_table_kernel<double, SCH_FORWARD><<<bl, th, 0, a.stream>>>(d_keys, n_classes, make_const<double>(a), (ClassEntry<double>*)d_table);
+  }
+  PF_CUDA(cudaGetLastError());
+  return PFDTD_OK;
+}
+
+size_t class_entry_bytes(int dtype) { return dtype == PFDTD_F32 ? sizeof(ClassEntry<float>) : sizeof(ClassEntry<double>); }
 
 int launch_update_tma(const UpdateArgs& a, const TmaMaps& maps, const TmaConfig& cfg) {
   if (a.z_end <= a.z_begin) return PFDTD_OK;

@@ -114,6 +114,89 @@ __device__ __forceinline__ T voxel_centred(uint32_t pos, const uint8_t* mat_ptr,
   return Ar<T>::mul(Ar<T>::mul(sw, inner), Ar<T>::rcp(one_p_beta));
 }
 
+// ---- node classes -----------------------------------------------------------------------------------
+// The product kernel does not read the reference's two node volumes in the step loop.  Every distinct
+// (position byte, material byte) pair that occurs in the mesh is a *node class* (<= 256 of them: one
+// byte per voxel, class 0 = solid, class 1 = air); everything the update needs from the pair is
+// evaluated once per class -- with exactly the operations of voxel_forward / voxel_centred above, so
+// the per-voxel result keeps its bits -- and kept in a small table:
+//   forward:  c0 = 2 - K*lam2,  c1 = -(1 - beta),  c2 = sw / (1 + beta)
+//   centred:  c0 = beta - 1,    c1 = 1 / (1 + beta), c2 = sw,   flags = position byte (DIR_* / SIGN_*)
+template <typename T>
+struct alignas(16) ClassEntry {
+  T c0, c1, c2;
+  uint32_t flags;
+};
+
+enum : uint32_t { CLS_SOLID = 0, CLS_AIR = 1 };
+
+template <typename T, int SCHEME>
+__device__ __forceinline__ ClassEntry<T> make_class_entry(uint32_t pos, uint32_t m, const UpdConst<T>& c) {
+  ClassEntry<T> e;
+  e.flags = pos;
+  T sw = (T)(pos >> 7);
+  if (pos == 0u) m = 0u;
+  if (SCHEME == SCH_CENTRED) {
+    T dsum = (T)((pos & 1u) + ((pos >> 1) & 1u) + ((pos >> 2) & 1u));
+    uint32_t idx = (uint32_t)Ar<T>::add((T)(m * 20u), c.octave);
+    T cl = Ar<T>::mul(load_coef(c, idx), c.lam);
+    e.c0 = Ar<T>::fma(cl, dsum, (T)-1);
+    e.c1 = Ar<T>::rcp(Ar<T>::fma(cl, dsum, (T)1));
+    e.c2 = sw;
+  } else {
+    T K = (T)(pos & 0x7Fu);
+    uint32_t idx = c.matidx_as_written ? (uint32_t)Ar<T>::mul((T)(m * 20u), c.octave) : m * 20u + (uint32_t)c.octave;
+    T t = Ar<T>::mul(Ar<T>::mul(load_coef(c, idx), Ar<T>::add((T)6, -K)), c.lam);
+    e.c0 = Ar<T>::fma(K, -c.lam2, (T)2);
+    e.c1 = -Ar<T>::fma(t, (T)-0.5, (T)1);
+    e.c2 = Ar<T>::mul(sw, Ar<T>::rcp(Ar<T>::fma(t, (T)0.5, (T)1)));
+  }
+  return e;
+}
+
+// forward, any class: identical bits to voxel_forward (air: c1 = -1, c2 = 1, multiplying by 1 is exact)
+template <typename T>
+__device__ __forceinline__ T voxel_forward_cls(const ClassEntry<T>& e, T p, T S, T p_old, T lam2) {
+  T inner = Ar<T>::fma(S, lam2, Ar<T>::mul(p, e.c0));
+  inner = Ar<T>::fma(p_old, e.c1, inner);
+  return Ar<T>::mul(e.c2, inner);
+}
+template <typename T>
+__device__ __forceinline__ T voxel_forward_air(T p, T S, T p_old, T lam2, T a_air) {
+  T inner = Ar<T>::fma(S, lam2, Ar<T>::mul(p, a_air));
+  return Ar<T>::fma(p_old, (T)-1, inner);
+}
+
+template <typename T>
+__device__ __forceinline__ T sum6_centred(T zp, T zm, T yp, T ym, T xp, T xm) {
+  T S = Ar<T>::add(xm, xp);
+  S = Ar<T>::add(S, ym);
+  S = Ar<T>::add(S, yp);
+  S = Ar<T>::add(S, zp);
+  S = Ar<T>::add(S, zm);
+  return S;
+}
+template <typename T>
+__device__ __forceinline__ T voxel_centred_air(T p, T S, T p_old, T lam2, T a_air) {
+  S = Ar<T>::add(S, (T)0);
+  T inner = Ar<T>::fma(S, lam2, -Ar<T>::mul(p, a_air));
+  return Ar<T>::fma(p_old, (T)-1, inner);
+}
+template <typename T>
+__device__ __forceinline__ T voxel_centred_cls(const ClassEntry<T>& e, T p, T S, T zp, T zm, T yp, T ym, T xp, T xm, T p_old,
+                                               T lam2, T a_air) {
+  const uint32_t pos = e.flags;
+  T dir_x = (T)(pos & 1u), dir_y = (T)((pos >> 1) & 1u), dir_z = (T)((pos >> 2) & 1u);
+  T sx = (pos & 0x10u) ? xp : xm;
+  T sy = (pos & 0x20u) ? yp : ym;
+  T sz = (pos & 0x40u) ? zm : zp;
+  T Sb = Ar<T>::add(Ar<T>::add(Ar<T>::mul(sx, dir_x), Ar<T>::mul(sy, dir_y)), Ar<T>::mul(sz, dir_z));
+  S = Ar<T>::add(S, Sb);
+  T inner = Ar<T>::fma(S, lam2, -Ar<T>::mul(p, a_air));
+  inner = Ar<T>::fma(p_old, e.c0, inner);
+  return Ar<T>::mul(Ar<T>::mul(e.c2, inner), e.c1);
+}
+
 template <typename T, int SCHEME>
 __device__ __forceinline__ T voxel_update(uint32_t pos, const uint8_t* mat_ptr, T p, T zp, T zm, T yp, T ym, T xp, T xm,
                                           T p_old, const UpdConst<T>& c) {
