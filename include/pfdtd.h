@@ -108,8 +108,9 @@ int pfdtd_setup_mesh(pfdtd_solver* s, const uint8_t* h_bid, const uint8_t* h_mat
                      uint32_t block_x, uint32_t block_y, uint32_t block_z,
                      uint32_t element_type, int dtype,
                      const void* params, const void* material_coefs, uint32_t n_unique_materials);
-/* same, but the two volumes are DEVICE pointers on `device` and are adopted (freed by the
- * library), exactly like the reference's setupMesh arguments (cudaMesh.cu:290-291). */
+/* same, but the two volumes are DEVICE pointers on `device` (-1 = the calling thread's current
+ * device) and are adopted (freed by the library), exactly like the reference's setupMesh arguments
+ * (cudaMesh.cu:290-291). */
 int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t* d_mat,
                             uint32_t vx, uint32_t vy, uint32_t vz,
                             uint32_t block_x, uint32_t block_y, uint32_t block_z,
@@ -134,6 +135,12 @@ int pfdtd_export_partition_nodes(pfdtd_solver* s, uint32_t k, uint8_t* h_pos, ui
 /* current pressure field of partition k (host buffer of n_slices*dimX*dimY elements of the dtype);
  * which = 0 current, 1 past */
 int pfdtd_export_partition_pressure(pfdtd_solver* s, uint32_t k, int which, void* h_out);
+
+/* raw device pointers of partition k (CudaMesh::getPressurePtrAt / getPastPressurePtrAt /
+ * getPositionIdxPtrAt / getMaterialIdxPtrAt, cudaMesh.h:184-212) for capture / visualisation code that runs
+ * its own kernels on the fields; any out pointer may be NULL.  Valid until the next pfdtd_make_partition. */
+int pfdtd_get_device_pointers(pfdtd_solver* s, uint32_t k, void** d_pressure, void** d_pressure_past,
+                              uint8_t** d_position_idx, uint8_t** d_material_idx);
 
 /* ---- single samples (CudaMesh::setSample/addSample/getSample, cudaMesh.h:321-404,497-584) -- */
 int pfdtd_set_sample(pfdtd_solver* s, uint32_t x, uint32_t y, uint32_t z, double value);

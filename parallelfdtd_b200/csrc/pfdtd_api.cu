@@ -555,6 +555,7 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
   PF_CHECK(element_type <= PFDTD_SRL, PFDTD_ERR_INVALID,
            "update type %u: the interpolated IISO/IWB schemes are not available in this build", element_type);
   free_partitions(s);
+  if (device < 0) PF_CUDA(cudaGetDevice(&device));
   PF_CUDA(cudaSetDevice(device));
   if (s->d_pos0) { cudaFree(s->d_pos0); cudaFree(s->d_mat0); cudaFree(s->d_cls0); s->d_pos0 = s->d_mat0 = s->d_cls0 = nullptr; }
   s->dtype = dtype;
@@ -818,6 +819,19 @@ int pfdtd_export_partition_pressure(pfdtd_solver* s, uint32_t k, int which, void
   PF_CUDA(cudaSetDevice(p.device));
   const size_t n = (size_t)p.size * s->X * s->Y * esize(s);
   PF_CUDA(cudaMemcpy(h_out, p.P[which ? 1 - s->cur : s->cur], n, cudaMemcpyDeviceToHost));
+  return PFDTD_OK;
+}
+
+int pfdtd_get_device_pointers(pfdtd_solver* s, uint32_t k, void** d_pressure, void** d_pressure_past, uint8_t** d_position_idx,
+                              uint8_t** d_material_idx) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  PF_CHECK(k < s->parts.size(), PFDTD_ERR_RANGE, "partition %u out of range", k);
+  PF_TRY(sync_all(s));
+  Partition& p = s->parts[k];
+  if (d_pressure) *d_pressure = p.P[s->cur];
+  if (d_pressure_past) *d_pressure_past = p.P[1 - s->cur];
+  if (d_position_idx) *d_position_idx = p.pos;
+  if (d_material_idx) *d_material_idx = p.mat;
   return PFDTD_OK;
 }
 

@@ -492,16 +492,21 @@ int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device
   if (opt_chunk > 0) {
     chunk = (int)opt_chunk;
   } else {
-    // choose the number of z-chunks that best fills whole waves, charging 2 extra plane loads per chunk
+    // Measured on B200 (profiles/r01_sweep.md): when the launch is many waves deep, short chunks win even
+    // though every chunk re-reads two planes (those re-reads hit L2, and the fine grain evens out the
+    // SMs' finishing times); when the whole launch is only a wave or two, wave quantisation dominates.
+    const int lo = dtype == PFDTD_F32 ? 12 : 20, hi = dtype == PFDTD_F32 ? 16 : 28;
+    const bool deep = tiles * (int64_t)((nplanes + lo - 1) / lo) >= 4 * resident;
     double best = -1;
     for (int gz = 1; gz <= nplanes; gz++) {
       int ch = (nplanes + gz - 1) / gz;
-      if (ch < 8 && gz > 1) break;
+      if (deep && ch > hi) continue;
+      if (ch < (deep ? lo : 8) && gz > 1) break;
       int gz_eff = (nplanes + ch - 1) / ch;
       int64_t total = tiles * gz_eff;
       int64_t waves = (total + resident - 1) / resident;
       double fill = (double)total / (double)(waves * resident);
-      double eff = fill * (double)ch / (double)(ch + 2);
+      double eff = deep ? fill : fill * (double)ch / (double)(ch + 2);
       if (eff > best + 1e-9) { best = eff; chunk = ch; }
     }
     if (chunk <= 0) chunk = nplanes;
