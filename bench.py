@@ -212,7 +212,7 @@ def run_ours(args):
 
     # ---- device-resident measurement (`value`) --------------------------------------------------------
     ss = make_solver()
-    ss.connect()
+    uid = ss.connect()
     s = ss.solver
     ss.set_sources(src_xyz, [capi.SRC_HARD], src_tab)
     ss.set_receivers(rec_xyz)
@@ -266,7 +266,7 @@ def run_ours(args):
         te0 = time.time()
         se = make_solver()                                   # H2D of both node volumes, pad, translate, partition, alloc
         if world > 1:
-            se.connect()
+            se.connect(uid)                                   # communicator of this job: created once per process, reused
         se.set_sources(src_xyz, [capi.SRC_HARD], src_tab[:, :K])     # H2D of the source table happens in run()
         se.set_receivers(rec_xyz)
         r_e2e, _ = se.solver.run(K)                          # K steps + D2H of the responses
@@ -278,7 +278,7 @@ def run_ours(args):
         e2e = {"value": nvox_global * K / t_e2e / 1e6, "unit": "Mvox/s", "h2d_bytes_per_step": h2d * world / K,
                "d2h_bytes_per_step": d2h / K, "seconds": t_e2e,
                "what": "pfdtd_setup_mesh(host bid+mat, pinned) + make_partition + set_sources/receivers + pfdtd_run(K) incl. response D2H"
-                       + ("; NCCL communicator creation included" if world > 1 else "")}
+                       + ("; the job's NCCL communicator already exists (created once per process)" if world > 1 else "")}
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----------------------------
     cpu = None
@@ -322,8 +322,11 @@ def cpu_baseline(args, bid, mat, tab, prm, src_xyz, rec_xyz, src_tab):
     pos, m, _, _ = oracle.setup_mesh(bid, mat, (32, 4, 1), args.update_type, double)
     nvox = pos.size
     threads = oracle.num_threads()
-    steps = args.cpu_steps or int(max(4, min(200, 15.0 * 0.6e9 * max(threads, 1) / 16 / nvox)))
     scheme = 0 if args.update_type in (0, 1) else 2
+    steps = args.cpu_steps
+    if not steps:   # calibrate on 4 steps, then size the sample for ~12 s of CPU work
+        _, s4 = oracle.run(pos, m, scheme, prm, tab, src_xyz, [0], np.ascontiguousarray(src_tab[:, :5]), rec_xyz, 5, 1, 0, 0, 1)
+        steps = int(max(8, min(src_tab.shape[1], 12.0 / max(s4 / 4, 1e-6))))
     smp = np.ascontiguousarray(src_tab[:, :steps])
     _, secs = oracle.run(pos, m, scheme, prm, tab, src_xyz, [0], smp, rec_xyz, steps, 1, 0, 0, 1)
     timed = steps - 1

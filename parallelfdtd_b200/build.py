@@ -44,10 +44,40 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
         subprocess.check_call(cmd)
     return LIB
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_LIB = os.path.join(HERE, "libpfdtd_host.so")
+HOST_SOURCES = [os.path.join("base", "SimulationParameters.cpp"), os.path.join("base", "MaterialHandler.cpp"), "App.cpp"]
+HOST_TEST_SRC = os.path.normpath(os.path.join(HERE, "..", "tests", "cpp", "host_tests.cpp"))
+HOST_TEST_BIN = os.path.normpath(os.path.join(HERE, "..", "tests", "cpp", "host_tests"))
+
+
+def _host_cxx() -> str:
+    return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else os.environ.get("CXX", "g++")
+
+
+def build_host(force: bool = False) -> str:
+    """C++ host layer (reference class names over the C ABI) -> libpfdtd_host.so, plus its test binary."""
+    build_lib()
+    srcs = [os.path.join(HOST_DIR, s) for s in HOST_SOURCES]
+    deps = []
+    for root, _, files in os.walk(HOST_DIR):
+        deps += [os.path.join(root, f) for f in files]
+    deps.append(os.path.normpath(os.path.join(HERE, "..", "include", "pfdtd.h")))
+    flags = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wno-unused-function", "-I", os.path.join(HERE, "host")]
+    link = ["-L", HERE, "-l:libpfdtd_b200.so", "-Wl,-rpath,$ORIGIN"]
+    if force or any(_newer(d, HOST_LIB) for d in deps):
+        subprocess.check_call([_host_cxx()] + flags + ["-shared", "-o", HOST_LIB] + srcs + link)
+    if os.path.exists(HOST_TEST_SRC) and (force or _newer(HOST_TEST_SRC, HOST_TEST_BIN) or _newer(HOST_LIB, HOST_TEST_BIN)):
+        subprocess.check_call([_host_cxx()] + flags + ["-o", HOST_TEST_BIN, HOST_TEST_SRC, "-L", HERE, "-l:libpfdtd_host.so",
+                                                       "-l:libpfdtd_b200.so", "-Wl,-rpath," + HERE])
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

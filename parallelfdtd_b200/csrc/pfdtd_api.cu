@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <map>
+#include <mutex>
 
 namespace pfdtd {
 
@@ -502,7 +504,7 @@ int pfdtd_destroy(pfdtd_solver* s) {
   if (!s) return PFDTD_OK;
   free_partitions(s);
   if (s->d_pos0) { cudaSetDevice(s->stage_device); cudaFree(s->d_pos0); cudaFree(s->d_mat0); cudaFree(s->d_cls0); }
-  if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+  // s->comm is owned by the process-wide communicator cache (pfdtd_comm_init)
   if (s->ev_h0) cudaEventDestroy(s->ev_h0);
   if (s->ev_h1) cudaEventDestroy(s->ev_h1);
   delete s;
@@ -1181,8 +1183,24 @@ int pfdtd_comm_init(pfdtd_solver* s, const uint8_t* id128, int rank, int nranks)
   NcclId id;
   memcpy(id.bytes, id128, 128);
   PF_CUDA(cudaSetDevice(s->parts[0].device));
+  // communicators are process-lifetime objects keyed by (id, rank, nranks): a second solver created with the
+  // same id (e.g. the next simulation of the same job) reuses the communicator instead of paying
+  // ncclCommInitRank again
+  static std::map<std::string, void*> cache;
+  static std::mutex cache_mu;
+  std::string key((const char*)id128, 128);
+  key += "/" + std::to_string(rank) + "/" + std::to_string(nranks) + "/" + std::to_string(s->parts[0].device);
   void* comm = nullptr;
-  PF_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+  {
+    std::lock_guard<std::mutex> g(cache_mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) comm = it->second;
+  }
+  if (!comm) {
+    PF_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    std::lock_guard<std::mutex> g(cache_mu);
+    cache[key] = comm;
+  }
   s->comm = comm;
   s->rank = rank;
   s->nranks = nranks;

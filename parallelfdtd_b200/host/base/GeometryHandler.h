@@ -1,0 +1,58 @@
+// GeometryHandler.h -- triangle soup container with the accessors App uses (reference
+// src/base/GeometryHandler.h: vertices/indices, bounding box, per-triangle surface area).  Header-only.
+#pragma once
+#include <cmath>
+#include <stdexcept>
+#include <vector>
+#include "../math/geomMath.h"
+
+class GeometryHandler {
+ public:
+  GeometryHandler() {}
+  void initialize(unsigned int* indices, float* vertices, unsigned int number_of_indices, unsigned int number_of_vertices) {
+    indices_.assign(indices, indices + number_of_indices);
+    vertices_.assign(vertices, vertices + (size_t)number_of_vertices * 3);
+    for (size_t i = 0; i < indices_.size(); i++)
+      if (indices_[i] >= number_of_vertices) throw std::out_of_range("GeometryHandler::initialize: vertex index out of range");
+    update_();
+  }
+  void initialize(std::vector<unsigned int> indices, std::vector<float> vertices) {
+    initialize(indices.empty() ? 0 : &indices[0], vertices.empty() ? 0 : &vertices[0], (unsigned int)indices.size(),
+               (unsigned int)(vertices.size() / 3));
+  }
+  unsigned int getNumberOfTriangles() const { return (unsigned int)(indices_.size() / 3); }
+  unsigned int getNumberOfVertices() const { return (unsigned int)(vertices_.size() / 3); }
+  unsigned int getNumberOfIndices() const { return (unsigned int)indices_.size(); }
+  unsigned int* getIndexPtr() { return indices_.empty() ? 0 : &indices_[0]; }
+  float* getVerticePtr() { return vertices_.empty() ? 0 : &vertices_[0]; }
+  nv::Vec3f getVertexAt(unsigned int i) const { return nv::Vec3f(vertices_.at(3 * i), vertices_.at(3 * i + 1), vertices_.at(3 * i + 2)); }
+  nv::Vec3ui getTriangleAt(unsigned int t) const { return nv::Vec3ui(indices_.at(3 * t), indices_.at(3 * t + 1), indices_.at(3 * t + 2)); }
+  nv::Vec3f getBoundingBox() const { return bb_max_ - bb_min_; }
+  nv::Vec3f getBoundingBoxMin() const { return bb_min_; }
+  nv::Vec3f getBoundingBoxMax() const { return bb_max_; }
+  float getSurfaceAreaAt(unsigned int t) const { return areas_.at(t); }
+  float getTotalSurfaceArea() const { float s = 0.f; for (size_t i = 0; i < areas_.size(); i++) s += areas_[i]; return s; }
+
+ private:
+  void update_() {
+    bb_min_ = nv::Vec3f(0, 0, 0); bb_max_ = nv::Vec3f(0, 0, 0);
+    for (unsigned int i = 0; i < getNumberOfVertices(); i++) {
+      nv::Vec3f v = getVertexAt(i);
+      if (i == 0) { bb_min_ = v; bb_max_ = v; }
+      bb_min_.set(std::fmin(bb_min_.x, v.x), std::fmin(bb_min_.y, v.y), std::fmin(bb_min_.z, v.z));
+      bb_max_.set(std::fmax(bb_max_.x, v.x), std::fmax(bb_max_.y, v.y), std::fmax(bb_max_.z, v.z));
+    }
+    areas_.resize(getNumberOfTriangles());
+    for (unsigned int t = 0; t < getNumberOfTriangles(); t++) {
+      nv::Vec3ui tri = getTriangleAt(t);
+      nv::Vec3f a = getVertexAt(tri.x), b = getVertexAt(tri.y), c = getVertexAt(tri.z);
+      nv::Vec3f u = b - a, v = c - a;
+      nv::Vec3f n(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
+      areas_[t] = 0.5f * std::sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+    }
+  }
+  std::vector<unsigned int> indices_;
+  std::vector<float> vertices_;
+  std::vector<float> areas_;
+  nv::Vec3f bb_min_, bb_max_;
+};

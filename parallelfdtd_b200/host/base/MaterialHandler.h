@@ -1,0 +1,46 @@
+// MaterialHandler.h -- per-surface material coefficients, de-duplicated into the unique-material table
+// the kernels index with the material byte (reference src/base/MaterialHandler.h:29-161; table layout
+// [unique][20], reference src/base/MaterialHandler.cpp:100-164).
+#pragma once
+#include <vector>
+
+#define MATERIAL_COEF_NUM 20
+
+class MaterialHandler {
+ public:
+  MaterialHandler();
+  ~MaterialHandler() {}
+
+  struct material_t { float coefs[MATERIAL_COEF_NUM]; };
+
+  void addMaterials(float* material_ptr, unsigned int number_of_surfaces, unsigned int number_of_coefficients);
+  unsigned int addSurfaceMaterial(std::vector<float> material_coefficients);
+  void coefsAreAdmittances() { admitance_ = true; }
+  void coefsAreReflectances() { admitance_ = false; }
+
+  unsigned int getNumberOfCoefficients() { return number_of_coefficients_; }
+  unsigned int getNumberOfSurfaces() { return number_of_surfaces_; }
+  unsigned int getNumberOfUniqueMaterials() { return number_of_unique_materials_; }
+  unsigned int getMaterialIdxAt(unsigned int idx) { return material_indices_.at(idx); }
+  unsigned char* getMaterialIdxPtr();
+  float* getMaterialCoefficientPtr();
+  double* getMaterialCoefficientPtrDouble();
+  float getUniqueCoefAt(unsigned int material, unsigned int coef_idx);
+  float getSurfaceCoefAt(unsigned int surface, unsigned int coef_idx);
+  float getMeanAbsorption(unsigned int octave);
+
+  void setNumberOfCoefficients(unsigned int n) { number_of_coefficients_ = n; }
+  void setGlobalMaterial(unsigned int number_of_surfaces, float coef);
+  void setMaterialIndexAt(unsigned int surface_idx, unsigned char material_idx);
+
+ private:
+  unsigned int findOrAdd(const std::vector<float>& coefs);
+  bool admitance_;
+  unsigned int number_of_coefficients_;
+  unsigned int number_of_surfaces_;
+  unsigned int number_of_unique_materials_;
+  std::vector<unsigned char> material_indices_;
+  std::vector<material_t> unique_coefficients_;
+  std::vector<float> coefficient_vector_;
+  std::vector<double> coefficient_vector_double_;
+};

@@ -129,15 +129,19 @@ class SlabSolver:
         self.solver = s
         self._rec_z: List[int] = []
 
-    def connect(self):
-        """Create the NCCL communicator for the halo exchange (collective over all ranks)."""
+    def connect(self, uid: bytes | None = None) -> bytes | None:
+        """Attach the NCCL communicator for the halo exchange (collective over all ranks).  Without `uid` a
+        fresh 128-byte id is made on rank 0 and handed round; passing the id returned by an earlier connect()
+        reuses that communicator (the library caches communicators per id for the life of the process)."""
         if self.world == 1:
-            return
+            return None
         import torch.distributed as dist
-        uid = self.capi.comm_unique_id() if self.rank == 0 else None
-        uid = broadcast_bytes(uid, 128, 0)
+        if uid is None:
+            uid = self.capi.comm_unique_id() if self.rank == 0 else None
+            uid = broadcast_bytes(uid, 128, 0)
         self.solver.comm_init(uid, self.rank, self.world)
         dist.barrier()
+        return uid
 
     def set_sources(self, xyz, types, samples):
         self.solver.set_sources(xyz, types, samples)        # global coordinates; the library keeps those in its slab
