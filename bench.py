@@ -37,7 +37,9 @@ WORKLOADS = {
     "c2half": ((512, 512, 256), 6, "shoebox 512x512x256 per GPU"),
 }
 ALGO_BYTES = {"f32": 13, "f64": 25}     # P^n + P^(n-1) + P^(n+1) + node byte per voxel update
-UPDATE_NAMES = {0: "SRL_FORWARD", 1: "SHARED", 2: "SRL"}
+UPDATE_NAMES = {0: "SRL_FORWARD", 1: "SHARED", 2: "SRL", 3: "IISO", 4: "IWB"}
+COURANT = {0: float(np.sqrt(1.0 / 3.0)), 1: float(np.sqrt(1.0 / 3.0)), 2: float(np.sqrt(1.0 / 3.0)),   # setUpdateType, SimulationParameters.cpp:123-137
+           3: float(np.sqrt(3.0) / 2), 4: 1.0}                                                          # IISO / IWB stability limits
 
 
 def parse_args():
@@ -50,7 +52,7 @@ def parse_args():
                     help="reference arm: the reference's own CUDA build (oracle/_ref) or the CPU oracle port")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--update-type", type=int, default=0, choices=[0, 1, 2])
+    ap.add_argument("--update-type", type=int, default=0, choices=[0, 1, 2, 3, 4])
     ap.add_argument("--kernel", default="auto", choices=["auto", "tma", "plain"])
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
@@ -178,7 +180,7 @@ def run_ours(args):
     double = args.dtype == "f64"
     dt = capi.F64 if double else capi.F32
     npdt = np.float64 if double else np.float32
-    lam = float(np.sqrt(1.0 / 3.0))      # SimulationParameters::setUpdateType, reference SimulationParameters.cpp:123-137
+    lam = COURANT[args.update_type]
     prm = np.array([lam, lam * lam, 1.0 / 3.0, 0.0], dtype=npdt)
     tab = synth.material_table(list(np.linspace(0.99, 0.5, n_mat)) if n_mat > 1 else [0.9]).astype(npdt)
     plan = slabs.SlabPlan(gdims[2], world)
@@ -322,7 +324,9 @@ def cpu_baseline(args, bid, mat, tab, prm, src_xyz, rec_xyz, src_tab):
     pos, m, _, _ = oracle.setup_mesh(bid, mat, (32, 4, 1), args.update_type, double)
     nvox = pos.size
     threads = oracle.num_threads()
-    scheme = 0 if args.update_type in (0, 1) else 2
+    scheme = 0 if args.update_type in (0, 1) else (2 if args.update_type == 2 else 3)
+    if scheme == 3:
+        prm = oracle.params_interp(float(prm[0]), 0, oracle.interp_coefficients(args.update_type, float(prm[1])), double)
     steps = args.cpu_steps
     if not steps:   # calibrate on 4 steps, then size the sample for ~12 s of CPU work
         _, s4 = oracle.run(pos, m, scheme, prm, tab, src_xyz, [0], np.ascontiguousarray(src_tab[:, :5]), rec_xyz, 5, 1, 0, 0, 1)

@@ -94,6 +94,11 @@ int pfdtd_create(pfdtd_solver** out);
 int pfdtd_destroy(pfdtd_solver* s);
 int pfdtd_set_option(pfdtd_solver* s, int option, int64_t value);
 int pfdtd_get_option(pfdtd_solver* s, int option, int64_t* value);
+/* Interpolated schemes (PFDTD_IISO / PFDTD_IWB; not in the reference): override the four weights of the
+ * 27-point compact explicit update, d[0] axial, d[1] edge, d[2] corner, d[3] centre; NULL restores the
+ * scheme's own values.  (lam2, 0, 0, 2 - 6 lam2) is the reference's SRL_FORWARD equation.  Call before
+ * pfdtd_setup_mesh. */
+int pfdtd_set_scheme_coefficients(pfdtd_solver* s, const double* d4);
 
 /* ---- mesh setup ---------------------------------------------------------- */
 /* CudaMesh::setupMesh / setupMeshDouble (src/kernels/cudaMesh.cu:26-153): pad the voxelizer-style

@@ -116,6 +116,58 @@ inline T update_centred(uint8_t pos, uint8_t mat, const T* P, int64_t cur, int64
   return (sw * inner) * rcp;
 }
 
+// Interpolated 27-point compact schemes (IISO / IWB).  NOT in the mounted reference:
+// "parity unpinned" -- this restates the builder-defined equation documented in
+// parallelfdtd_b200/csrc/update_math.cuh ("interpolated"), operation by operation:
+//   p_new = sw/(1+beta) * ( d1*A6 + d2*A12 + d3*A8 + c0*p - (1-beta)*p_old ),
+//   c0 = d4 + d1*(6-K6) + d2*(12-K12) + d3*(8-K8),  beta = 0.5*Y*(6-K6)*lam,
+// which for d = (lam2, 0, 0, 2-6*lam2) is the reference's SRL_FORWARD update (kernels3d.cu:508-528).
+// Values outside the xy extent read as 0; K12/K8 count the non-solid edge/corner neighbours.
+template <typename T>
+inline T update_interp(const uint8_t* pos, const uint8_t* mat, const T* P, int64_t x, int64_t y, int64_t z, int64_t X, int64_t Y,
+                       T p_old, const T* params, const T* materials, const T* d) {
+  const int64_t XY = X * Y;
+  auto at = [&](int64_t xx, int64_t yy, int64_t zz) -> T {
+    if (xx < 0 || yy < 0 || xx >= X || yy >= Y) return (T)0;
+    return P[zz * XY + yy * X + xx];
+  };
+  auto inside = [&](int64_t xx, int64_t yy, int64_t zz) -> unsigned {
+    if (xx < 0 || yy < 0 || xx >= X || yy >= Y) return 0u;
+    return (unsigned)(pos[zz * XY + yy * X + xx] >> 7);
+  };
+  T c[3], a4[3], g4[3];
+  for (int k = 0; k < 3; k++) {
+    const int64_t zz = z - 1 + k;
+    c[k] = at(x, y, zz);
+    a4[k] = ((at(x - 1, y, zz) + at(x + 1, y, zz)) + at(x, y - 1, zz)) + at(x, y + 1, zz);
+    g4[k] = ((at(x - 1, y - 1, zz) + at(x + 1, y - 1, zz)) + at(x - 1, y + 1, zz)) + at(x + 1, y + 1, zz);
+  }
+  const uint8_t pb = pos[z * XY + y * X + x];
+  unsigned k12 = 0, k8 = 0;
+  for (int dz = -1; dz <= 1; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
+    const int nz_ = (dx != 0) + (dy != 0) + (dz != 0);
+    if (nz_ == 2) k12 += inside(x + dx, y + dy, z + dz);
+    if (nz_ == 3) k8 += inside(x + dx, y + dy, z + dz);
+  }
+  const T K = (T)(pb & 0x7F);
+  const T sw = (T)(pb >> 7);
+  const unsigned m = pb == 0 ? 0u : (unsigned)mat[z * XY + y * X + x];
+  const unsigned idx = m * 20u + (unsigned)params[3];
+  const T t = (materials[idx] * ((T)6 - K)) * params[0];
+  T c0 = FMA(d[0], (T)6 - K, d[3]);
+  c0 = FMA(d[1], (T)(12u - k12), c0);
+  c0 = FMA(d[2], (T)(8u - k8), c0);
+  const T c1 = -FMA(t, (T)-0.5, (T)1);
+  const T c2 = sw * ((T)1 / FMA(t, (T)0.5, (T)1));
+  const T A6 = (a4[1] + c[0]) + c[2];
+  const T A12 = (g4[1] + a4[0]) + a4[2];
+  T inner = FMA(A6, d[0], c[1] * c0);
+  inner = FMA(A12, d[1], inner);
+  if (d[2] != (T)0) inner = FMA(g4[0] + g4[2], d[2], inner);
+  inner = FMA(p_old, c1, inner);
+  return c2 * inner;
+}
+
 // One launch of the update kernel over a slab: local slices 1..nz-2 of `Q` (the past field) are
 // overwritten with the next field (kernels3d.cu:109-153: grid.z = slab slices - 2, pointers offset
 // by one slice).  pos/mat point at the slab's first slice.
@@ -123,6 +175,16 @@ template <typename T>
 void update_slab(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int64_t nz, int scheme, const T* params,
                  const T* materials, int matidx_mode, const T* P, T* Q) {
   const int64_t XY = X * Y;
+  if (scheme >= 3) {   // interpolated: params[4..7] = d1..d4
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int64_t z = 1; z < nz - 1; z++)
+      for (int64_t y = 0; y < Y; y++)
+        for (int64_t x = 0; x < X; x++) {
+          const int64_t e = z * XY + y * X + x;
+          Q[e] = update_interp<T>(pos, mat, P, x, y, z, X, Y, Q[e], params, materials, params + 4);
+        }
+    return;
+  }
 #pragma omp parallel for collapse(2) schedule(static)
   for (int64_t z = 1; z < nz - 1; z++) {
     for (int64_t y = 0; y < Y; y++) {
@@ -290,7 +352,8 @@ void pfo_to_kowalczyk(uint8_t* pos, uint8_t* mat, uint64_t n, uint64_t* counts) 
 }
 
 // Full run; pos/mat are the padded, scheme-translated GLOBAL volumes [Z][Y][X].
-// scheme: 0 SRL_FORWARD, 1 SHARED (mapped to the forward equations, SURVEY C-3), 2 SRL (centred).
+// scheme: 0 SRL_FORWARD, 1 SHARED (mapped to the forward equations, SURVEY C-3), 2 SRL (centred),
+// 3 interpolated 27-point family (params then has 8 entries: [lam, lam2, 1/3, octave, d1, d2, d3, d4]).
 // src_samples [n_src][steps], out [n_rec][steps]. Returns wall seconds spent in steps >= timed_from_step.
 double pfo_run_f32(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int64_t Z, int scheme,
                    const float* params, const float* materials, int matidx_mode, int soft_mode, int n_parts,

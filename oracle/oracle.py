@@ -85,7 +85,9 @@ def setup_mesh(bid, mat, block=(32, 4, 1), element_type=0, dtype_is_double=False
         blk[1] = blk[0]
     pos = pad_with_zeros(bid, blk)
     m = pad_with_zeros(mat, blk)
-    centred = element_type not in (0, 1) if dtype_is_double else element_type not in (0, 1, 3)
+    # reference: types 0,1,(3) -> Bilbao / forward byte, 2 -> Kowalczyk (cudaMesh.cu:70-73,134-137); the enum values
+    # 3 (IISO) and 4 (IWB) appended by this build use the forward byte in both precisions
+    centred = element_type == 2
     air, bnd = translate(pos, m, centred)
     return pos, m, air, bnd
 
@@ -94,6 +96,26 @@ def params(lam, octave, double=False):
     out = np.zeros(4, dtype=np.float64 if double else np.float32)
     (lib().pfo_params_f64 if double else lib().pfo_params_f32)(C.c_double(lam), C.c_uint(octave), _p(out))
     return out
+
+
+def interp_coefficients(update_type, lam2):
+    """d1..d4 of the compact explicit family as the library derives them (pfdtd_api.cu)."""
+    l2 = float(lam2)
+    if update_type == 3:      # IISO: a = 1/6, b = 0
+        return [l2 / 3, l2 / 6, 0.0, 2 - 4 * l2]
+    if update_type == 4:      # IWB: a = 1/4, b = 1/16
+        return [l2 / 4, l2 / 8, l2 / 16, 2 - 3.5 * l2]
+    raise ValueError(update_type)
+
+
+def interp_lambda(update_type):
+    return {3: float(np.sqrt(3.0) / 2), 4: 1.0}[update_type]
+
+
+def params_interp(lam, octave, d, double=False):
+    """8-entry parameter vector of the interpolated schemes: [lam, lam^2, 1/3, octave, d1, d2, d3, d4]."""
+    p = params(lam, octave, double)
+    return np.concatenate([p, np.asarray(d, dtype=p.dtype)])
 
 
 def run(pos, mat, scheme, params_v, materials, src_xyz, src_type, src_samples, rec_xyz, steps, n_parts=1,

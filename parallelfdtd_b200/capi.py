@@ -115,6 +115,10 @@ class Solver:
         _check(lib().pfdtd_get_option(self._h, C.c_int(opt), C.byref(v)))
         return v.value
 
+    def set_scheme_coefficients(self, d):
+        arr = (C.c_double * 4)(*[float(v) for v in d]) if d is not None else None
+        _check(lib().pfdtd_set_scheme_coefficients(self._h, arr))
+
     def setup_mesh(self, bid, mat, block=(32, 4, 1), element_type=SRL_FORWARD, dtype=F32, params=None, materials=None):
         bid = np.ascontiguousarray(bid, dtype=np.uint8)
         mat = np.ascontiguousarray(mat, dtype=np.uint8)

@@ -98,44 +98,100 @@ int launch_translate_nodes(uint8_t* d_pos, uint8_t* d_mat, uint64_t n, int centr
 }
 
 // ---- node classes ---------------------------------------------------------------------------------
-// key = pos | mat << 8; air nodes are normalised to material 0 (their admittance term vanishes:
-// 6-K = 0 in the forward scheme, no direction flags in the centred one), solid nodes already carry 0.
-__device__ __forceinline__ uint32_t class_key(uint32_t pos, uint32_t mat, uint32_t air_code) {
-  return (pos == air_code || pos == 0u) ? pos : (pos | (mat << 8));
+// key = pos | mat << 8 | K12 << 16 | K8 << 20.  K12 / K8 = number of non-solid voxels among the 12 edge- and
+// 8 corner-neighbours; only the interpolated (27-point) schemes need them, the 7-point schemes use 0.
+// Nodes whose admittance term vanishes (forward byte with K = 6 / centred byte without direction flags)
+// are normalised to material 0; solid nodes already carry material 0.
+__device__ __forceinline__ uint32_t node_key(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ mat, uint64_t i, uint32_t p,
+                                             uint32_t air_code, int interp, uint32_t X, uint32_t Y, uint32_t Z) {
+  uint32_t key = (p == air_code) ? p : (p | ((uint32_t)mat[i] << 8));
+  if (interp) {
+    const int x = (int)(i % X), y = (int)((i / X) % Y), z = (int)(i / ((uint64_t)X * Y));
+    uint32_t k12 = 0, k8 = 0;
+#pragma unroll
+    for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+      for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+          const int nz_ = (dx != 0) + (dy != 0) + (dz != 0);
+          if (nz_ < 2) continue;
+          const int xx = x + dx, yy = y + dy, zz = z + dz;
+          uint32_t in = 0;
+          if (xx >= 0 && yy >= 0 && zz >= 0 && xx < (int)X && yy < (int)Y && zz < (int)Z)
+            in = pos[((uint64_t)zz * Y + yy) * X + xx] >> 7;
+          if (nz_ == 2) k12 += in; else k8 += in;
+        }
+    key |= (k12 << 16) | (k8 << 20);
+  }
+  return key;
 }
 
-__global__ void mark_classes_kernel(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ mat, uint64_t n, uint32_t air_code,
-                                    uint8_t* __restrict__ flags) {
+__device__ __forceinline__ uint32_t key_hash(uint32_t k) { k ^= k >> 15; k *= 0x2c1b3c6dU; k ^= k >> 12; k *= 0x297a2d39U; k ^= k >> 15; return k; }
+
+// open-addressing set of keys (EMPTY = 0xffffffff); `count` = number of distinct keys inserted
+__global__ void mark_classes_kernel(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ mat, uint64_t n, uint32_t air_key,
+                                    uint32_t air_code, int interp, uint32_t X, uint32_t Y, uint32_t Z, uint32_t* __restrict__ table,
+                                    uint32_t cap, uint32_t* __restrict__ count) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t p = pos[i];
-    if (p == air_code || p == 0u) continue;      // classes 0 and 1 always exist
-    flags[class_key(p, mat[i], air_code)] = 1;    // benign race: every writer stores 1
+    if (p == 0u) continue;
+    const uint32_t key = node_key(pos, mat, i, p, air_code, interp, X, Y, Z);
+    if (key == air_key) continue;                 // classes 0 (solid) and 1 (air) always exist
+    uint32_t slot = key_hash(key) % cap;
+    for (uint32_t probe = 0; probe < cap; probe++) {
+      const uint32_t cur = table[slot];
+      if (cur == key) break;
+      if (cur == 0xffffffffu) {
+        const uint32_t prev = atomicCAS(&table[slot], 0xffffffffu, key);
+        if (prev == 0xffffffffu) { atomicAdd(count, 1u); break; }
+        if (prev == key) break;
+      }
+      slot = (slot + 1) % cap;
+    }
   }
 }
 
-__global__ void assign_classes_kernel(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ mat, uint64_t n, uint32_t air_code,
-                                      const uint8_t* __restrict__ lut, uint8_t* __restrict__ cls) {
+__global__ void assign_classes_kernel(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ mat, uint64_t n, uint32_t air_key,
+                                      uint32_t air_code, int interp, uint32_t X, uint32_t Y, uint32_t Z,
+                                      const uint32_t* __restrict__ table, const uint8_t* __restrict__ ids, uint32_t cap,
+                                      uint8_t* __restrict__ cls) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t p = pos[i];
-    cls[i] = (p == 0u) ? (uint8_t)0 : (p == air_code) ? (uint8_t)1 : lut[class_key(p, mat[i], air_code)];
+    uint8_t c = 0;
+    if (p != 0u) {
+      const uint32_t key = node_key(pos, mat, i, p, air_code, interp, X, Y, Z);
+      if (key == air_key) c = 1;
+      else {
+        uint32_t slot = key_hash(key) % cap;
+        for (uint32_t probe = 0; probe < cap; probe++) {
+          if (table[slot] == key) { c = ids[slot]; break; }
+          slot = (slot + 1) % cap;
+        }
+      }
+    }
+    cls[i] = c;
   }
 }
 
-int launch_mark_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_code, uint8_t* d_flags, cudaStream_t stream) {
+static int class_blocks(uint64_t n) {
   int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
-  if (blocks < 1) blocks = 1;
-  mark_classes_kernel<<<blocks, 256, 0, stream>>>(d_pos, d_mat, n, air_code, d_flags);
+  return blocks < 1 ? 1 : blocks;
+}
+
+int launch_mark_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_key, uint32_t air_code, int interp,
+                        uint32_t X, uint32_t Y, uint32_t Z, uint32_t* d_table, uint32_t cap, uint32_t* d_count, cudaStream_t stream) {
+  mark_classes_kernel<<<class_blocks(n), 256, 0, stream>>>(d_pos, d_mat, n, air_key, air_code, interp, X, Y, Z, d_table, cap, d_count);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }
 
-int launch_assign_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_code, const uint8_t* d_lut,
+int launch_assign_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_key, uint32_t air_code, int interp,
+                          uint32_t X, uint32_t Y, uint32_t Z, const uint32_t* d_table, const uint8_t* d_ids, uint32_t cap,
                           uint8_t* d_cls, cudaStream_t stream) {
-  int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
-  if (blocks < 1) blocks = 1;
-  assign_classes_kernel<<<blocks, 256, 0, stream>>>(d_pos, d_mat, n, air_code, d_lut, d_cls);
+  assign_classes_kernel<<<class_blocks(n), 256, 0, stream>>>(d_pos, d_mat, n, air_key, air_code, interp, X, Y, Z, d_table, d_ids, cap, d_cls);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }

@@ -81,7 +81,7 @@ struct Partition {
   uint8_t* mat = nullptr;
   uint8_t* cls = nullptr;               // node class byte (what the TMA kernel reads instead of pos + mat)
   void* class_table = nullptr;          // ClassEntry<T>[n_classes]
-  uint16_t* d_class_keys = nullptr;
+  uint32_t* d_class_keys = nullptr;
   bool owns_nodes = true;
   void* P[2] = {nullptr, nullptr};
   void* materials = nullptr;
@@ -124,7 +124,9 @@ struct pfdtd_solver {
   uint8_t* d_pos0 = nullptr;             // padded + translated node volumes before partitioning
   uint8_t* d_mat0 = nullptr;
   uint8_t* d_cls0 = nullptr;             // class byte volume before partitioning (null when > 256 classes)
-  std::vector<uint16_t> class_keys;      // class id -> pos | mat << 8
+  std::vector<uint32_t> class_keys;      // class id -> pos | mat << 8 | K12 << 16 | K8 << 20
+  double dcoef[4] = {0, 0, 0, 0};        // interpolated schemes: d1..d4
+  bool dcoef_user = false;
   bool tables_dirty = true;
   std::vector<Partition> parts;
   int cur = 0;                           // index of the current field in Partition::P
@@ -264,6 +266,7 @@ static UpdateArgs make_update_args(pfdtd_solver* s, Partition& p, int z_begin, i
   a.materials = p.materials;
   a.n_coefs = s->n_unique * 20;
   for (int i = 0; i < 4; i++) a.params[i] = s->params[i];
+  for (int i = 0; i < 4; i++) a.dcoef[i] = s->dcoef[i];
   a.matidx_as_written = (int)s->opt_matidx_as_written;
   a.X = (int)s->X;
   a.Y = (int)s->Y;
@@ -300,7 +303,10 @@ static int launch_update(pfdtd_solver* s, Partition& p, int z_begin, int z_end, 
     p.kev.push_back(e1);
     PF_CUDA(cudaEventRecord(e0, st));
   }
-  if (p.use_tma) PF_TRY(launch_update_tma(a, p.maps[s->cur], cfg));
+  if (s->scheme == SCH_INTERP) {
+    if (p.use_tma) PF_TRY(launch_update_interp_tma(a, p.maps[s->cur], cfg, nullptr));
+    else PF_TRY(launch_update_interp_plain(a));
+  } else if (p.use_tma) PF_TRY(launch_update_tma(a, p.maps[s->cur], cfg));
   else PF_TRY(launch_update_plain(a));
   if (timed) PF_CUDA(cudaEventRecord(e1, st));
   s->launch_count++;
@@ -539,6 +545,15 @@ int pfdtd_set_option(pfdtd_solver* s, int option, int64_t value) {
   return PFDTD_OK;
 }
 
+int pfdtd_set_scheme_coefficients(pfdtd_solver* s, const double* d4) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  if (d4) { for (int i = 0; i < 4; i++) s->dcoef[i] = d4[i]; s->dcoef_user = true; }
+  else s->dcoef_user = false;
+  s->tables_dirty = true;
+  if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+  return PFDTD_OK;
+}
+
 int pfdtd_get_option(pfdtd_solver* s, int option, int64_t* value) {
   PF_CHECK(s && value, PFDTD_ERR_INVALID, "null argument");
   int64_t* slot = option_slot(s, option);
@@ -554,8 +569,7 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
   PF_CHECK(dtype == PFDTD_F32 || dtype == PFDTD_F64, PFDTD_ERR_INVALID, "bad dtype %d", dtype);
   PF_CHECK(vx && vy && vz && block_x && block_y && block_z, PFDTD_ERR_INVALID, "zero dimension");
   PF_CHECK(n_unique_materials >= 1, PFDTD_ERR_INVALID, "at least one material is required");
-  PF_CHECK(element_type <= PFDTD_SRL, PFDTD_ERR_INVALID,
-           "update type %u: the interpolated IISO/IWB schemes are not available in this build", element_type);
+  PF_CHECK(element_type <= PFDTD_IWB, PFDTD_ERR_INVALID, "unknown update type %u", element_type);
   free_partitions(s);
   if (device < 0) PF_CUDA(cudaGetDevice(&device));
   PF_CUDA(cudaSetDevice(device));
@@ -563,7 +577,7 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
   s->dtype = dtype;
   s->element_type = (int)element_type;
   // scheme choice as in setupMesh: types 0,1,(3) -> Bilbao/forward, else Kowalczyk/centred (cudaMesh.cu:70-73,134-137)
-  s->scheme = (element_type == 0 || element_type == 1) ? SCH_FORWARD : SCH_CENTRED;
+  s->scheme = (element_type == 0 || element_type == 1) ? SCH_FORWARD : (element_type == PFDTD_SRL ? SCH_CENTRED : SCH_INTERP);
   s->bx = block_x; s->by = block_y; s->bz = block_z;
   // padWithZeros (cudaMesh.cu:253-304); setupMeshDouble pads y with block.x (cudaMesh.cu:106-111) when asked to
   uint32_t pby = (dtype == PFDTD_F64 && s->opt_double_pad) ? block_x : block_y;
@@ -586,31 +600,49 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
   PF_CUDA(cudaFree(d_counts));
   PF_CUDA(cudaFree(d_bid));   // adopted, like the reference (cudaMesh.cu:290-291)
   PF_CUDA(cudaFree(d_mat));
-  // node classes: distinct (position byte, material byte) pairs -> one class byte per voxel
+  // node classes: distinct node keys (position byte, material byte [, K12, K8]) -> one class byte per voxel
   {
     const uint32_t air_code = s->scheme == SCH_CENTRED ? 0x80u : 0x86u;
-    uint8_t* d_flags = nullptr;
-    PF_CUDA(cudaMalloc(&d_flags, 65536));
-    PF_CUDA(cudaMemset(d_flags, 0, 65536));
-    PF_TRY(launch_mark_classes(np, nm, n_new, air_code, d_flags, 0));
-    std::vector<uint8_t> flags(65536);
-    PF_CUDA(cudaMemcpy(flags.data(), d_flags, 65536, cudaMemcpyDeviceToHost));
+    const int interp = s->scheme == SCH_INTERP;
+    const uint32_t air_key = interp ? (air_code | (12u << 16) | (8u << 20)) : air_code;
+    const uint32_t cap = 4096;
+    uint32_t* d_table = nullptr;
+    uint32_t* d_count = nullptr;
+    uint8_t* d_ids = nullptr;
+    PF_CUDA(cudaMalloc(&d_table, cap * sizeof(uint32_t)));
+    PF_CUDA(cudaMalloc(&d_count, sizeof(uint32_t)));
+    PF_CUDA(cudaMalloc(&d_ids, cap));
+    PF_CUDA(cudaMemset(d_table, 0xff, cap * sizeof(uint32_t)));
+    PF_CUDA(cudaMemset(d_count, 0, sizeof(uint32_t)));
+    PF_TRY(launch_mark_classes(np, nm, n_new, air_key, air_code, interp, nx, ny, nz, d_table, cap, d_count, 0));
+    std::vector<uint32_t> table(cap);
+    uint32_t count = 0;
+    PF_CUDA(cudaMemcpy(table.data(), d_table, cap * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    PF_CUDA(cudaMemcpy(&count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     s->class_keys.clear();
-    s->class_keys.push_back(0);                    // class 0: solid
-    s->class_keys.push_back((uint16_t)air_code);   // class 1: air
-    for (uint32_t k = 0; k < 65536; k++)
-      if (flags[k] && k != 0 && k != air_code) s->class_keys.push_back((uint16_t)k);
+    s->class_keys.push_back(0);          // class 0: solid
+    s->class_keys.push_back(air_key);    // class 1: air
+    std::vector<uint32_t> found;
+    for (uint32_t k : table) if (k != 0xffffffffu) found.push_back(k);
+    std::sort(found.begin(), found.end());
+    for (uint32_t k : found) s->class_keys.push_back(k);
     s->d_cls0 = nullptr;
-    if (s->class_keys.size() <= 256) {
-      std::vector<uint8_t> lut(65536, 0);
-      for (size_t c = 0; c < s->class_keys.size(); c++) lut[s->class_keys[c]] = (uint8_t)c;
-      PF_CUDA(cudaMemcpy(d_flags, lut.data(), 65536, cudaMemcpyHostToDevice));
+    if (count + 2 <= 256 && count < cap / 2) {
+      std::vector<uint8_t> ids(cap, 0);
+      for (uint32_t slot = 0; slot < cap; slot++)
+        if (table[slot] != 0xffffffffu)
+          ids[slot] = (uint8_t)(2 + (std::lower_bound(found.begin(), found.end(), table[slot]) - found.begin()));
+      PF_CUDA(cudaMemcpy(d_ids, ids.data(), cap, cudaMemcpyHostToDevice));
       PF_CUDA(cudaMalloc(&s->d_cls0, n_new));
-      PF_TRY(launch_assign_classes(np, nm, n_new, air_code, d_flags, s->d_cls0, 0));
+      PF_TRY(launch_assign_classes(np, nm, n_new, air_key, air_code, interp, nx, ny, nz, d_table, d_ids, cap, s->d_cls0, 0));
       PF_CUDA(cudaDeviceSynchronize());
       s->launch_count += 2;
+    } else {
+      s->class_keys.resize(2);
     }
-    PF_CUDA(cudaFree(d_flags));
+    PF_CUDA(cudaFree(d_table));
+    PF_CUDA(cudaFree(d_count));
+    PF_CUDA(cudaFree(d_ids));
   }
   s->d_pos0 = np; s->d_mat0 = nm;
   s->stage_device = device;
@@ -618,6 +650,14 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
   s->n_air = h_counts[0]; s->n_boundary = h_counts[1];
   if (dtype == PFDTD_F32) for (int i = 0; i < 4; i++) s->params[i] = (double)((const float*)params)[i];
   else for (int i = 0; i < 4; i++) s->params[i] = ((const double*)params)[i];
+  if (s->scheme == SCH_INTERP && !s->dcoef_user) {
+    // compact explicit family written so that the standard Courant numbers give exact
+    // binary fractions: IISO (a=1/6, b=0): d = lam2*(1/3, 1/6, 0), d4 = 2 - 4 lam2;  IWB (a=1/4, b=1/16):
+    // d = lam2*(1/4, 1/8, 1/16), d4 = 2 - 3.5 lam2
+    const double l2 = s->params[1];
+    if (element_type == PFDTD_IISO) { s->dcoef[0] = l2 / 3; s->dcoef[1] = l2 / 6; s->dcoef[2] = 0; s->dcoef[3] = 2 - 4 * l2; }
+    else { s->dcoef[0] = l2 / 4; s->dcoef[1] = l2 / 8; s->dcoef[2] = l2 / 16; s->dcoef[3] = 2 - 3.5 * l2; }
+  }
   s->n_unique = n_unique_materials;
   s->materials_host.assign((const unsigned char*)material_coefs,
                            (const unsigned char*)material_coefs + (size_t)n_unique_materials * 20 * esize(s));
@@ -705,8 +745,8 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
     if (p.cls) {
       const size_t nc = s->class_keys.size();
       PF_CUDA(cudaMalloc(&p.class_table, nc * class_entry_bytes(s->dtype)));
-      PF_CUDA(cudaMalloc(&p.d_class_keys, nc * sizeof(uint16_t)));
-      PF_CUDA(cudaMemcpy(p.d_class_keys, s->class_keys.data(), nc * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      PF_CUDA(cudaMalloc(&p.d_class_keys, nc * sizeof(uint32_t)));
+      PF_CUDA(cudaMemcpy(p.d_class_keys, s->class_keys.data(), nc * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     for (int b = 0; b < 2; b++) {
       PF_CUDA(cudaMalloc(&p.P[b], nelem * es));
@@ -729,11 +769,15 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
     // kernel choice
     const int nplanes = (int)p.size - 2;
     p.use_tma = (s->opt_kernel != KERNEL_PLAIN) && tma_supported((int)s->X, (int)s->Y, s->dtype) && nplanes >= 1 && p.cls != nullptr;
+    PF_CHECK(!(s->scheme == SCH_INTERP && p.cls == nullptr), PFDTD_ERR_INVALID,
+             "the interpolated schemes need <= 256 node classes (this mesh has more)");
     PF_CHECK(!(s->opt_kernel == KERNEL_TMA && !p.use_tma), PFDTD_ERR_INVALID,
              "TMA kernel requested but mesh %ux%u (slab of %lld slices, %zu node classes) is not supported by it", s->X, s->Y,
              (long long)p.size, s->class_keys.size());
     if (p.use_tma) {
-      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->X, (int)s->Y, nplanes, p.device, s->opt_tma_tile, s->opt_tma_chunk,
+      int64_t want_tile = s->opt_tma_tile;
+      if (s->scheme == SCH_INTERP && want_tile == 0) want_tile = 1;   // 128x8, one row per warp (profiles/r01_sweep.md)
+      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->X, (int)s->Y, nplanes, p.device, want_tile, s->opt_tma_chunk,
                              &p.cfg_full));
       PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->X, (int)s->Y, std::max(1, nplanes - 2), p.device,
                              p.cfg_full.tile + 1, s->opt_tma_chunk, &p.cfg_int));
@@ -1214,12 +1258,13 @@ int pfdtd_kernel_name(pfdtd_solver* s, char* buf, size_t buflen) {
   PF_CHECK(s && buf && buflen > 0, PFDTD_ERR_INVALID, "bad argument");
   if (s->parts.empty()) { snprintf(buf, buflen, "none"); return PFDTD_OK; }
   const Partition& p = s->parts[0];
+  const char* sch = s->scheme == SCH_CENTRED ? "centred" : s->scheme == SCH_INTERP ? (s->dcoef[2] != 0 ? "interp27+corners" : "interp27") : "forward";
+  const char* fam = s->scheme == SCH_INTERP ? "fdtd_update_interp" : "fdtd_update";
   if (p.use_tma)
-    snprintf(buf, buflen, "fdtd_update_tma<%s,%s> tile %s chunk %d", s->dtype == PFDTD_F32 ? "f32" : "f64",
-             s->scheme == SCH_CENTRED ? "centred" : "forward", tma_tile_name(s->dtype, p.cfg_full.tile), p.cfg_full.chunk);
+    snprintf(buf, buflen, "%s_tma<%s,%s> tile %s chunk %d", fam, s->dtype == PFDTD_F32 ? "f32" : "f64", sch,
+             tma_tile_name(s->dtype, p.cfg_full.tile), p.cfg_full.chunk);
   else
-    snprintf(buf, buflen, "fdtd_update_plain<%s,%s>", s->dtype == PFDTD_F32 ? "f32" : "f64",
-             s->scheme == SCH_CENTRED ? "centred" : "forward");
+    snprintf(buf, buflen, "%s_plain<%s,%s>", fam, s->dtype == PFDTD_F32 ? "f32" : "f64", sch);
   return PFDTD_OK;
 }
 

@@ -14,7 +14,8 @@ void set_error(const char* fmt, ...);
 
 // equation families: the reference's SRL_FORWARD and SHARED share the forward-difference boundary
 // (kernels3d.cu:485-606), SRL uses the centred-difference boundary (:608-665)
-enum : int { SCH_FORWARD = 0, SCH_CENTRED = 2 };
+// SCH_INTERP: the 27-point compact explicit family (IISO, IWB) with the forward-difference boundary
+enum : int { SCH_FORWARD = 0, SCH_CENTRED = 2, SCH_INTERP = 3 };
 
 #define PF_CUDA(call)                                                                          \
   do {                                                                                         \
@@ -45,10 +46,12 @@ int launch_pad_with_zeros(const uint8_t* d_old, uint8_t* d_new, uint32_t dx, uin
                           uint32_t nx, uint32_t ny, uint32_t nz, int skip_z0, cudaStream_t stream);
 int launch_translate_nodes(uint8_t* d_pos, uint8_t* d_mat, uint64_t n, int centred, unsigned long long* d_counts2,
                            cudaStream_t stream);
-// node classes: mark which (pos, mat) pairs occur (d_flags: 65536 bytes, zeroed by the caller), then
-// write the class byte volume through a 65536-entry key -> class LUT
-int launch_mark_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_code, uint8_t* d_flags, cudaStream_t stream);
-int launch_assign_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_code, const uint8_t* d_lut,
+// node classes: collect the distinct node keys (pos | mat << 8 | K12 << 16 | K8 << 20) in an open-addressing
+// table (d_table: cap slots preset to 0xffffffff), then write the class byte volume through it
+int launch_mark_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_key, uint32_t air_code, int interp,
+                        uint32_t X, uint32_t Y, uint32_t Z, uint32_t* d_table, uint32_t cap, uint32_t* d_count, cudaStream_t stream);
+int launch_assign_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_key, uint32_t air_code, int interp,
+                          uint32_t X, uint32_t Y, uint32_t Z, const uint32_t* d_table, const uint8_t* d_ids, uint32_t cap,
                           uint8_t* d_cls, cudaStream_t stream);
 
 // ---- update kernels (update_kernels.cu) ---------------------------------------------------------
@@ -72,6 +75,7 @@ struct UpdateArgs {
   const void* materials;   // device [n_coefs]
   uint32_t n_coefs;
   double params[4];        // lambda, lambda^2, 1/3, octave  (already rounded to the dtype)
+  double dcoef[4];         // SCH_INTERP: d1 (axial), d2 (edge), d3 (corner), d4 (centre) of the compact scheme
   int matidx_as_written;
   int X, Y;
   int z_begin, z_end;      // local planes [z_begin, z_end) are updated
@@ -86,11 +90,14 @@ struct TmaConfig { int tile; int chunk; };
 
 bool tma_supported(int X, int Y, int dtype);
 int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void* Pold, const uint8_t* cls, int X, int Y, int nz);
-int build_class_table(const UpdateArgs& a, const uint16_t* d_keys, int n_classes, void* d_table);
+int build_class_table(const UpdateArgs& a, const uint32_t* d_keys, int n_classes, void* d_table);
 size_t class_entry_bytes(int dtype);
 int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk, TmaConfig* out);
 int launch_update_tma(const UpdateArgs& a, const TmaMaps& maps, const TmaConfig& cfg);
 int launch_update_plain(const UpdateArgs& a);
+// 27-point kernels (interp_kernels.cu); the TMA variant shares TmaMaps / TmaConfig with the 7-point one
+int launch_update_interp_tma(const UpdateArgs& a, const TmaMaps& maps, const TmaConfig& cfg, int* occupancy_out);
+int launch_update_interp_plain(const UpdateArgs& a);
 const char* tma_tile_name(int dtype, int tile);
 
 // ---- source / receiver kernel (srcrec_kernels.cu) -------------------------------------------------

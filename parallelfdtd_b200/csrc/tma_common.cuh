@@ -1,0 +1,101 @@
+// tma_common.cuh -- device helpers shared by the TMA z-march kernels (update_kernels.cu: 7-point SRL,
+// interp_kernels.cu: 27-point IISO/IWB): mbarrier + cp.async.bulk.tensor wrappers, 128-bit shared/global
+// vector access, and the shared-memory stage geometry.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace pfdtd {
+namespace {
+
+constexpr int TX = 128;  // voxels per tile row: 32 lanes x 4 voxels
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], "
+      "[%5], %6;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+template <typename T> struct V4 { T v[4]; };
+
+__device__ __forceinline__ void lds4(const float* p, V4<float>& o) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  o.v[0] = t.x; o.v[1] = t.y; o.v[2] = t.z; o.v[3] = t.w;
+}
+__device__ __forceinline__ void lds4(const double* p, V4<double>& o) {
+  double2 a = *reinterpret_cast<const double2*>(p);
+  double2 b = *reinterpret_cast<const double2*>(p + 2);
+  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = b.x; o.v[3] = b.y;
+}
+__device__ __forceinline__ void stg4(float* p, const V4<float>& o) {
+  *reinterpret_cast<float4*>(p) = make_float4(o.v[0], o.v[1], o.v[2], o.v[3]);
+}
+__device__ __forceinline__ void stg4(double* p, const V4<double>& o) {
+  *reinterpret_cast<double2*>(p) = make_double2(o.v[0], o.v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(o.v[2], o.v[3]);
+}
+
+constexpr int align128(int x) { return (x + 127) & ~127; }
+
+template <typename T, int TY>
+struct TileGeom {
+  static constexpr int HX = 16 / (int)sizeof(T);           // x halo columns each side (16 B keeps rows 16-B aligned)
+  static constexpr int PW = TX + 2 * HX;                    // halo tile row pitch (elements)
+  static constexpr int PT_BYTES = (TY + 2) * PW * (int)sizeof(T);
+  static constexpr int PO_BYTES = TY * TX * (int)sizeof(T);
+  static constexpr int PS_BYTES = TY * TX;
+  static constexpr int PT_OFF = 0;
+  static constexpr int PO_OFF = align128(PT_BYTES);
+  static constexpr int PS_OFF = PO_OFF + align128(PO_BYTES);
+  static constexpr int STAGE_BYTES = PS_OFF + align128(PS_BYTES);
+};
+
+
+}  // namespace
+}  // namespace pfdtd

@@ -1,0 +1,26 @@
+// update_host.cuh -- host-side construction of the per-launch constants shared by the update kernels
+#pragma once
+#include <cmath>
+#include "pfdtd_internal.h"
+#include "update_math.cuh"
+
+namespace pfdtd {
+
+template <typename T>
+inline UpdConst<T> make_const(const UpdateArgs& a) {
+  UpdConst<T> c;
+  for (int i = 0; i < 4; i++) c.d[i] = (T)a.dcoef[i];
+  c.lam = (T)a.params[0];
+  c.lam2 = (T)a.params[1];
+  c.octave = (T)a.params[3];
+  // computed on the host with the same single-rounding fma the device would use
+  if (a.scheme == SCH_CENTRED) c.a_air = (T)std::fma((T)a.params[1], (T)-6, (T)2);
+  else c.a_air = (T)std::fma((T)6, -(T)a.params[1], (T)2);
+  c.materials = (const T*)a.materials;
+  c.n_coefs = a.n_coefs;
+  c.matidx_as_written = a.matidx_as_written;
+  return c;
+}
+
+
+}  // namespace pfdtd

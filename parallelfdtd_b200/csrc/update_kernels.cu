@@ -20,6 +20,8 @@
 //    TMA path does not cover and as an on-device cross-check.
 #include "pfdtd_internal.h"
 #include "update_math.cuh"
+#include "tma_common.cuh"
+#include "update_host.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -47,21 +49,6 @@ __global__ void __launch_bounds__(128) fdtd_update_plain(const uint8_t* __restri
   Pn[cur] = voxel_update<T, SCHEME>(ps, mat + cur, p, zp, zm, yp, ym, xp, xm, p_old, c);
 }
 
-template <typename T>
-static UpdConst<T> make_const(const UpdateArgs& a) {
-  UpdConst<T> c;
-  c.lam = (T)a.params[0];
-  c.lam2 = (T)a.params[1];
-  c.octave = (T)a.params[3];
-  // computed on the host with the same single-rounding fma the device would use
-  if (a.scheme == SCH_CENTRED) c.a_air = (T)std::fma((T)a.params[1], (T)-6, (T)2);
-  else c.a_air = (T)std::fma((T)6, -(T)a.params[1], (T)2);
-  c.materials = (const T*)a.materials;
-  c.n_coefs = a.n_coefs;
-  c.matidx_as_written = a.matidx_as_written;
-  return c;
-}
-
 template <typename T, int SCHEME>
 static int launch_plain_t(const UpdateArgs& a) {
   dim3 block(32, 4, 1);
@@ -81,97 +68,6 @@ int launch_update_plain(const UpdateArgs& a) {
 // =====================================================================================================
 // TMA z-march kernel
 // =====================================================================================================
-namespace {
-
-constexpr int TX = 128;  // voxels per tile row: 32 lanes x 4 voxels
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar,
-                                                 uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], "
-      "[%5], %6;" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-
-template <typename T> struct V4 { T v[4]; };
-
-__device__ __forceinline__ void lds4(const float* p, V4<float>& o) {
-  float4 t = *reinterpret_cast<const float4*>(p);
-  o.v[0] = t.x; o.v[1] = t.y; o.v[2] = t.z; o.v[3] = t.w;
-}
-__device__ __forceinline__ void lds4(const double* p, V4<double>& o) {
-  double2 a = *reinterpret_cast<const double2*>(p);
-  double2 b = *reinterpret_cast<const double2*>(p + 2);
-  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = b.x; o.v[3] = b.y;
-}
-__device__ __forceinline__ void stg4(float* p, const V4<float>& o) {
-  *reinterpret_cast<float4*>(p) = make_float4(o.v[0], o.v[1], o.v[2], o.v[3]);
-}
-__device__ __forceinline__ void stg4(double* p, const V4<double>& o) {
-  *reinterpret_cast<double2*>(p) = make_double2(o.v[0], o.v[1]);
-  *reinterpret_cast<double2*>(p + 2) = make_double2(o.v[2], o.v[3]);
-}
-
-constexpr int align128(int x) { return (x + 127) & ~127; }
-
-template <typename T, int TY>
-struct TileGeom {
-  static constexpr int HX = 16 / (int)sizeof(T);           // x halo columns each side (16 B keeps rows 16-B aligned)
-  static constexpr int PW = TX + 2 * HX;                    // halo tile row pitch (elements)
-  static constexpr int PT_BYTES = (TY + 2) * PW * (int)sizeof(T);
-  static constexpr int PO_BYTES = TY * TX * (int)sizeof(T);
-  static constexpr int PS_BYTES = TY * TX;
-  static constexpr int PT_OFF = 0;
-  static constexpr int PO_OFF = align128(PT_BYTES);
-  static constexpr int PS_OFF = PO_OFF + align128(PO_BYTES);
-  static constexpr int STAGE_BYTES = PS_OFF + align128(PS_BYTES);
-};
-
-}  // namespace
-
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: (TY/RPW + 1) warps (last warp = TMA producer)
 template <typename T, int SCHEME, int TY, int RPW, int NST>
 __global__ void __launch_bounds__((TY / RPW + 1) * 32)
@@ -343,11 +239,12 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
 
 // builds the per-class table with the device arithmetic of update_math.cuh (one thread per class)
 template <typename T, int SCHEME>
-__global__ void build_class_table_kernel(const uint16_t* __restrict__ keys, int n_classes, UpdConst<T> c, ClassEntry<T>* __restrict__ out) {
+__global__ void build_class_table_kernel(const uint32_t* __restrict__ keys, int n_classes, UpdConst<T> c, ClassEntry<T>* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_classes) return;
   const uint32_t key = keys[i];
-  out[i] = make_class_entry<T, SCHEME>(key & 0xffu, key >> 8, c);
+  if (SCHEME == SCH_INTERP) out[i] = make_class_entry_interp<T>(key & 0xffu, (key >> 8) & 0xffu, (key >> 16) & 0xfu, (key >> 20) & 0xfu, c);
+  else out[i] = make_class_entry<T, SCHEME>(key & 0xffu, (key >> 8) & 0xffu, c);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -482,7 +379,12 @@ int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device
   probe.scheme = scheme;
   TmaMaps dummy{};
   int occ = 0;
-  PF_TRY(dispatch(probe, dummy, tile, 1, &occ));
+  if (scheme == SCH_INTERP) {
+    TmaConfig pc{tile, 1};
+    PF_TRY(launch_update_interp_tma(probe, dummy, pc, &occ));
+  } else {
+    PF_TRY(dispatch(probe, dummy, tile, 1, &occ));
+  }
   PF_CHECK(occ >= 1, PFDTD_ERR_CUDA, "TMA kernel variant %d does not fit on an SM", tile);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -516,9 +418,15 @@ int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device
   return PFDTD_OK;
 }
 
-int build_class_table(const UpdateArgs& a, const uint16_t* d_keys, int n_classes, void* d_table) {
+int build_class_table(const UpdateArgs& a, const uint32_t* d_keys, int n_classes, void* d_table) {
   if (n_classes <= 0) return PFDTD_OK;
   const int th = 64, bl = (n_classes + th - 1) / th;
+  if (a.scheme == SCH_INTERP) {
+    if (a.dtype == PFDTD_F32) build_class_table_kernel<float, SCH_INTERP><<<bl, th, 0, a.stream>>>(d_keys, n_classes, make_const<float>(a), (ClassEntry<float>*)d_table);
+    else build_class_table_kernel<double, SCH_INTERP><<<bl, th, 0, a.stream>>>(d_keys, n_classes, make_const<double>(a), (ClassEntry<double>*)d_table);
+    PF_CUDA(cudaGetLastError());
+    return PFDTD_OK;
+  }
   if (a.dtype == PFDTD_F32) {
     if (a.scheme == SCH_CENTRED) build_class_table_kernel<float, SCH_CENTRED><<<bl, th, 0, a.stream>>>(d_keys, n_classes, make_const<float>(a), (ClassEntry<float>*)d_table);
     else build_class_table_kernel<float, SCH_FORWARD><<<bl, th, 0, a.stream>>>(d_keys, n_classes, make_const<float>(a), (ClassEntry<float>*)d_table);

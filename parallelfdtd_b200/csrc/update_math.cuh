@@ -35,6 +35,7 @@ struct UpdConst {
   T lam2;         // params[1]
   T octave;       // params[3]
   T a_air;        // forward:  fma(6, -lam2, 2)     centred: fma(lam2, -6, 2)
+  T d[4];         // interpolated schemes: d1 axial, d2 edge, d3 corner, d4 centre weights
   const T* materials;      // [n_unique][20] admittances on this device
   uint32_t n_coefs;        // entries in `materials` (index is clamped; the reference would read out of bounds)
   int matidx_as_written;   // forward kernel only, kernels3d.cu:513
@@ -152,6 +153,48 @@ __device__ __forceinline__ ClassEntry<T> make_class_entry(uint32_t pos, uint32_t
     e.c2 = Ar<T>::mul(sw, Ar<T>::rcp(Ar<T>::fma(t, (T)0.5, (T)1)));
   }
   return e;
+}
+
+// ---- interpolated (27-point) compact schemes: IISO, IWB (not in the reference) ---------
+//   p_new = sw/(1+beta) * ( d1*A6 + d2*A12 + d3*A8 + c0*p - (1-beta)*p_old )
+//   A6/A12/A8 = sums over the axial / edge / corner neighbours (solid voxels hold 0),
+//   c0 = d4 + d1*(6-K6) + d2*(12-K12) + d3*(8-K8): a missing (solid) neighbour is replaced by the centre
+//   value -- the rigid-wall mirror that turns (2 - 6 lam2) into (2 - K lam2) in the reference's SRL kernel --
+//   beta = 0.5*Y*(6-K6)*lam: the reference's forward-difference admittance loss (kernels3d.cu:514-528).
+//   With (d1,d2,d3,d4) = (lam2, 0, 0, 2-6 lam2) this IS the reference's SRL_FORWARD equation.
+template <typename T>
+__device__ __forceinline__ ClassEntry<T> make_class_entry_interp(uint32_t pos, uint32_t m, uint32_t k12, uint32_t k8, const UpdConst<T>& c) {
+  ClassEntry<T> e;
+  e.flags = pos;
+  const T sw = (T)(pos >> 7);
+  if (pos == 0u) m = 0u;
+  const T K = (T)(pos & 0x7Fu);
+  const uint32_t idx = m * 20u + (uint32_t)c.octave;
+  const T t = Ar<T>::mul(Ar<T>::mul(load_coef(c, idx), Ar<T>::add((T)6, -K)), c.lam);
+  T c0 = Ar<T>::fma(c.d[0], Ar<T>::add((T)6, -K), c.d[3]);
+  c0 = Ar<T>::fma(c.d[1], (T)(12u - k12), c0);
+  c0 = Ar<T>::fma(c.d[2], (T)(8u - k8), c0);
+  e.c0 = c0;
+  e.c1 = -Ar<T>::fma(t, (T)-0.5, (T)1);
+  e.c2 = Ar<T>::mul(sw, Ar<T>::rcp(Ar<T>::fma(t, (T)0.5, (T)1)));
+  return e;
+}
+// in-plane partial sums of one voxel: a4 = ((x- + x+) + y-) + y+ ; g4 = ((x-y- + x+y-) + x-y+) + x+y+
+template <typename T>
+__device__ __forceinline__ T interp_a4(T xm, T xp, T ym, T yp) { return Ar<T>::add(Ar<T>::add(Ar<T>::add(xm, xp), ym), yp); }
+template <typename T>
+__device__ __forceinline__ T interp_g4(T mm, T pm, T mp, T pp) { return Ar<T>::add(Ar<T>::add(Ar<T>::add(mm, pm), mp), pp); }
+// combine the partial sums of planes z-1, z, z+1:  A6 = (a4 + c-) + c+ ; A12 = (g4 + a4-) + a4+ ; A8 = g4- + g4+
+template <typename T, bool HAS_D3>
+__device__ __forceinline__ T voxel_interp(T c0, T c1, T c2, T p, T a4, T g4, T c_m, T a4_m, T g4_m, T c_p, T a4_p, T g4_p, T p_old,
+                                          T d1, T d2, T d3) {
+  const T A6 = Ar<T>::add(Ar<T>::add(a4, c_m), c_p);
+  const T A12 = Ar<T>::add(Ar<T>::add(g4, a4_m), a4_p);
+  T inner = Ar<T>::fma(A6, d1, Ar<T>::mul(p, c0));
+  inner = Ar<T>::fma(A12, d2, inner);
+  if (HAS_D3) inner = Ar<T>::fma(Ar<T>::add(g4_m, g4_p), d3, inner);
+  inner = Ar<T>::fma(p_old, c1, inner);
+  return Ar<T>::mul(c2, inner);
 }
 
 // forward, any class: identical bits to voxel_forward (air: c1 = -1, c2 = 1, multiplying by 1 is exact)

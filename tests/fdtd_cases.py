@@ -72,7 +72,35 @@ def source_table(case):
     return tab
 
 
+def interp_cases():
+    """Interpolated 27-point schemes (IISO = 3, IWB = 4): not in the reference, checked against our own oracle."""
+    return [
+        make_case("iiso_shoebox_48x40x49_f32_6mat", (48, 40, 49), 3, False, 300, 6, 2, _SRC3, _REC3, input_data=_DATA),
+        make_case("iwb_shoebox_48x40x49_f64_6mat", (48, 40, 49), 4, True, 300, 6, 3, _SRC3, _REC3, input_data=_DATA),
+        make_case("iiso_hall_96x128x64_f64_5mat_oct1", (96, 128, 64), 3, True, 200, 5, 1, [(40, 20, 20, 0, 0, 0)],
+                  [(50, 60, 30), (20, 100, 40)], geometry="hall", octave=1),
+        make_case("iwb_hall_96x128x64_f32_5mat", (96, 128, 64), 4, False, 200, 5, 2, [(40, 20, 20, 0, 0, 0)],
+                  [(50, 60, 30), (20, 100, 40)], geometry="hall"),
+    ]
+
+
+def lam_of(case):
+    return oracle.interp_lambda(case["update_type"]) if case["update_type"] >= 3 else LAM
+
+
+def params_of(case, for_oracle):
+    """4-entry reference parameter vector; the oracle's interpolated path takes 4 more (d1..d4)."""
+    lam = lam_of(case)
+    prm = oracle.params(lam, case["octave"], case["double"])
+    if case["update_type"] >= 3 and for_oracle:
+        d = case.get("dcoef") or oracle.interp_coefficients(case["update_type"], float(prm[1]))
+        return oracle.params_interp(lam, case["octave"], d, case["double"])
+    return prm
+
+
 def scheme_of(case):
+    if case["update_type"] >= 3:
+        return 3
     if case["double"]:
         return 0 if case["update_type"] in (0, 1) else 2          # setupMeshDouble, cudaMesh.cu:134-137
     return 0 if case["update_type"] in (0, 1, 3) else 2           # setupMesh, cudaMesh.cu:70-73
@@ -81,7 +109,9 @@ def scheme_of(case):
 def run_oracle(case, n_parts=None, matidx=1, soft=0, double_pad=False):
     pos, mat, air, bnd = oracle.setup_mesh(case["bid"], case["mat"], case["block"], case["update_type"], case["double"],
                                            double_pad)
-    prm = oracle.params(LAM, case["octave"], case["double"])
+    prm = params_of(case, True)
+    if case["update_type"] >= 3:
+        matidx = 0          # the new schemes index the material table as intended (mat*20 + octave)
     src = np.asarray(case["sources"], dtype=np.int32).reshape(-1, 6)
     r, secs = oracle.run(pos, mat, scheme_of(case), prm, case["materials"], src[:, :3], src[:, 3], source_table(case),
                          case["receivers"], case["steps"], n_parts or case["n_parts"], matidx, soft)
@@ -96,7 +126,9 @@ def run_ours(capi, case, n_parts=None, kernel=None, matidx=1, opts=(), devices=N
         for k, v in opts:
             s.set_option(k, v)
         dt = capi.F64 if case["double"] else capi.F32
-        prm = oracle.params(LAM, case["octave"], case["double"])
+        prm = params_of(case, False)
+        if case.get("dcoef"):
+            s.set_scheme_coefficients(case["dcoef"])
         s.setup_mesh(case["bid"], case["mat"], case["block"], case["update_type"], dt, prm, case["materials"])
         n = n_parts or case["n_parts"]
         s.make_partition(n, devices or [0] * n)

@@ -1,0 +1,77 @@
+"""CPU: the oracle's interpolated 27-point schemes (IISO / IWB).  The reference does not contain them
+ -- parity unpinned -- so the anchors are: (1) with the SRL weights the equation IS the
+pinned SRL_FORWARD update, (2) the standard weights satisfy the consistency condition
+6 d1 + 12 d2 + 8 d3 + d4 = 2, (3) rigid rooms neither gain nor lose energy at the stability limit,
+(4) slab count does not change results, (5) wave speed: first arrival along an axis after distance/lambda steps."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from parallelfdtd_b200 import synth
+from tests import fdtd_cases as fc
+
+
+@pytest.mark.parametrize("ut", [3, 4])
+def test_weights_are_consistent(ut):
+    lam = oracle.interp_lambda(ut)
+    d = oracle.interp_coefficients(ut, lam * lam)
+    assert abs(6 * d[0] + 12 * d[1] + 8 * d[2] + d[3] - 2) < 1e-15
+    assert np.allclose(d, [0.25, 0.125, 0.0, -1.0] if ut == 3 else [0.25, 0.125, 0.0625, -1.5], rtol=0, atol=1e-15)
+    # in float the squared Courant number is exact (0.75 / 1.0), so the weights are exact binary fractions
+    d32 = oracle.interp_coefficients(ut, np.float32(lam * lam))
+    assert d32 == ([0.25, 0.125, 0.0, -1.0] if ut == 3 else [0.25, 0.125, 0.0625, -1.5])
+
+
+@pytest.mark.parametrize("double", [False, True])
+def test_srl_weights_reproduce_the_pinned_forward_scheme(double):
+    bid, mat = synth.shoebox((24, 20, 22), 3)
+    pos, m, _, _ = oracle.setup_mesh(bid, mat, (8, 4, 1), 0, double)
+    prm = oracle.params(fc.LAM, 0, double)
+    tab = synth.material_table([0.9, 0.8, 0.7])
+    steps = 200
+    src = oracle.source_samples(1, steps, double=double)
+    a, _ = oracle.run(pos, m, 0, prm, tab, [(8, 8, 8)], [0], src, [(15, 12, 10), (3, 3, 3)], steps, 1, 0)
+    # 2 - 6*lam2 with ONE rounding, as the reference's contracted fma computes it (exact in double for a float lam2)
+    d = [float(prm[1]), 0.0, 0.0, float(2 - 6 * np.float64(prm[1]))]
+    b, _ = oracle.run(pos, m, 3, oracle.params_interp(fc.LAM, 0, d, double), tab, [(8, 8, 8)], [0], src, [(15, 12, 10), (3, 3, 3)], steps, 1, 0)
+    assert np.abs(a).max() > 0
+    # same equation, different summation order of the six axial taps: rounding-level agreement
+    assert fc.rel_l2(b, a) < (1e-12 if double else 2e-5)
+
+
+@pytest.mark.parametrize("ut", [3, 4])
+def test_rigid_room_is_stable_and_lossless(ut):
+    bid, mat = synth.shoebox((20, 18, 16), 1)
+    pos, m, _, _ = oracle.setup_mesh(bid, mat, (4, 2, 1), 0, True)
+    lam = oracle.interp_lambda(ut)
+    p8 = oracle.params_interp(lam, 0, oracle.interp_coefficients(ut, lam * lam), True)
+    tab = np.zeros((1, 20))                                   # Y = 0: rigid walls
+    steps = 3000
+    g = oracle.source_samples(1, steps, double=True)          # gaussian pulse
+    src = np.zeros(steps)
+    src[1:] = np.diff(g)                                      # zero-mean (a net injected volume would excite the linear-in-time DC mode)
+    src[80:] = 0                                              # accumulate for 80 steps, then leave the node free
+    r, _ = oracle.run(pos, m, 3, p8, tab, [(7, 8, 6)], [1], src, [(12, 9, 8), (4, 4, 4)], steps, 1, 0, 1)
+    early = np.abs(r[:, 100:600]).max()
+    late = np.abs(r[:, -500:]).max()
+    assert np.isfinite(r).all() and early > 0
+    assert 0.2 * early < late < 5 * early                     # no blow-up, no decay
+
+
+@pytest.mark.parametrize("ut", [3, 4])
+def test_partition_invariance_and_first_arrival(ut):
+    bid, mat = synth.shoebox((40, 24, 49), 6)
+    pos, m, _, _ = oracle.setup_mesh(bid, mat, (8, 4, 1), 0, False)
+    lam = oracle.interp_lambda(ut)
+    p8 = oracle.params_interp(lam, 0, oracle.interp_coefficients(ut, np.float32(lam * lam)), False)
+    tab = synth.material_table(list(np.linspace(0.99, 0.5, 6)))
+    steps = 120
+    src = oracle.source_samples(0, steps)
+    rx = [(20, 12, 5), (20, 12, 23), (20, 12, 24), (30, 12, 24)]
+    base, _ = oracle.run(pos, m, 3, p8, tab, [(20, 12, 24)], [0], src, rx, steps, 1, 0)
+    for n in (2, 5, 7):
+        r, _ = oracle.run(pos, m, 3, p8, tab, [(20, 12, 24)], [0], src, rx, steps, n, 0)
+        assert np.array_equal(r, base), n
+    # a 27-point stencil reaches a node 10 voxels away along x after 10 updates (impulse at step 1 -> response index 10)
+    first = np.flatnonzero(base[3] != 0)[0]
+    assert first == 10

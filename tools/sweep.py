@@ -27,7 +27,7 @@ dt = capi.F64 if double else capi.F32
 npdt = np.float64 if double else np.float32
 bid, mat = synth.shoebox(dims, 6)
 tab = synth.material_table(list(np.linspace(0.99, 0.5, 6))).astype(npdt)
-lam = float(np.sqrt(1 / 3))
+lam = float(np.sqrt(1 / 3)) if a.update_type < 3 else (float(np.sqrt(3.0) / 2) if a.update_type == 3 else 1.0)
 prm = np.array([lam, lam * lam, 1 / 3, 0], dtype=npdt)
 bpv = 25 if double else 13
 for spec in a.sets.split(";"):
