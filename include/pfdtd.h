@@ -75,7 +75,13 @@ enum {
   PFDTD_OPT_TIME_KERNELS = 11,
   /* L2 cache hints on the TMA loads: bit0 = evict_first for operands read once per step (P_old,
    * node bytes), bit1 = evict_last for P (shared with neighbouring tiles).  Default 0. */
-  PFDTD_OPT_TMA_HINTS = 12
+  PFDTD_OPT_TMA_HINTS = 12,
+  /* Frequency-dependent boundaries (digital impedance filters; not in the reference -- its `dif_` members are a
+   * stub, cudaMesh.h:88,122-123).  N > 0 (<= 4): row m of the material table is read as the IIR admittance of
+   * material m, [b0 .. bN, a1 .. aN] (a0 = 1), the octave index is ignored, and every boundary node carries N
+   * filter states updated in the same kernel pass.  N = 0 (default): the reference's scalar admittance
+   * materials[m*20 + octave].  Order-0 filters reproduce that path bit for bit.  Set before pfdtd_make_partition. */
+  PFDTD_OPT_DIF_ORDER = 13
 };
 
 typedef int (*pfdtd_interrupt_cb)(void);                      /* kernels3d.h: bool (*)(void) */

@@ -168,13 +168,66 @@ inline T update_interp(const uint8_t* pos, const uint8_t* mat, const T* P, int64
   return c2 * inner;
 }
 
+// Digital impedance filter boundary (frequency-dependent admittance).  NOT in the reference (its dif_ members
+// are a stub, cudaMesh.h:88,122-123): "parity unpinned"; restates csrc/update_math.cuh "digital impedance filters".
+// Material row = [b0..bN, a1..aN]; val0 = the frequency-independent update evaluated with Y = b0; st = the voxel's
+// N transposed-direct-form-II states (stride `stride`).  Returns p_new and advances the states.
+template <typename T>
+inline T dif_voxel(uint8_t pos, uint8_t mat, int scheme, T val0, T p_old, const T* params, const T* materials, int order, T* st,
+                   int64_t stride) {
+  const T* row = materials + (size_t)(pos == 0 ? 0 : mat) * 20;
+  const T b0 = row[0];
+  const T sw = (T)(pos >> 7);
+  T kap, rc;
+  if (scheme == 2) {
+    const T dsum = (T)((pos & 1) + ((pos >> 1) & 1) + ((pos >> 2) & 1));
+    kap = params[0] * dsum;
+    rc = sw * ((T)1 / FMA(b0 * params[0], dsum, (T)1));
+  } else {
+    const T K = (T)(pos & 0x7F);
+    kap = ((T)0.5 * ((T)6 - K)) * params[0];
+    const T t = (b0 * ((T)6 - K)) * params[0];
+    rc = sw * ((T)1 / FMA(t, (T)0.5, (T)1));
+  }
+  const T c3 = kap * rc;
+  T s[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < order; i++) s[i] = st[i * stride];
+  const T p_new = FMA(-c3, s[0], val0);
+  const T u = p_new + (-p_old);
+  const T y = FMA(b0, u, s[0]);
+  for (int i = 0; i < order; i++) st[i * stride] = FMA(row[1 + i], u, FMA(-row[1 + order + i], y, s[i + 1]));
+  return p_new;
+}
+inline bool is_lossy(uint8_t pos, int scheme) { return scheme == 2 ? (pos & 7) != 0 : (pos != 0 && (pos & 0x7F) < 6); }
+
 // One launch of the update kernel over a slab: local slices 1..nz-2 of `Q` (the past field) are
 // overwritten with the next field (kernels3d.cu:109-153: grid.z = slab slices - 2, pointers offset
 // by one slice).  pos/mat point at the slab's first slice.
 template <typename T>
 void update_slab(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int64_t nz, int scheme, const T* params,
-                 const T* materials, int matidx_mode, const T* P, T* Q) {
+                 const T* materials, int matidx_mode, const T* P, T* Q, int dif_order = 0, T* dif_state = nullptr) {
   const int64_t XY = X * Y;
+  const int64_t nvox = nz * XY;
+  if (dif_order > 0) {
+    // filters on: the scalar admittance of material m is its b0 = materials[m*20] (octave ignored)
+    T prm[8];
+    for (int i = 0; i < 8; i++) prm[i] = (scheme >= 3 || i < 4) ? params[i] : (T)0;
+    prm[3] = (T)0;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int64_t z = 1; z < nz - 1; z++)
+      for (int64_t y = 0; y < Y; y++)
+        for (int64_t x = 0; x < X; x++) {
+          const int64_t e = z * XY + y * X + x;
+          const T p_old = Q[e];
+          T v;
+          if (scheme >= 3) v = update_interp<T>(pos, mat, P, x, y, z, X, Y, p_old, prm, materials, params + 4);
+          else if (scheme == 2) v = update_centred<T>(pos[e], mat[e], P, e, X, XY, p_old, prm, materials);
+          else v = update_forward<T>(pos[e], mat[e], P, e, X, XY, p_old, prm, materials, 0);
+          if (is_lossy(pos[e], scheme)) v = dif_voxel<T>(pos[e], mat[e], scheme, v, p_old, prm, materials, dif_order, dif_state + e, nvox);
+          Q[e] = v;
+        }
+    return;
+  }
   if (scheme >= 3) {   // interpolated: params[4..7] = d1..d4
 #pragma omp parallel for collapse(2) schedule(static)
     for (int64_t z = 1; z < nz - 1; z++)
@@ -211,10 +264,12 @@ template <typename T>
 double run_sim(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int64_t Z, int scheme,
                const T* params, const T* materials, int matidx_mode, int soft_mode, int n_parts,
                int n_src, const int32_t* src_xyz, const int32_t* src_type, const T* src_samples,
-               int n_rec, const int32_t* rec_xyz, int64_t steps, T* out, int timed_from_step) {
+               int n_rec, const int32_t* rec_xyz, int64_t steps, T* out, int timed_from_step, int dif_order = 0) {
   const int64_t XY = X * Y;
   std::vector<Slab> slabs = partition_indexing(Z, n_parts);
-  std::vector<std::vector<T>> Pc(n_parts), Pp(n_parts);
+  std::vector<std::vector<T>> Pc(n_parts), Pp(n_parts), Ds(n_parts);
+  if (dif_order > 0)
+    for (int k = 0; k < n_parts; k++) Ds[k].assign((size_t)dif_order * slabs[k].size * XY, (T)0);
   for (int k = 0; k < n_parts; k++) {
     // +1+dimX slack like the reference (cudaMesh.h:735)
     Pc[k].assign(slabs[k].size * XY + 1 + X, (T)0);
@@ -241,7 +296,7 @@ double run_sim(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int
     // (2) update local slices 1..size-2 of every slab (kernels3d.cu:109-153)
     for (int k = 0; k < n_parts; k++)
       update_slab<T>(pos + slabs[k].first * XY, mat + slabs[k].first * XY, X, Y, slabs[k].size, scheme, params, materials,
-                     matidx_mode, cur[k], past[k]);
+                     matidx_mode, cur[k], past[k], dif_order, dif_order > 0 ? Ds[k].data() : nullptr);
     // (3) flip (kernels3d.cu:160)
     for (int k = 0; k < n_parts; k++) std::swap(cur[k], past[k]);
     // (4) halos (kernels3d.cu:161, cudaMesh.h:432-463)
@@ -361,6 +416,19 @@ double pfo_run_f32(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y,
                    const int32_t* rec_xyz, int64_t steps, float* out, int timed_from_step) {
   return run_sim<float>(pos, mat, X, Y, Z, scheme, params, materials, matidx_mode, soft_mode, n_parts, n_src, src_xyz,
                         src_type, src_samples, n_rec, rec_xyz, steps, out, timed_from_step);
+}
+// same with digital-impedance-filter boundaries of order dif_order (material rows = [b0..bN, a1..aN])
+double pfo_run_dif_f32(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int64_t Z, int scheme,
+                       const float* params, const float* materials, int dif_order, int n_parts, int n_src, const int32_t* src_xyz,
+                       const int32_t* src_type, const float* src_samples, int n_rec, const int32_t* rec_xyz, int64_t steps, float* out) {
+  return run_sim<float>(pos, mat, X, Y, Z, scheme, params, materials, 0, 0, n_parts, n_src, src_xyz, src_type, src_samples, n_rec,
+                        rec_xyz, steps, out, 0, dif_order);
+}
+double pfo_run_dif_f64(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int64_t Z, int scheme,
+                       const double* params, const double* materials, int dif_order, int n_parts, int n_src, const int32_t* src_xyz,
+                       const int32_t* src_type, const double* src_samples, int n_rec, const int32_t* rec_xyz, int64_t steps, double* out) {
+  return run_sim<double>(pos, mat, X, Y, Z, scheme, params, materials, 0, 0, n_parts, n_src, src_xyz, src_type, src_samples, n_rec,
+                         rec_xyz, steps, out, 0, dif_order);
 }
 double pfo_run_f64(const uint8_t* pos, const uint8_t* mat, int64_t X, int64_t Y, int64_t Z, int scheme,
                    const double* params, const double* materials, int matidx_mode, int soft_mode, int n_parts,

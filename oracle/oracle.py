@@ -153,6 +153,28 @@ def step_slab(pos, mat, scheme, params_v, materials, cur, past, matidx_as_writte
     return new
 
 
+def run_dif(pos, mat, scheme, params_v, materials, dif_order, src_xyz, src_type, src_samples, rec_xyz, steps, n_parts=1):
+    """run() with digital-impedance-filter boundaries: materials rows are [b0..bN, a1..aN]."""
+    double = params_v.dtype == np.float64
+    dt = np.float64 if double else np.float32
+    Z, Y, X = pos.shape
+    materials = np.ascontiguousarray(materials, dtype=dt)
+    assert materials.ndim == 2 and materials.shape[1] == 20 and 2 * dif_order + 1 <= 20
+    src_xyz = np.ascontiguousarray(src_xyz, dtype=np.int32).reshape(-1, 3)
+    src_type = np.ascontiguousarray(src_type, dtype=np.int32).reshape(-1)
+    rec_xyz = np.ascontiguousarray(rec_xyz, dtype=np.int32).reshape(-1, 3)
+    n_src, n_rec = src_xyz.shape[0], rec_xyz.shape[0]
+    src_samples = np.ascontiguousarray(src_samples, dtype=dt).reshape(n_src, steps) if n_src else np.zeros((0, steps), dt)
+    out = np.zeros((n_rec, steps), dtype=dt)
+    L = lib()
+    fn = L.pfo_run_dif_f64 if double else L.pfo_run_dif_f32
+    fn.restype = C.c_double
+    secs = fn(_p(pos), _p(mat), C.c_int64(X), C.c_int64(Y), C.c_int64(Z), C.c_int(scheme), _p(params_v), _p(materials),
+              C.c_int(dif_order), C.c_int(n_parts), C.c_int(n_src), _p(src_xyz), _p(src_type), _p(src_samples), C.c_int(n_rec),
+              _p(rec_xyz), C.c_int64(steps), _p(out))
+    return out, secs
+
+
 def source_samples(input_type, steps, fs=7000, data=None, double=False, transparent=False, grid_ir=None):
     """SimulationParameters::getSourceSample[Double] for steps 0..steps-1."""
     dt = np.float64 if double else np.float32

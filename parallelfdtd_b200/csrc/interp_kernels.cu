@@ -54,17 +54,19 @@ __device__ __forceinline__ void load_plane(const T* __restrict__ pt, int r, int 
 }  // namespace
 
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: TY consumer warps (one tile row each) + 1 producer warp
-template <typename T, bool HAS_D3, int TY, int NST>
+template <typename T, bool HAS_D3, int TY, int NST, bool DIF>
 __global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 : 2) : (TY == 8 ? 2 : 1))
     fdtd_update_interp_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                            const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
-                           T* __restrict__ Pn, T d1, T d2, T d3, T d4, int X, int Y, int z_begin, int z_end, int chunk) {
+                           T* __restrict__ Pn, T d1, T d2, T d3, T d4, int X, int Y, int z_begin, int z_end, int chunk,
+                           const DifArgs<T> dif) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[NST];
   __shared__ __align__(8) uint64_t bar_empty[NST];
   __shared__ ClassEntry<T> s_table[256];
+  __shared__ DifEntry<T> s_dif[DIF ? 64 : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 :
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   for (int i = threadIdx.x; i < n_classes; i += blockDim.x) s_table[i] = g_table[i];
+  if (DIF) for (int i = threadIdx.x; i < dif.n_dif; i += blockDim.x) s_dif[i] = dif.table[i];
   __syncthreads();
 
   if (warp == NW) {
@@ -129,6 +132,8 @@ __global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 :
   for (int j = 0; j < n; j++) {
     const int i2 = j + 2;
     const int s2 = i2 % NST;
+    uint32_t seg_base = 0;
+    if (DIF && gy < Y) seg_base = __ldg(dif.rowbase + ((size_t)(z_lo + j) * Y + gy) * dif.segs + blockIdx.x);
     mbar_wait(&bar_full[s2], (uint32_t)((i2 / NST) & 1));
     const unsigned char* st2 = smem_raw + (size_t)s2 * G::STAGE_BYTES;
     load_plane<T, TY, HAS_D3>(reinterpret_cast<const T*>(st2 + G::PT_OFF), r, lane, pp);
@@ -139,8 +144,8 @@ __global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 :
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_empty[s2]);
 
+    V4<T> res;
     if (active) {
-      V4<T> res;
       if (pw == AIR4) {
 #pragma unroll
         for (int q = 0; q < 4; q++)
@@ -154,8 +159,9 @@ __global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 :
                                              pp.a4[q], pp.g4[q], old.v[q], d1, d2, d3);
         }
       }
-      stg4(Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx, res);
     }
+    if (DIF) dif_apply_row<T>(res.v, old.v, pw, active, lane, seg_base, dif, s_dif);
+    if (active) stg4(Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx, res);
     pm = pc;
     pc = pp;
   }
@@ -190,9 +196,9 @@ __global__ void __launch_bounds__(128) fdtd_update_interp_plain(const uint8_t* _
 
 namespace {
 
-template <typename T, bool HAS_D3, int TY, int NST>
+template <typename T, bool HAS_D3, int TY, int NST, bool DIF>
 int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupancy_out) {
-  auto kern = fdtd_update_interp_tma<T, HAS_D3, TY, NST>;
+  auto kern = fdtd_update_interp_tma<T, HAS_D3, TY, NST, DIF>;
   const int smem = NST * TileGeom<T, TY>::STAGE_BYTES;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -210,7 +216,7 @@ int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occup
   dim3 grid((a.X + TX - 1) / TX, (a.Y + TY - 1) / TY, (nplanes + chunk - 1) / chunk);
   const UpdConst<T> c = make_const<T>(a);
   kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.cls, (const ClassEntry<T>*)a.class_table, a.n_classes, (T*)a.Pn, c.d[0],
-                                          c.d[1], c.d[2], c.d[3], a.X, a.Y, a.z_begin, a.z_end, chunk);
+                                          c.d[1], c.d[2], c.d[3], a.X, a.Y, a.z_begin, a.z_end, chunk, make_dif<T>(a));
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }
@@ -218,9 +224,15 @@ int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occup
 template <typename T, bool HAS_D3>
 int dispatch_interp(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
   // tile variants shared with the 7-point kernel: only the one-row-per-warp shapes apply here
+  if (a.dif_order > 0) {
+    switch (tile) {
+      case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, true>(a, m, chunk, occ);
+      case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4, true>(a, m, chunk, occ);
+    }
+  }
   switch (tile) {
-    case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4>(a, m, chunk, occ);
-    case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4>(a, m, chunk, occ);
+    case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, false>(a, m, chunk, occ);
+    case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4, false>(a, m, chunk, occ);
   }
   set_error("tile variant %d is not available for the interpolated schemes", tile);
   return PFDTD_ERR_INVALID;

@@ -4,6 +4,7 @@
 //   toBilbao / toKowalczyk (+kernels)   src/kernels/cudaMesh.cu:328-498
 //   calcBoundaries                      src/kernels/cudaMesh.cu:500-514
 #include "pfdtd_internal.h"
+#include <algorithm>
 
 namespace pfdtd {
 
@@ -174,6 +175,36 @@ __global__ void assign_classes_kernel(const uint8_t* __restrict__ pos, const uin
     }
     cls[i] = c;
   }
+}
+
+// one warp per 128-voxel row segment (4 class bytes per lane)
+__global__ void count_dif_segments_kernel(const uint8_t* __restrict__ cls, int X, int Y, int nz, uint32_t dif_lo,
+                                          uint32_t* __restrict__ counts) {
+  const int segs = (X + 127) / 128;
+  const int64_t n_seg = (int64_t)nz * Y * segs;
+  const int lane = threadIdx.x & 31;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_seg; w += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int sx = (int)(w % segs);
+    const int64_t row = w / segs;             // z*Y + y
+    const int z = (int)(row / Y);
+    uint32_t c = 0;
+    if (z >= 1 && z < nz - 1) {
+      const int x = sx * 128 + 4 * lane;
+      for (int q = 0; q < 4; q++)
+        if (x + q < X) c += cls[row * X + x + q] >= dif_lo;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if (lane == 0) counts[w] = c;
+  }
+}
+
+int launch_count_dif_segments(const uint8_t* d_cls, int X, int Y, int nz, uint32_t dif_lo, uint32_t* d_counts, cudaStream_t stream) {
+  const int64_t n_seg = (int64_t)nz * Y * ((X + 127) / 128);
+  int blocks = (int)std::min<int64_t>((n_seg * 32 + 255) / 256, 148 * 16);
+  if (blocks < 1) blocks = 1;
+  count_dif_segments_kernel<<<blocks, 256, 0, stream>>>(d_cls, X, Y, nz, dif_lo, d_counts);
+  PF_CUDA(cudaGetLastError());
+  return PFDTD_OK;
 }
 
 static int class_blocks(uint64_t n) {

@@ -13,6 +13,8 @@
 #include <map>
 #include <mutex>
 
+#define PFDTD_DIF_MAX_ORDER_HOST 4
+
 namespace pfdtd {
 
 static thread_local std::string g_last_error;
@@ -82,6 +84,11 @@ struct Partition {
   uint8_t* cls = nullptr;               // node class byte (what the TMA kernel reads instead of pos + mat)
   void* class_table = nullptr;          // ClassEntry<T>[n_classes]
   uint32_t* d_class_keys = nullptr;
+  // digital impedance filters
+  void* dif_state = nullptr;            // [order][dif_nb]
+  uint32_t* dif_rowbase = nullptr;      // [size][Y][ceil(X/128)]
+  void* dif_table = nullptr;            // DifEntry<T>[n_lossy]
+  uint32_t dif_nb = 0;
   bool owns_nodes = true;
   void* P[2] = {nullptr, nullptr};
   void* materials = nullptr;
@@ -109,7 +116,7 @@ struct pfdtd_solver {
   // options
   int64_t opt_matidx_as_written = 1, opt_soft_accumulate = 0, opt_kernel = KERNEL_AUTO, opt_global_z_first = 0,
           opt_global_z_dim = 0, opt_double_pad = 0, opt_use_graph = 1, opt_overlap = 1, opt_tma_chunk = 0, opt_tma_tile = 0,
-          opt_time_kernels = 0, opt_tma_hints = 0;
+          opt_time_kernels = 0, opt_tma_hints = 0, opt_dif_order = 0;
   int dtype = PFDTD_F32;
   int element_type = 0;
   int scheme = SCH_FORWARD;
@@ -128,6 +135,7 @@ struct pfdtd_solver {
   double dcoef[4] = {0, 0, 0, 0};        // interpolated schemes: d1..d4
   bool dcoef_user = false;
   bool tables_dirty = true;
+  uint32_t dif_lo = 2, n_lossy = 0;       // class ids >= dif_lo are lossy boundary classes
   std::vector<Partition> parts;
   int cur = 0;                           // index of the current field in Partition::P
   int past_direction = 1;                // launchFDTD3dStep's static (kernels3d.cu:386)
@@ -174,6 +182,7 @@ static int free_partitions(pfdtd_solver* s) {
     if (p.s_edge) cudaStreamSynchronize(p.s_edge);
     if (p.owns_nodes) { cudaFree(p.pos); cudaFree(p.mat); cudaFree(p.cls); }
     cudaFree(p.class_table); cudaFree(p.d_class_keys);
+    cudaFree(p.dif_state); cudaFree(p.dif_rowbase); cudaFree(p.dif_table);
     cudaFree(p.P[0]); cudaFree(p.P[1]); cudaFree(p.materials); cudaFree(p.d_step);
     cudaFree(p.d_src_elem); cudaFree(p.d_src_type); cudaFree(p.d_src_slot); cudaFree(p.d_rec_elem); cudaFree(p.d_rec_slot);
     cudaFree(p.d_src_samples); cudaFree(p.d_rec_out);
@@ -261,6 +270,13 @@ static UpdateArgs make_update_args(pfdtd_solver* s, Partition& p, int z_begin, i
   a.class_table = p.class_table;
   a.n_classes = (int)s->class_keys.size();
   a.tma_hints = (int)s->opt_tma_hints;
+  a.dif_order = p.dif_rowbase ? (int)s->opt_dif_order : 0;
+  a.dif_state = p.dif_state;
+  a.dif_rowbase = p.dif_rowbase;
+  a.dif_table = p.dif_table;
+  a.dif_nb = p.dif_nb;
+  a.dif_lo = s->dif_lo;
+  a.n_dif = (int)s->n_lossy;
   a.P = p.P[s->cur];
   a.Pn = p.P[1 - s->cur];
   a.materials = p.materials;
@@ -283,7 +299,9 @@ static int ensure_class_tables(pfdtd_solver* s) {
     if (!p.class_table) continue;
     PF_CUDA(cudaSetDevice(p.device));
     UpdateArgs a = make_update_args(s, p, 0, 0, p.s_main);
+    a.dif_order = (int)s->opt_dif_order;     // class entries take b0 as the scalar admittance when filters are on
     PF_TRY(build_class_table(a, p.d_class_keys, (int)s->class_keys.size(), p.class_table));
+    if (p.dif_table) PF_TRY(build_dif_table(a, p.d_class_keys + s->dif_lo, (int)s->n_lossy, p.dif_table));
     PF_CUDA(cudaStreamSynchronize(p.s_main));
     s->launch_count++;
   }
@@ -531,6 +549,7 @@ static int64_t* option_slot(pfdtd_solver* s, int option) {
     case PFDTD_OPT_TMA_TILE: return &s->opt_tma_tile;
     case PFDTD_OPT_TIME_KERNELS: return &s->opt_time_kernels;
     case PFDTD_OPT_TMA_HINTS: return &s->opt_tma_hints;
+    case PFDTD_OPT_DIF_ORDER: return &s->opt_dif_order;
   }
   return nullptr;
 }
@@ -624,14 +643,21 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
     s->class_keys.push_back(air_key);    // class 1: air
     std::vector<uint32_t> found;
     for (uint32_t k : table) if (k != 0xffffffffu) found.push_back(k);
-    std::sort(found.begin(), found.end());
-    for (uint32_t k : found) s->class_keys.push_back(k);
+    // lossless classes first, lossy boundary classes (K < 6 / a direction flag set) last: "is a filter boundary"
+    // becomes one unsigned compare on the class byte
+    const bool centred_bytes = s->scheme == SCH_CENTRED;
+    auto lossy = [centred_bytes](uint32_t k) { const uint32_t p = k & 0xffu; return centred_bytes ? (p & 7u) != 0u : (p & 0x7fu) < 6u; };
+    std::sort(found.begin(), found.end(), [&](uint32_t a, uint32_t b) { return lossy(a) != lossy(b) ? lossy(b) : a < b; });
+    uint32_t n_lossless = 0;
+    for (uint32_t k : found) { s->class_keys.push_back(k); if (!lossy(k)) n_lossless++; }
+    s->dif_lo = 2 + n_lossless;
+    s->n_lossy = (uint32_t)found.size() - n_lossless;
     s->d_cls0 = nullptr;
     if (count + 2 <= 256 && count < cap / 2) {
       std::vector<uint8_t> ids(cap, 0);
       for (uint32_t slot = 0; slot < cap; slot++)
         if (table[slot] != 0xffffffffu)
-          ids[slot] = (uint8_t)(2 + (std::lower_bound(found.begin(), found.end(), table[slot]) - found.begin()));
+          ids[slot] = (uint8_t)(2 + (std::find(found.begin(), found.end(), table[slot]) - found.begin()));
       PF_CUDA(cudaMemcpy(d_ids, ids.data(), cap, cudaMemcpyHostToDevice));
       PF_CUDA(cudaMalloc(&s->d_cls0, n_new));
       PF_TRY(launch_assign_classes(np, nm, n_new, air_key, air_code, interp, nx, ny, nz, d_table, d_ids, cap, s->d_cls0, 0));
@@ -639,6 +665,7 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
       s->launch_count += 2;
     } else {
       s->class_keys.resize(2);
+      s->dif_lo = 2; s->n_lossy = 0;
     }
     PF_CUDA(cudaFree(d_table));
     PF_CUDA(cudaFree(d_count));
@@ -774,8 +801,31 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
     PF_CHECK(!(s->opt_kernel == KERNEL_TMA && !p.use_tma), PFDTD_ERR_INVALID,
              "TMA kernel requested but mesh %ux%u (slab of %lld slices, %zu node classes) is not supported by it", s->X, s->Y,
              (long long)p.size, s->class_keys.size());
+    if (s->opt_dif_order > 0) {
+      PF_CHECK(s->opt_dif_order <= PFDTD_DIF_MAX_ORDER_HOST, PFDTD_ERR_INVALID, "filter order %lld > %d", (long long)s->opt_dif_order,
+               PFDTD_DIF_MAX_ORDER_HOST);
+      PF_CHECK(p.use_tma, PFDTD_ERR_INVALID, "filter (DIF) boundaries need the TMA kernel (X %% 16 == 0 and <= 256 node classes)");
+      PF_CHECK(s->n_lossy <= 64, PFDTD_ERR_INVALID, "filter (DIF) boundaries support <= 64 lossy node classes, mesh has %u", s->n_lossy);
+      const int segs = ((int)s->X + 127) / 128;
+      const size_t n_seg = (size_t)p.size * s->Y * segs;
+      PF_CUDA(cudaMalloc(&p.dif_rowbase, n_seg * sizeof(uint32_t)));
+      PF_TRY(launch_count_dif_segments(p.cls, (int)s->X, (int)s->Y, (int)p.size, s->dif_lo, p.dif_rowbase, 0));
+      std::vector<uint32_t> cnt(n_seg);
+      PF_CUDA(cudaMemcpy(cnt.data(), p.dif_rowbase, n_seg * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      uint64_t run = 0;
+      for (size_t i = 0; i < n_seg; i++) { const uint32_t c = cnt[i]; cnt[i] = (uint32_t)run; run += c; }
+      PF_CHECK(run < 0xffffffffull, PFDTD_ERR_INVALID, "too many boundary voxels in one slab");
+      p.dif_nb = (uint32_t)run;
+      PF_CUDA(cudaMemcpy(p.dif_rowbase, cnt.data(), n_seg * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      const size_t sb = (size_t)std::max<uint32_t>(p.dif_nb, 1) * s->opt_dif_order * es;
+      PF_CUDA(cudaMalloc(&p.dif_state, sb));
+      PF_CUDA(cudaMemset(p.dif_state, 0, sb));
+      PF_CUDA(cudaMalloc(&p.dif_table, std::max<uint32_t>(s->n_lossy, 1) * dif_entry_bytes(s->dtype)));
+      s->launch_count++;
+    }
     if (p.use_tma) {
       int64_t want_tile = s->opt_tma_tile;
+      if (s->opt_dif_order > 0 && s->scheme != SCH_INTERP && want_tile == 0) want_tile = s->dtype == PFDTD_F32 ? 3 : 1;
       if (s->scheme == SCH_INTERP && want_tile == 0) want_tile = 1;   // 128x8, one row per warp (profiles/r01_sweep.md)
       PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->X, (int)s->Y, nplanes, p.device, want_tile, s->opt_tma_chunk,
                              &p.cfg_full));
@@ -978,6 +1028,7 @@ int pfdtd_reset_pressures(pfdtd_solver* s) {
     const size_t n = (size_t)p.size * s->X * s->Y * esize(s);
     PF_CUDA(cudaMemset(p.P[0], 0, n));
     PF_CUDA(cudaMemset(p.P[1], 0, n));
+    if (p.dif_state) PF_CUDA(cudaMemset(p.dif_state, 0, (size_t)std::max<uint32_t>(p.dif_nb, 1) * s->opt_dif_order * esize(s)));
   }
   return PFDTD_OK;
 }

@@ -77,6 +77,14 @@ struct UpdateArgs {
   double params[4];        // lambda, lambda^2, 1/3, octave  (already rounded to the dtype)
   double dcoef[4];         // SCH_INTERP: d1 (axial), d2 (edge), d3 (corner), d4 (centre) of the compact scheme
   int matidx_as_written;
+  // digital impedance filters (0 = off)
+  int dif_order;
+  void* dif_state;              // [order][dif_nb] of the dtype
+  const uint32_t* dif_rowbase;  // [nz][Y][ceil(X/128)]
+  const void* dif_table;        // DifEntry<T>[n_dif]
+  uint32_t dif_nb;
+  uint32_t dif_lo;
+  int n_dif;
   int X, Y;
   int z_begin, z_end;      // local planes [z_begin, z_end) are updated
   void* peer_lo;           // optional: base of the neighbour slab plane that receives plane z_begin (or null)
@@ -92,6 +100,10 @@ bool tma_supported(int X, int Y, int dtype);
 int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void* Pold, const uint8_t* cls, int X, int Y, int nz);
 int build_class_table(const UpdateArgs& a, const uint32_t* d_keys, int n_classes, void* d_table);
 size_t class_entry_bytes(int dtype);
+size_t dif_entry_bytes(int dtype);
+int build_dif_table(const UpdateArgs& a, const uint32_t* d_keys /* keys of the lossy classes */, int n_dif, void* d_table);
+// per 128-voxel row segment: number of voxels whose class id is >= dif_lo, planes [1, nz-1) only
+int launch_count_dif_segments(const uint8_t* d_cls, int X, int Y, int nz, uint32_t dif_lo, uint32_t* d_counts, cudaStream_t stream);
 int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk, TmaConfig* out);
 int launch_update_tma(const UpdateArgs& a, const TmaMaps& maps, const TmaConfig& cfg);
 int launch_update_plain(const UpdateArgs& a);

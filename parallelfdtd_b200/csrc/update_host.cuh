@@ -19,7 +19,22 @@ inline UpdConst<T> make_const(const UpdateArgs& a) {
   c.materials = (const T*)a.materials;
   c.n_coefs = a.n_coefs;
   c.matidx_as_written = a.matidx_as_written;
+  c.dif_order = a.dif_order;
   return c;
+}
+
+template <typename T>
+inline DifArgs<T> make_dif(const UpdateArgs& a) {
+  DifArgs<T> d;
+  d.state = (T*)a.dif_state;
+  d.rowbase = a.dif_rowbase;
+  d.table = (const DifEntry<T>*)a.dif_table;
+  d.nb = a.dif_nb;
+  d.order = a.dif_order;
+  d.dif_lo = a.dif_lo;
+  d.n_dif = a.n_dif;
+  d.segs = (a.X + 127) / 128;
+  return d;
 }
 
 

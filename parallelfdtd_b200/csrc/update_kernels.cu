@@ -69,17 +69,19 @@ int launch_update_plain(const UpdateArgs& a) {
 // TMA z-march kernel
 // =====================================================================================================
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: (TY/RPW + 1) warps (last warp = TMA producer)
-template <typename T, int SCHEME, int TY, int RPW, int NST>
+template <typename T, int SCHEME, int TY, int RPW, int NST, bool DIF>
 __global__ void __launch_bounds__((TY / RPW + 1) * 32)
     fdtd_update_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                     const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
-                    T* __restrict__ Pn, T lam2, T a_air, int X, int Y, int z_begin, int z_end, int chunk, int hints) {
+                    T* __restrict__ Pn, T lam2, T a_air, int X, int Y, int z_begin, int z_end, int chunk, int hints,
+                    const DifArgs<T> dif) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY / RPW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[NST];
   __shared__ __align__(8) uint64_t bar_empty[NST];
   __shared__ ClassEntry<T> s_table[256];
+  __shared__ DifEntry<T> s_dif[DIF ? 64 : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
   const int z_hi = min(z_lo + chunk, z_end);
   const int n = z_hi - z_lo;              // planes this CTA computes
   if (n <= 0) return;
+  if (DIF) for (int i = threadIdx.x; i < dif.n_dif; i += blockDim.x) s_dif[i] = dif.table[i];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; s++) {
@@ -171,6 +174,14 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
     const unsigned char* ps2 = st2 + G::PS_OFF;
     const T* pt1 = reinterpret_cast<const T*>(smem_raw + (size_t)s1 * G::STAGE_BYTES + G::PT_OFF);
     const int z = z_lo + j;
+    uint32_t seg_base[RPW];
+    if (DIF) {
+#pragma unroll
+      for (int k = 0; k < RPW; k++) {
+        const int gyk = y0 + r0 + k;
+        seg_base[k] = gyk < Y ? __ldg(dif.rowbase + ((size_t)z * Y + gyk) * dif.segs + blockIdx.x) : 0u;
+      }
+    }
 
     V4<T> old[RPW];
     uint32_t pw[RPW];
@@ -192,11 +203,11 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
       if (lane == 0) xm_edge = pt1[(r0 + k + 1) * G::PW + G::HX - 1];
       if (lane == 31) xp_edge = pt1[(r0 + k + 1) * G::PW + G::HX + TX];
       const int gy = y0 + r0 + k;
-      if (x_ok && gy < Y) {
+      const bool active = x_ok && gy < Y;
+      V4<T> res;
+      if (active) {
         const V4<T>& ym = (k == 0) ? ym0 : cur[k - 1 < 0 ? 0 : k - 1];
         const V4<T>& yp = (k == RPW - 1) ? yp1 : cur[k + 1 >= RPW ? RPW - 1 : k + 1];
-        const int64_t e = (int64_t)z * XY + (int64_t)gy * X + gx;
-        V4<T> res;
         T S[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -226,8 +237,9 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
             }
           }
         }
-        stg4(Pn + e, res);
       }
+      if (DIF) dif_apply_row<T>(res.v, old[k].v, pw[k], active, lane, seg_base[k], dif, s_dif);
+      if (active) stg4(Pn + (int64_t)z * XY + (int64_t)gy * X + gx, res);
     }
     // every read of stage s1 (plane z tile, plus P_old/node bytes of plane z-1 read last iteration) is done
     __syncwarp();
@@ -298,9 +310,9 @@ constexpr int kNumTiles = (int)(sizeof(kTiles) / sizeof(kTiles[0]));
 template <typename T, int TY>
 constexpr int stage_bytes() { return TileGeom<T, TY>::STAGE_BYTES; }
 
-template <typename T, int SCHEME, int TY, int RPW, int NST>
+template <typename T, int SCHEME, int TY, int RPW, int NST, bool DIF = false>
 int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupancy_out) {
-  auto kern = fdtd_update_tma<T, SCHEME, TY, RPW, NST>;
+  auto kern = fdtd_update_tma<T, SCHEME, TY, RPW, NST, DIF>;
   const int smem = NST * stage_bytes<T, TY>();
   static bool attr_set[64] = {false};   // per device
   int dev = 0;
@@ -318,13 +330,21 @@ int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupanc
   dim3 grid((a.X + TX - 1) / TX, (a.Y + TY - 1) / TY, (nplanes + chunk - 1) / chunk);
   const UpdConst<T> c = make_const<T>(a);
   kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.cls, (const ClassEntry<T>*)a.class_table, a.n_classes, (T*)a.Pn,
-                                          c.lam2, c.a_air, a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints);
+                                          c.lam2, c.a_air, a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints, make_dif<T>(a));
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }
 
 template <typename T, int SCHEME>
 int dispatch_tile(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
+  if (a.dif_order > 0) {   // filter boundaries: the one-row-per-warp shapes only
+    switch (tile) {
+      case 0: return launch_tma_t<T, SCHEME, 8, 1, 4, true>(a, m, chunk, occ);
+      case 2: return launch_tma_t<T, SCHEME, 16, 1, 4, true>(a, m, chunk, occ);
+    }
+    set_error("tile variant %d is not available with filter (DIF) boundaries", tile);
+    return PFDTD_ERR_INVALID;
+  }
   switch (tile) {
     case 0: return launch_tma_t<T, SCHEME, 8, 1, 4>(a, m, chunk, occ);
     case 1: return launch_tma_t<T, SCHEME, 16, 2, 4>(a, m, chunk, occ);
@@ -437,6 +457,30 @@ int build_class_table(const UpdateArgs& a, const uint32_t* d_keys, int n_classes
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }
+
+template <typename T, int SCHEME>
+__global__ void build_dif_table_kernel(const uint32_t* __restrict__ keys, int n, UpdConst<T> c, int order, DifEntry<T>* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t key = keys[i];
+  out[i] = make_dif_entry<T, SCHEME>(key & 0xffu, (key >> 8) & 0xffu, c, order);
+}
+
+int build_dif_table(const UpdateArgs& a, const uint32_t* d_keys, int n_dif, void* d_table) {
+  if (n_dif <= 0) return PFDTD_OK;
+  const int th = 64, bl = (n_dif + th - 1) / th;
+  if (a.dtype == PFDTD_F32) {
+    if (a.scheme == SCH_CENTRED) build_dif_table_kernel<float, SCH_CENTRED><<<bl, th, 0, a.stream>>>(d_keys, n_dif, make_const<float>(a), a.dif_order, (DifEntry<float>*)d_table);
+    else build_dif_table_kernel<float, SCH_FORWARD><<<bl, th, 0, a.stream>>>(d_keys, n_dif, make_const<float>(a), a.dif_order, (DifEntry<float>*)d_table);
+  } else {
+    if (a.scheme == SCH_CENTRED) build_dif_table_kernel<double, SCH_CENTRED><<<bl, th, 0, a.stream>>>(d_keys, n_dif, make_const<double>(a), a.dif_order, (DifEntry<double>*)d_table);
+    else build_dif_table_kernel<double, SCH_FORWARD><<<bl, th, 0, a.stream>>>(d_keys, n_dif, make_const<double>(a), a.dif_order, (DifEntry<double>*)d_table);
+  }
+  PF_CUDA(cudaGetLastError());
+  return PFDTD_OK;
+}
+
+size_t dif_entry_bytes(int dtype) { return dtype == PFDTD_F32 ? sizeof(DifEntry<float>) : sizeof(DifEntry<double>); }
 
 size_t class_entry_bytes(int dtype) { return dtype == PFDTD_F32 ? sizeof(ClassEntry<float>) : sizeof(ClassEntry<double>); }
 

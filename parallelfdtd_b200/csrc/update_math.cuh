@@ -39,6 +39,7 @@ struct UpdConst {
   const T* materials;      // [n_unique][20] admittances on this device
   uint32_t n_coefs;        // entries in `materials` (index is clamped; the reference would read out of bounds)
   int matidx_as_written;   // forward kernel only, kernels3d.cu:513
+  int dif_order;           // > 0: material rows hold filter coefficients [b0..bN, a1..aN]; the scalar admittance is b0
 };
 
 template <typename T>
@@ -131,6 +132,72 @@ struct alignas(16) ClassEntry {
 
 enum : uint32_t { CLS_SOLID = 0, CLS_AIR = 1 };
 
+// ---- digital impedance filters (frequency-dependent boundaries; not in the reference) ----
+// Material m has the admittance Y_m(z) = (b0 + b1 z^-1 + .. + bN z^-N) / (1 + a1 z^-1 + .. + aN z^-N) acting on
+// u^n = p^(n+1) - p^(n-1).  With the filter in transposed direct form II (states s_1..s_N per boundary voxel):
+//     p_new = val0 - c3 * s_1          val0 = the frequency-independent update with Y = b0 (class entry c0..c2)
+//     u = p_new - p_old ;  y = b0*u + s_1 ;  s_i <- b_i*u - a_i*y + s_(i+1)   (s_(N+1) = 0)
+// c3 = kappa * sw/(1+beta0), kappa = 0.5*(6-K)*lam (forward / interpolated) or lam*(dir_x+dir_y+dir_z) (centred).
+// Order 0 leaves p_new = val0: exactly the reference's locally-reacting boundary.
+#define PFDTD_DIF_MAX_ORDER 4
+template <typename T>
+struct DifEntry {
+  T c3, b0;
+  T b[PFDTD_DIF_MAX_ORDER], a[PFDTD_DIF_MAX_ORDER];
+};
+template <typename T>
+struct DifArgs {
+  T* state;                      // [order][nb] filter states of this slab's boundary voxels
+  const uint32_t* rowbase;       // [nz][Y][segs]: index of the first boundary voxel of each 128-voxel row segment
+  const DifEntry<T>* table;      // [n_dif] per lossy class
+  uint32_t nb;
+  int order;
+  uint32_t dif_lo;               // class ids >= dif_lo are lossy boundary classes
+  int n_dif;
+  int segs;                      // row segments per row = ceil(X / 128)
+};
+
+// one boundary voxel: returns p_new and advances the voxel's filter states
+template <typename T>
+__device__ __forceinline__ T dif_voxel(const DifEntry<T>& e, T val0, T p_old, T* __restrict__ st, uint32_t nb, int order) {
+  T s[PFDTD_DIF_MAX_ORDER + 1];
+#pragma unroll
+  for (int i = 0; i < PFDTD_DIF_MAX_ORDER; i++) s[i] = i < order ? st[(size_t)i * nb] : (T)0;
+  s[PFDTD_DIF_MAX_ORDER] = (T)0;
+  const T p_new = Ar<T>::fma(-e.c3, s[0], val0);
+  const T u = Ar<T>::add(p_new, -p_old);
+  const T y = Ar<T>::fma(e.b0, u, s[0]);
+#pragma unroll
+  for (int i = 0; i < PFDTD_DIF_MAX_ORDER; i++)
+    if (i < order) st[(size_t)i * nb] = Ar<T>::fma(e.b[i], u, Ar<T>::fma(-e.a[i], y, s[i + 1]));
+  return p_new;
+}
+
+// Warp-convergent: every lane of the warp calls it for its four x-adjacent voxels of one row segment.
+// pw = the four class bytes, seg_base = rowbase entry of the segment; ranks follow x order.
+template <typename T>
+__device__ __forceinline__ void dif_apply_row(T (&res)[4], const T (&old)[4], uint32_t pw, bool active, int lane, uint32_t seg_base,
+                                              const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif) {
+  uint32_t isd[4], m[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t c = (pw >> (8 * q)) & 0xffu;
+    isd[q] = (active && (c - d.dif_lo) < (uint32_t)d.n_dif) ? 1u : 0u;
+    m[q] = __ballot_sync(0xffffffffu, isd[q]);
+  }
+  if ((m[0] | m[1] | m[2] | m[3]) == 0u) return;
+  const uint32_t below = (1u << lane) - 1u;
+  uint32_t run = seg_base + __popc(m[0] & below) + __popc(m[1] & below) + __popc(m[2] & below) + __popc(m[3] & below);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    if (isd[q]) {
+      const uint32_t c = (pw >> (8 * q)) & 0xffu;
+      res[q] = dif_voxel<T>(s_dif[c - d.dif_lo], res[q], old[q], d.state + run, d.nb, d.order);
+      run++;
+    }
+  }
+}
+
 template <typename T, int SCHEME>
 __device__ __forceinline__ ClassEntry<T> make_class_entry(uint32_t pos, uint32_t m, const UpdConst<T>& c) {
   ClassEntry<T> e;
@@ -139,14 +206,15 @@ __device__ __forceinline__ ClassEntry<T> make_class_entry(uint32_t pos, uint32_t
   if (pos == 0u) m = 0u;
   if (SCHEME == SCH_CENTRED) {
     T dsum = (T)((pos & 1u) + ((pos >> 1) & 1u) + ((pos >> 2) & 1u));
-    uint32_t idx = (uint32_t)Ar<T>::add((T)(m * 20u), c.octave);
+    uint32_t idx = c.dif_order > 0 ? m * 20u : (uint32_t)Ar<T>::add((T)(m * 20u), c.octave);
     T cl = Ar<T>::mul(load_coef(c, idx), c.lam);
     e.c0 = Ar<T>::fma(cl, dsum, (T)-1);
     e.c1 = Ar<T>::rcp(Ar<T>::fma(cl, dsum, (T)1));
     e.c2 = sw;
   } else {
     T K = (T)(pos & 0x7Fu);
-    uint32_t idx = c.matidx_as_written ? (uint32_t)Ar<T>::mul((T)(m * 20u), c.octave) : m * 20u + (uint32_t)c.octave;
+    uint32_t idx = c.dif_order > 0 ? m * 20u
+                   : (c.matidx_as_written ? (uint32_t)Ar<T>::mul((T)(m * 20u), c.octave) : m * 20u + (uint32_t)c.octave);
     T t = Ar<T>::mul(Ar<T>::mul(load_coef(c, idx), Ar<T>::add((T)6, -K)), c.lam);
     e.c0 = Ar<T>::fma(K, -c.lam2, (T)2);
     e.c1 = -Ar<T>::fma(t, (T)-0.5, (T)1);
@@ -169,7 +237,7 @@ __device__ __forceinline__ ClassEntry<T> make_class_entry_interp(uint32_t pos, u
   const T sw = (T)(pos >> 7);
   if (pos == 0u) m = 0u;
   const T K = (T)(pos & 0x7Fu);
-  const uint32_t idx = m * 20u + (uint32_t)c.octave;
+  const uint32_t idx = c.dif_order > 0 ? m * 20u : m * 20u + (uint32_t)c.octave;
   const T t = Ar<T>::mul(Ar<T>::mul(load_coef(c, idx), Ar<T>::add((T)6, -K)), c.lam);
   T c0 = Ar<T>::fma(c.d[0], Ar<T>::add((T)6, -K), c.d[3]);
   c0 = Ar<T>::fma(c.d[1], (T)(12u - k12), c0);
@@ -179,6 +247,33 @@ __device__ __forceinline__ ClassEntry<T> make_class_entry_interp(uint32_t pos, u
   e.c2 = Ar<T>::mul(sw, Ar<T>::rcp(Ar<T>::fma(t, (T)0.5, (T)1)));
   return e;
 }
+// DIF entry of a lossy class: c3 = kappa * (sw / (1 + beta0)); material row = [b0..bN, a1..aN]
+template <typename T, int SCHEME>
+__device__ __forceinline__ DifEntry<T> make_dif_entry(uint32_t pos, uint32_t m, const UpdConst<T>& c, int order) {
+  DifEntry<T> e;
+  const T* row = c.materials + (size_t)m * 20u;
+  const T b0 = __ldg(row);
+  const T sw = (T)(pos >> 7);
+  T kap, rc;
+  if (SCHEME == SCH_CENTRED) {
+    const T dsum = (T)((pos & 1u) + ((pos >> 1) & 1u) + ((pos >> 2) & 1u));
+    kap = Ar<T>::mul(c.lam, dsum);
+    rc = Ar<T>::mul(sw, Ar<T>::rcp(Ar<T>::fma(Ar<T>::mul(b0, c.lam), dsum, (T)1)));
+  } else {
+    const T K = (T)(pos & 0x7Fu);
+    kap = Ar<T>::mul(Ar<T>::mul((T)0.5, Ar<T>::add((T)6, -K)), c.lam);
+    const T t = Ar<T>::mul(Ar<T>::mul(b0, Ar<T>::add((T)6, -K)), c.lam);
+    rc = Ar<T>::mul(sw, Ar<T>::rcp(Ar<T>::fma(t, (T)0.5, (T)1)));
+  }
+  e.c3 = Ar<T>::mul(kap, rc);
+  e.b0 = b0;
+  for (int i = 0; i < PFDTD_DIF_MAX_ORDER; i++) {
+    e.b[i] = i < order ? __ldg(row + 1 + i) : (T)0;
+    e.a[i] = i < order ? __ldg(row + 1 + order + i) : (T)0;
+  }
+  return e;
+}
+
 // in-plane partial sums of one voxel: a4 = ((x- + x+) + y-) + y+ ; g4 = ((x-y- + x+y-) + x-y+) + x+y+
 template <typename T>
 __device__ __forceinline__ T interp_a4(T xm, T xp, T ym, T yp) { return Ar<T>::add(Ar<T>::add(Ar<T>::add(xm, xp), ym), yp); }

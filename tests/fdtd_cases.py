@@ -84,6 +84,38 @@ def interp_cases():
     ]
 
 
+def dif_table(n_mat, order, seed=7):
+    """[n_mat][20] rows [b0..bN, a1..aN]: passive-looking low-order admittance filters (poles well inside the unit circle)."""
+    rng = np.random.default_rng(seed)
+    t = np.zeros((n_mat, 20), dtype=np.float64)
+    for m in range(n_mat):
+        y0 = 0.02 + 0.3 * (m + 1) / (n_mat + 1)
+        t[m, 0] = y0 * (0.6 + 0.3 * rng.random())
+        for i in range(1, order + 1):
+            t[m, i] = y0 * 0.25 * (rng.random() - 0.3) / i
+            t[m, order + i] = 0.5 * (rng.random() - 0.5) / i
+    return t
+
+
+def dif_cases():
+    """Frequency-dependent (digital impedance filter) boundaries: not in the reference, checked against our oracle."""
+    out = []
+    for name, dims, ut, dbl, steps, n_mat, parts, geom, order in [
+            ("dif2_shoebox_48x40x49_fwd_f32", (48, 40, 49), 0, False, 300, 6, 2, "shoebox", 2),
+            ("dif4_shoebox_48x40x49_ctr_f64", (48, 40, 49), 2, True, 300, 6, 3, "shoebox", 4),
+            ("dif1_hall_96x128x64_fwd_f64", (96, 128, 64), 0, True, 200, 5, 1, "hall", 1),
+            ("dif2_hall_96x128x64_iiso_f32", (96, 128, 64), 3, False, 200, 5, 2, "hall", 2),
+            ("dif3_shoebox_48x40x49_iwb_f64", (48, 40, 49), 4, True, 300, 6, 1, "shoebox", 3)]:
+        if geom == "shoebox":
+            c = make_case(name, dims, ut, dbl, steps, n_mat, parts, _SRC3, _REC3, input_data=_DATA)
+        else:
+            c = make_case(name, dims, ut, dbl, steps, n_mat, parts, [(40, 20, 20, 0, 0, 0)], [(50, 60, 30), (20, 100, 40)], geometry="hall")
+        c["dif_order"] = order
+        c["materials"] = dif_table(n_mat, order).astype(np.float64 if dbl else np.float32)
+        out.append(c)
+    return out
+
+
 def lam_of(case):
     return oracle.interp_lambda(case["update_type"]) if case["update_type"] >= 3 else LAM
 
@@ -113,6 +145,10 @@ def run_oracle(case, n_parts=None, matidx=1, soft=0, double_pad=False):
     if case["update_type"] >= 3:
         matidx = 0          # the new schemes index the material table as intended (mat*20 + octave)
     src = np.asarray(case["sources"], dtype=np.int32).reshape(-1, 6)
+    if case.get("dif_order") is not None:
+        r, secs = oracle.run_dif(pos, mat, scheme_of(case), prm, case["materials"], case["dif_order"], src[:, :3], src[:, 3],
+                                 source_table(case), case["receivers"], case["steps"], n_parts or case["n_parts"])
+        return r, (pos, mat, air, bnd), secs
     r, secs = oracle.run(pos, mat, scheme_of(case), prm, case["materials"], src[:, :3], src[:, 3], source_table(case),
                          case["receivers"], case["steps"], n_parts or case["n_parts"], matidx, soft)
     return r, (pos, mat, air, bnd), secs
@@ -129,6 +165,8 @@ def run_ours(capi, case, n_parts=None, kernel=None, matidx=1, opts=(), devices=N
         prm = params_of(case, False)
         if case.get("dcoef"):
             s.set_scheme_coefficients(case["dcoef"])
+        if case.get("dif_order") is not None:
+            s.set_option(capi.OPT_DIF_ORDER, case["dif_order"])
         s.setup_mesh(case["bid"], case["mat"], case["block"], case["update_type"], dt, prm, case["materials"])
         n = n_parts or case["n_parts"]
         s.make_partition(n, devices or [0] * n)

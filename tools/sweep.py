@@ -41,7 +41,18 @@ for spec in a.sets.split(";"):
         s.set_option(capi.OPT_TMA_HINTS, int(kv.get("hints", 0)))
         s.set_option(capi.OPT_MATIDX_AS_WRITTEN, 0)
         s.set_option(capi.OPT_TIME_KERNELS, 1)
-        s.setup_mesh(bid, mat, (32, 4, 1), a.update_type, dt, prm, tab)
+        dif = int(kv.get("dif", 0))
+        s.set_option(capi.OPT_DIF_ORDER, dif)
+        if dif:
+            t = np.zeros((6, 20), dtype=npdt)
+            t[:, 0] = tab[:, 0] * 0.7
+            for i in range(1, dif + 1):
+                t[:, i] = tab[:, 0] * 0.1 / i
+                t[:, dif + i] = -0.3 / i
+            tab_use = t
+        else:
+            tab_use = tab
+        s.setup_mesh(bid, mat, (32, 4, 1), a.update_type, dt, prm, tab_use)
         s.make_partition(1, [0])
         c = [d // 2 for d in dims]
         src = np.zeros((1, a.steps + 16), dtype=npdt)
