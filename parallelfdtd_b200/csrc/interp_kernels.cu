@@ -121,12 +121,11 @@ __global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 :
   {
     mbar_wait(&bar_full[0], 0);
     load_plane<T, TY, HAS_D3>(reinterpret_cast<const T*>(smem_raw + G::PT_OFF), r, lane, pm);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_empty[0]);
     mbar_wait(&bar_full[1 % NST], (uint32_t)((1 / NST) & 1));
     load_plane<T, TY, HAS_D3>(reinterpret_cast<const T*>(smem_raw + (size_t)(1 % NST) * G::STAGE_BYTES + G::PT_OFF), r, lane, pc);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_empty[1 % NST]);
+    // No stage is handed back before a global store that depends on what was loaded from it: an issued but not
+    // yet performed shared-memory load is not ordered before the mbarrier arrive, so the producer's next TMA
+    // write into the stage could overtake it (update_kernels.cu has the B200 observation).
   }
 
   for (int j = 0; j < n; j++) {
@@ -140,10 +139,6 @@ __global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 :
     V4<T> old;
     lds4(reinterpret_cast<const T*>(st2 + G::PO_OFF) + r * TX + xl, old);
     const uint32_t pw = *reinterpret_cast<const uint32_t*>(st2 + G::PS_OFF + r * TX + xl);
-    // every shared-memory read of this stage is done: hand it back before the arithmetic
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_empty[s2]);
-
     V4<T> res;
     if (active) {
       if (pw == AIR4) {
@@ -162,6 +157,12 @@ __global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 :
     }
     if (DIF) dif_apply_row<T>(res.v, old.v, pw, active, lane, seg_base, dif, s_dif);
     if (active) stg4(Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx, res);
+    // the store above consumed everything read from stage s2 (and, at j == 0, from the two prologue stages)
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&bar_empty[s2]);
+      if (j == 0) { mbar_arrive(&bar_empty[0]); mbar_arrive(&bar_empty[1 % NST]); }
+    }
     pm = pc;
     pc = pp;
   }

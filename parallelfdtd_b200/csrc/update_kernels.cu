@@ -153,8 +153,10 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
     const T* pt = reinterpret_cast<const T*>(smem_raw + G::PT_OFF);
 #pragma unroll
     for (int k = 0; k < RPW; k++) lds4(pt + (r0 + k + 1) * G::PW + G::HX + xl, down[k]);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_empty[0]);
+    // stage 0 is NOT handed back here: a shared-memory load that has been issued but not yet performed is not
+    // ordered before the mbarrier arrive, so the producer's next TMA write into the stage could overtake it
+    // (seen on B200 with two CTAs per SM: `down` picked up bytes of plane z_lo+3).  Every release below comes
+    // after a global store that depends on the loaded values, which orders it behind the loads.
     mbar_wait(&bar_full[1 % NST], (uint32_t)((1 / NST) & 1));
     const T* pt1 = reinterpret_cast<const T*>(smem_raw + (size_t)(1 % NST) * G::STAGE_BYTES + G::PT_OFF);
 #pragma unroll
@@ -243,7 +245,10 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
     }
     // every read of stage s1 (plane z tile, plus P_old/node bytes of plane z-1 read last iteration) is done
     __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_empty[s1]);
+    if (lane == 0) {
+      mbar_arrive(&bar_empty[s1]);
+      if (j == 0) mbar_arrive(&bar_empty[0]);   // plane z_lo-1, read in the prologue
+    }
 #pragma unroll
     for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
   }
