@@ -53,6 +53,12 @@ def parse_args():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--update-type", type=int, default=0, choices=[0, 1, 2, 3, 4])
+    ap.add_argument("--dif-order", type=int, default=0, choices=[0, 1, 2, 3, 4],
+                    help="frequency-dependent boundaries: order of the per-material digital impedance filters (0 = the "
+                         "reference's frequency-independent admittance, the only boundary the reference arm can run)")
+    ap.add_argument("--no-variants", action="store_true",
+                    help="N=1 only: skip the short device-resident runs of the other BASELINE config-2 variants (DIF order 2, "
+                         "fp64, IISO) that are appended to the JSON line as `variants`")
     ap.add_argument("--kernel", default="auto", choices=["auto", "tma", "plain"])
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
@@ -128,14 +134,15 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload, dtype, update_type):
+def ncu_traffic(workload, dtype, update_type, dif_order=0):
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if one matches."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
         return None
     try:
         for e in json.load(open(p)):
-            if e.get("workload") == workload and e.get("dtype") == dtype and e.get("update_type") == update_type:
+            if (e.get("workload") == workload and e.get("dtype") == dtype and e.get("update_type") == update_type
+                    and e.get("dif_order", 0) == dif_order):
                 return e.get("dram_bytes_per_launch")
     except Exception:  # noqa: BLE001
         return None
@@ -182,7 +189,8 @@ def run_ours(args):
     npdt = np.float64 if double else np.float32
     lam = COURANT[args.update_type]
     prm = np.array([lam, lam * lam, 1.0 / 3.0, 0.0], dtype=npdt)
-    tab = synth.material_table(list(np.linspace(0.99, 0.5, n_mat)) if n_mat > 1 else [0.9]).astype(npdt)
+    refl = list(np.linspace(0.99, 0.5, n_mat)) if n_mat > 1 else [0.9]
+    tab = (synth.filter_material_table(refl, args.dif_order) if args.dif_order else synth.material_table(refl)).astype(npdt)
     plan = slabs.SlabPlan(gdims[2], world)
     z0, nz = plan.slab(rank)
     t_geo = time.time()
@@ -201,7 +209,7 @@ def run_ours(args):
     rec_xyz = [[cx + 17, cy + 5, min(gdims[2] - 2, 3 + (i * (gdims[2] - 6)) // 3)] for i in range(4)]
     opts = [(capi.OPT_MATIDX_AS_WRITTEN, 0), (capi.OPT_OVERLAP, 0 if args.no_overlap else 1),
             (capi.OPT_KERNEL, {"auto": capi.KERNEL_AUTO, "tma": capi.KERNEL_TMA, "plain": capi.KERNEL_PLAIN}[args.kernel]),
-            (capi.OPT_TMA_TILE, args.tile), (capi.OPT_TMA_CHUNK, args.chunk)]
+            (capi.OPT_TMA_TILE, args.tile), (capi.OPT_TMA_CHUNK, args.chunk), (capi.OPT_DIF_ORDER, args.dif_order)]
 
     def make_solver():
         ss = slabs.SlabSolver(capi, gdims, lambda a, b: (bid, mat), block=(32, 4, 1), element_type=args.update_type, dtype=dt,
@@ -258,7 +266,7 @@ def run_ours(args):
     kern_ms_per_step = kern_ms / max(steps_timed_k, 1)      # all update launches of one step on this rank
     peak, peak_src = measured_peak()
     achieved = slab_updates * ALGO_BYTES[args.dtype] / (kern_ms_per_step * 1e-3) / 1e9 if kern_ms_per_step > 0 else 0.0
-    traffic = ncu_traffic(args.workload, args.dtype, args.update_type)
+    traffic = ncu_traffic(args.workload, args.dtype, args.update_type, args.dif_order)
     ss.close()
 
     # ---- end-to-end through the C ABI with HOST buffers ------------------------------------------------
@@ -295,6 +303,9 @@ def run_ours(args):
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{wdesc}; global {gdims[0]}x{gdims[1]}x{gdims[2]} -> padded {X}x{Y}x{gdims[2]}",
                        "update_type": UPDATE_NAMES[args.update_type], "materials": n_mat, "sources": 1, "receivers": len(rec_xyz),
+                       "boundaries": (f"frequency-dependent: order-{args.dif_order} digital impedance filter per material, states of the "
+                                      "boundary voxels updated in the same kernel pass") if args.dif_order else
+                                     "frequency-independent admittance per material (the reference's boundary)",
                        "slabs": world, "halo": "none" if world == 1 else "one plane each way per interface per step, NCCL p2p over NVLink"
                        + ("" if args.no_overlap else ", overlapped with the interior update"),
                        "kernel": kname, "cache": "inputs larger than L2 (fields %.0f MiB per GPU vs 126 MB L2), no flush" %
@@ -308,12 +319,42 @@ def run_ours(args):
                          "how": f"CUDA events around every update launch over {steps_timed_k} steps right after the timed region"},
             "cpu_baseline": cpu,
         }
+        if world == 1 and not args.no_variants:
+            line["variants"] = run_variants(args)
         if world > 1:
             line["halo_ms_last_step"] = halo_ms_last
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+VARIANTS = [("f32 SRL_FORWARD + DIF order 2", ["--dtype", "f32", "--dif-order", "2"]),
+            ("f64 SRL_FORWARD", ["--dtype", "f64"]),
+            ("f64 SRL_FORWARD + DIF order 2", ["--dtype", "f64", "--dif-order", "2"]),
+            ("f32 IISO (27-point)", ["--dtype", "f32", "--update-type", "3"]),
+            ("f32 IISO + DIF order 2", ["--dtype", "f32", "--update-type", "3", "--dif-order", "2"])]
+
+
+def run_variants(args):
+    """The other variants BASELINE config 2 names (frequency-dependent DIF boundaries, fp64) and the interpolated scheme,
+    each as a short device-resident run of this same script in a child process (same workload, 200 steps)."""
+    out = []
+    for name, flags in VARIANTS:
+        if flags == (["--dtype", args.dtype] + (["--dif-order", str(args.dif_order)] if args.dif_order else [])
+                     + (["--update-type", str(args.update_type)] if args.update_type else [])):
+            continue
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--steps", "200", "--warmup", "10", "--no-e2e",
+               "--no-cpu-baseline", "--no-variants"] + flags
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            out.append({"variant": name, "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                        "kernel": d["config"]["kernel"], "roofline_achieved_gbs": d["roofline"]["achieved"],
+                        "roofline_frac": d["roofline"]["frac"], "bytes_per_voxel_update": d["roofline"]["bytes_per_voxel_update"]})
+        except Exception as e:  # noqa: BLE001
+            out.append({"variant": name, "error": repr(e)[:200]})
+    return out
 
 
 def cpu_baseline(args, bid, mat, tab, prm, src_xyz, rec_xyz, src_tab):
@@ -327,6 +368,18 @@ def cpu_baseline(args, bid, mat, tab, prm, src_xyz, rec_xyz, src_tab):
     scheme = 0 if args.update_type in (0, 1) else (2 if args.update_type == 2 else 3)
     if scheme == 3:
         prm = oracle.params_interp(float(prm[0]), 0, oracle.interp_coefficients(args.update_type, float(prm[1])), double)
+    if args.dif_order:
+        steps = args.cpu_steps or 8
+        t1 = time.time()
+        oracle.run_dif(pos, m, scheme, prm, tab, args.dif_order, src_xyz, [0], np.ascontiguousarray(src_tab[:, :3]), rec_xyz, 3, 1)
+        per = max((time.time() - t1) / 3, 1e-6)
+        steps = args.cpu_steps or int(max(4, min(src_tab.shape[1], 12.0 / per)))
+        t1 = time.time()
+        oracle.run_dif(pos, m, scheme, prm, tab, args.dif_order, src_xyz, [0], np.ascontiguousarray(src_tab[:, :steps]), rec_xyz, steps, 1)
+        secs = time.time() - t1
+        return {"value": nvox * steps / secs / 1e6, "unit": "Mvox/s", "cores": threads, "kind": "port",
+                "sample": f"same workload (order-{args.dif_order} filters), {steps} steps of the C++/OpenMP oracle incl. its per-run setup, "
+                          f"{time.time() - t0:.1f} s total"}
     steps = args.cpu_steps
     if not steps:   # calibrate on 4 steps, then size the sample for ~12 s of CPU work
         _, s4 = oracle.run(pos, m, scheme, prm, tab, src_xyz, [0], np.ascontiguousarray(src_tab[:, :5]), rec_xyz, 5, 1, 0, 0, 1)

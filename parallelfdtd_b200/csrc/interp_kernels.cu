@@ -54,7 +54,7 @@ __device__ __forceinline__ void load_plane(const T* __restrict__ pt, int r, int 
 }  // namespace
 
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: TY consumer warps (one tile row each) + 1 producer warp
-template <typename T, bool HAS_D3, int TY, int NST, bool DIF>
+template <typename T, bool HAS_D3, int TY, int NST, int DIF>
 __global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 : 2) : (TY == 8 ? 2 : 1))
     fdtd_update_interp_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                            const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
@@ -128,11 +128,30 @@ __global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 :
     // write into the stage could overtake it (update_kernels.cu has the B200 observation).
   }
 
+  // DIF: lane l holds the rowbase entry of plane (j & ~31) + l of this warp's row; st_nxt / st_cur are the filter
+  // states fetched for the next / this plane (dif_fetch)
+  constexpr int DMO = DIF ? DIF : 1;
+  uint32_t rowbases = 0u;
+  T st_cur[DMO], st_nxt[DMO];
+#pragma unroll
+  for (int i = 0; i < DMO; i++) st_cur[i] = st_nxt[i] = (T)0;
+  if (DIF) {
+    rowbases = dif_load_rowbases<T>(dif, z_lo, z_hi, gy, Y, lane);
+    dif_fetch<T, DMO>(dif, __shfl_sync(0xffffffffu, rowbases, 0), lane, st_nxt);
+  }
   for (int j = 0; j < n; j++) {
     const int i2 = j + 2;
     const int s2 = i2 % NST;
-    uint32_t seg_base = 0;
-    if (DIF && gy < Y) seg_base = __ldg(dif.rowbase + ((size_t)(z_lo + j) * Y + gy) * dif.segs + blockIdx.x);
+    uint32_t dif_entry = 0u;
+    if (DIF) {   // this plane's states were fetched an iteration ago; start the next plane's fetch now
+      dif_entry = __shfl_sync(0xffffffffu, rowbases, j & 31);
+#pragma unroll
+      for (int i = 0; i < DMO; i++) st_cur[i] = st_nxt[i];
+      if (j + 1 < n) {
+        if (((j + 1) & 31) == 0) rowbases = dif_load_rowbases<T>(dif, z_lo + j + 1, z_hi, gy, Y, lane);
+        dif_fetch<T, DMO>(dif, __shfl_sync(0xffffffffu, rowbases, (j + 1) & 31), lane, st_nxt);
+      }
+    }
     mbar_wait(&bar_full[s2], (uint32_t)((i2 / NST) & 1));
     const unsigned char* st2 = smem_raw + (size_t)s2 * G::STAGE_BYTES;
     load_plane<T, TY, HAS_D3>(reinterpret_cast<const T*>(st2 + G::PT_OFF), r, lane, pp);
@@ -155,7 +174,7 @@ __global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 :
         }
       }
     }
-    if (DIF) dif_apply_row<T>(res.v, old.v, pw, active, lane, seg_base, dif, s_dif);
+    if (DIF && (dif_entry & DIF_HAS)) dif_apply_row<T, DMO>(res.v, old.v, pw, active, lane, dif_entry, st_cur, dif, s_dif);
     if (active) stg4(Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx, res);
     // the store above consumed everything read from stage s2 (and, at j == 0, from the two prologue stages)
     __syncwarp();
@@ -197,7 +216,7 @@ __global__ void __launch_bounds__(128) fdtd_update_interp_plain(const uint8_t* _
 
 namespace {
 
-template <typename T, bool HAS_D3, int TY, int NST, bool DIF>
+template <typename T, bool HAS_D3, int TY, int NST, int DIF>
 int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupancy_out) {
   auto kern = fdtd_update_interp_tma<T, HAS_D3, TY, NST, DIF>;
   const int smem = NST * TileGeom<T, TY>::STAGE_BYTES;
@@ -226,14 +245,21 @@ template <typename T, bool HAS_D3>
 int dispatch_interp(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
   // tile variants shared with the 7-point kernel: only the one-row-per-warp shapes apply here
   if (a.dif_order > 0) {
-    switch (tile) {
-      case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, true>(a, m, chunk, occ);
-      case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4, true>(a, m, chunk, occ);
+    if (a.dif_order <= 2) {
+      switch (tile) {
+        case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, 2>(a, m, chunk, occ);
+        case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4, 2>(a, m, chunk, occ);
+      }
+    } else {
+      switch (tile) {
+        case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, 4>(a, m, chunk, occ);
+        case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4, 4>(a, m, chunk, occ);
+      }
     }
   }
   switch (tile) {
-    case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, false>(a, m, chunk, occ);
-    case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4, false>(a, m, chunk, occ);
+    case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, 0>(a, m, chunk, occ);
+    case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4, 0>(a, m, chunk, occ);
   }
   set_error("tile variant %d is not available for the interpolated schemes", tile);
   return PFDTD_ERR_INVALID;

@@ -813,8 +813,9 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       std::vector<uint32_t> cnt(n_seg);
       PF_CUDA(cudaMemcpy(cnt.data(), p.dif_rowbase, n_seg * sizeof(uint32_t), cudaMemcpyDeviceToHost));
       uint64_t run = 0;
-      for (size_t i = 0; i < n_seg; i++) { const uint32_t c = cnt[i]; cnt[i] = (uint32_t)run; run += c; }
-      PF_CHECK(run < 0xffffffffull, PFDTD_ERR_INVALID, "too many boundary voxels in one slab");
+      // entry = index of the segment's first boundary voxel | bit 31 when the segment has any (DIF_HAS, update_math.cuh)
+      for (size_t i = 0; i < n_seg; i++) { const uint32_t c = cnt[i]; cnt[i] = (uint32_t)run | (c ? 0x80000000u : 0u); run += c; }
+      PF_CHECK(run < 0x7fffffffull, PFDTD_ERR_INVALID, "too many boundary voxels in one slab");
       p.dif_nb = (uint32_t)run;
       PF_CUDA(cudaMemcpy(p.dif_rowbase, cnt.data(), n_seg * sizeof(uint32_t), cudaMemcpyHostToDevice));
       const size_t sb = (size_t)std::max<uint32_t>(p.dif_nb, 1) * s->opt_dif_order * es;

@@ -69,7 +69,8 @@ int launch_update_plain(const UpdateArgs& a) {
 // TMA z-march kernel
 // =====================================================================================================
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: (TY/RPW + 1) warps (last warp = TMA producer)
-template <typename T, int SCHEME, int TY, int RPW, int NST, bool DIF>
+// DIF = 0: frequency-independent boundaries; 2 / 4: digital impedance filters up to that order
+template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF>
 __global__ void __launch_bounds__((TY / RPW + 1) * 32)
     fdtd_update_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                     const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
@@ -164,6 +165,18 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
   }
 
   constexpr uint32_t AIR4 = CLS_AIR * 0x01010101u;
+  // DIF (one row per warp): lane l holds the rowbase entry of plane (j & ~31) + l of the warp's row; st_nxt / st_cur
+  // are the filter states fetched for the next / this plane (dif_fetch)
+  static_assert(!DIF || RPW == 1, "filter boundaries use the one-row-per-warp tile shapes");
+  constexpr int DMO = DIF ? DIF : 1;
+  uint32_t rowbases = 0u;
+  T st_cur[DMO], st_nxt[DMO];
+#pragma unroll
+  for (int i = 0; i < DMO; i++) st_cur[i] = st_nxt[i] = (T)0;
+  if (DIF) {
+    rowbases = dif_load_rowbases<T>(dif, z_lo, z_hi, y0 + r0, Y, lane);
+    dif_fetch<T, DMO>(dif, __shfl_sync(0xffffffffu, rowbases, 0), lane, st_nxt);
+  }
 
   for (int j = 0; j < n; j++) {
     const int i2 = j + 2;
@@ -176,12 +189,14 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
     const unsigned char* ps2 = st2 + G::PS_OFF;
     const T* pt1 = reinterpret_cast<const T*>(smem_raw + (size_t)s1 * G::STAGE_BYTES + G::PT_OFF);
     const int z = z_lo + j;
-    uint32_t seg_base[RPW];
-    if (DIF) {
+    uint32_t dif_entry = 0u;
+    if (DIF) {   // this plane's states were fetched an iteration ago; start the next plane's fetch now
+      dif_entry = __shfl_sync(0xffffffffu, rowbases, j & 31);
 #pragma unroll
-      for (int k = 0; k < RPW; k++) {
-        const int gyk = y0 + r0 + k;
-        seg_base[k] = gyk < Y ? __ldg(dif.rowbase + ((size_t)z * Y + gyk) * dif.segs + blockIdx.x) : 0u;
+      for (int i = 0; i < DMO; i++) st_cur[i] = st_nxt[i];
+      if (j + 1 < n) {
+        if (((j + 1) & 31) == 0) rowbases = dif_load_rowbases<T>(dif, z + 1, z_hi, y0 + r0, Y, lane);
+        dif_fetch<T, DMO>(dif, __shfl_sync(0xffffffffu, rowbases, (j + 1) & 31), lane, st_nxt);
       }
     }
 
@@ -240,7 +255,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
           }
         }
       }
-      if (DIF) dif_apply_row<T>(res.v, old[k].v, pw[k], active, lane, seg_base[k], dif, s_dif);
+      if (DIF && (dif_entry & DIF_HAS)) dif_apply_row<T, DMO>(res.v, old[k].v, pw[k], active, lane, dif_entry, st_cur, dif, s_dif);
       if (active) stg4(Pn + (int64_t)z * XY + (int64_t)gy * X + gx, res);
     }
     // every read of stage s1 (plane z tile, plus P_old/node bytes of plane z-1 read last iteration) is done
@@ -315,7 +330,7 @@ constexpr int kNumTiles = (int)(sizeof(kTiles) / sizeof(kTiles[0]));
 template <typename T, int TY>
 constexpr int stage_bytes() { return TileGeom<T, TY>::STAGE_BYTES; }
 
-template <typename T, int SCHEME, int TY, int RPW, int NST, bool DIF = false>
+template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF = 0>
 int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupancy_out) {
   auto kern = fdtd_update_tma<T, SCHEME, TY, RPW, NST, DIF>;
   const int smem = NST * stage_bytes<T, TY>();
@@ -343,9 +358,16 @@ int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupanc
 template <typename T, int SCHEME>
 int dispatch_tile(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
   if (a.dif_order > 0) {   // filter boundaries: the one-row-per-warp shapes only
-    switch (tile) {
-      case 0: return launch_tma_t<T, SCHEME, 8, 1, 4, true>(a, m, chunk, occ);
-      case 2: return launch_tma_t<T, SCHEME, 16, 1, 4, true>(a, m, chunk, occ);
+    if (a.dif_order <= 2) {
+      switch (tile) {
+        case 0: return launch_tma_t<T, SCHEME, 8, 1, 4, 2>(a, m, chunk, occ);
+        case 2: return launch_tma_t<T, SCHEME, 16, 1, 4, 2>(a, m, chunk, occ);
+      }
+    } else {
+      switch (tile) {
+        case 0: return launch_tma_t<T, SCHEME, 8, 1, 4, 4>(a, m, chunk, occ);
+        case 2: return launch_tma_t<T, SCHEME, 16, 1, 4, 4>(a, m, chunk, occ);
+      }
     }
     set_error("tile variant %d is not available with filter (DIF) boundaries", tile);
     return PFDTD_ERR_INVALID;

@@ -157,43 +157,78 @@ struct DifArgs {
   int segs;                      // row segments per row = ceil(X / 128)
 };
 
-// one boundary voxel: returns p_new and advances the voxel's filter states
+// rowbase entries of one (row, tile column) for 32 consecutive planes, one per lane: a single load per 32 planes
+// instead of a dependent global load per plane; the kernels pick the entry of a plane with a shuffle.
+// Entry = index of the segment's first boundary voxel | (segment has boundary voxels ? DIF_HAS : 0).
+constexpr uint32_t DIF_HAS = 0x80000000u;
 template <typename T>
-__device__ __forceinline__ T dif_voxel(const DifEntry<T>& e, T val0, T p_old, T* __restrict__ st, uint32_t nb, int order) {
-  T s[PFDTD_DIF_MAX_ORDER + 1];
-#pragma unroll
-  for (int i = 0; i < PFDTD_DIF_MAX_ORDER; i++) s[i] = i < order ? st[(size_t)i * nb] : (T)0;
-  s[PFDTD_DIF_MAX_ORDER] = (T)0;
-  const T p_new = Ar<T>::fma(-e.c3, s[0], val0);
-  const T u = Ar<T>::add(p_new, -p_old);
-  const T y = Ar<T>::fma(e.b0, u, s[0]);
-#pragma unroll
-  for (int i = 0; i < PFDTD_DIF_MAX_ORDER; i++)
-    if (i < order) st[(size_t)i * nb] = Ar<T>::fma(e.b[i], u, Ar<T>::fma(-e.a[i], y, s[i + 1]));
-  return p_new;
+__device__ __forceinline__ uint32_t dif_load_rowbases(const DifArgs<T>& d, int z_first, int z_end, int gy, int Y, int lane) {
+  const int z = z_first + lane;
+  return (gy < Y && z < z_end) ? __ldg(d.rowbase + ((size_t)z * Y + gy) * d.segs + blockIdx.x) : 0u;
 }
 
-// Warp-convergent: every lane of the warp calls it for its four x-adjacent voxels of one row segment.
-// pw = the four class bytes, seg_base = rowbase entry of the segment; ranks follow x order.
-template <typename T>
-__device__ __forceinline__ void dif_apply_row(T (&res)[4], const T (&old)[4], uint32_t pw, bool active, int lane, uint32_t seg_base,
-                                              const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif) {
-  uint32_t isd[4], m[4];
+// The filter states are the only dependent global loads of the march.  They are fetched one plane ahead, coalesced:
+// lane l reads the states of the segment's l-th boundary voxel (rank l, x order) into registers; dif_apply_row
+// hands each voxel its states with a shuffle.  MO = compiled maximum order (2 or 4).  Values of ranks beyond the
+// segment's own voxels belong to other rows and are never used.
+template <typename T, int MO>
+__device__ __forceinline__ void dif_fetch(const DifArgs<T>& d, uint32_t entry, int lane, T (&st)[MO]) {
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const uint32_t c = (pw >> (8 * q)) & 0xffu;
-    isd[q] = (active && (c - d.dif_lo) < (uint32_t)d.n_dif) ? 1u : 0u;
-    m[q] = __ballot_sync(0xffffffffu, isd[q]);
+  for (int i = 0; i < MO; i++) st[i] = (T)0;
+  if (entry & DIF_HAS) {
+    const uint32_t idx = (entry & ~DIF_HAS) + (uint32_t)lane;
+    if (idx < d.nb) {
+#pragma unroll
+      for (int i = 0; i < MO; i++)
+        if (i < d.order) st[i] = d.state[(size_t)i * d.nb + idx];
+    }
   }
-  if ((m[0] | m[1] | m[2] | m[3]) == 0u) return;
-  const uint32_t below = (1u << lane) - 1u;
-  uint32_t run = seg_base + __popc(m[0] & below) + __popc(m[1] & below) + __popc(m[2] & below) + __popc(m[3] & below);
+}
+
+// Warp-convergent: every lane of the warp calls it for its four x-adjacent voxels of one row segment whose
+// rowbase entry (uniform across the warp) has DIF_HAS set.  pw = the four class bytes, st = dif_fetch of this
+// plane; ranks follow x order.  A segment where a single lane has boundary voxels (a wall crossing the row) skips
+// the cross-lane prefix.  Per voxel (transposed direct form II, see above):
+//     p_new = val0 - c3*s_1 ; u = p_new - p_old ; y = b0*u + s_1 ; s_i <- b_i*u - a_i*y + s_(i+1)
+template <typename T, int MO>
+__device__ __forceinline__ void dif_apply_row(T (&res)[4], const T (&old)[4], uint32_t pw, bool active, int lane, uint32_t entry,
+                                              const T (&st)[MO], const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif) {
+  uint32_t mine = 0;   // bit q: voxel q of this lane is a lossy boundary voxel
+  if (active && pw != CLS_AIR * 0x01010101u) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) mine |= (((pw >> (8 * q)) & 0xffu) - d.dif_lo < (uint32_t)d.n_dif) ? (1u << q) : 0u;
+  }
+  const uint32_t lanes = __ballot_sync(0xffffffffu, mine != 0u);
+  uint32_t rank = 0;
+  if (lanes & (lanes - 1u)) {   // several lanes: rank = boundary voxels of the lanes below (x order)
+    const uint32_t below = (1u << lane) - 1u;
+#pragma unroll
+    for (int q = 0; q < 4; q++) rank += __popc(__ballot_sync(0xffffffffu, (mine >> q) & 1u) & below);
+  }
+  const uint32_t qmask = __reduce_or_sync(0xffffffffu, mine);   // voxel positions that occur anywhere in the warp
+  const uint32_t base = entry & ~DIF_HAS;
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    if (isd[q]) {
-      const uint32_t c = (pw >> (8 * q)) & 0xffu;
-      res[q] = dif_voxel<T>(s_dif[c - d.dif_lo], res[q], old[q], d.state + run, d.nb, d.order);
-      run++;
+    if (!((qmask >> q) & 1u)) continue;   // uniform
+    T s[MO + 1];
+#pragma unroll
+    for (int i = 0; i < MO; i++) s[i] = __shfl_sync(0xffffffffu, st[i], (int)(rank & 31u));
+    s[MO] = (T)0;
+    if ((mine >> q) & 1u) {
+      T* sp = d.state + base + rank;
+      if (rank >= 32u) {   // beyond the prefetched window (rows lying in a wall plane)
+#pragma unroll
+        for (int i = 0; i < MO; i++) s[i] = i < d.order ? sp[(size_t)i * d.nb] : (T)0;
+      }
+      const DifEntry<T>& e = s_dif[((pw >> (8 * q)) & 0xffu) - d.dif_lo];
+      const T p_new = Ar<T>::fma(-e.c3, s[0], res[q]);
+      const T u = Ar<T>::add(p_new, -old[q]);
+      const T y = Ar<T>::fma(e.b0, u, s[0]);
+#pragma unroll
+      for (int i = 0; i < MO; i++)
+        if (i < d.order) sp[(size_t)i * d.nb] = Ar<T>::fma(e.b[i], u, Ar<T>::fma(-e.a[i], y, s[i + 1]));
+      res[q] = p_new;
+      rank++;
     }
   }
 }

@@ -174,3 +174,27 @@ def material_table(reflectances, n_coef=20):
     for i, r in enumerate(reflectances):
         t[i, :n_coef] = reflection_to_admittance(r)
     return t
+
+
+def filter_material_table(reflectances, order, n_coef=20):
+    """[n_mat][20] float64 table of digital-impedance-filter admittances, row = [b0..bN, a1..aN] (PFDTD_OPT_DIF_ORDER).
+
+    Material m is a one-pole-per-order low-shelf around its frequency-independent admittance Y0 (derived from the
+    reflectance like `material_table`): Y(z) = Y0 * prod_i (1 - q_i z^-1) / (1 - p_i z^-1) with real poles/zeros
+    well inside the unit circle, so that Re Y(e^jw) > 0 (passive) and the DC / Nyquist values stay within a factor
+    of two of Y0.  Synthetic stand-in for fitted wall impedances (BASELINE config 2).
+    """
+    assert 1 <= order <= 4 and 2 * order + 1 <= n_coef
+    t = np.zeros((len(reflectances), n_coef), dtype=np.float64)
+    for m, r in enumerate(reflectances):
+        y0 = float(reflection_to_admittance(np.float32(r)))
+        b = np.array([1.0])
+        a = np.array([1.0])
+        for i in range(order):
+            p = 0.55 - 0.12 * i + 0.02 * (m % 3)
+            q = p - 0.18 / (i + 1)
+            b = np.convolve(b, [1.0, -q])
+            a = np.convolve(a, [1.0, -p])
+        t[m, 0:order + 1] = y0 * b
+        t[m, order + 1:2 * order + 1] = a[1:]
+    return t
