@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_plane(const T* __restrict__ pt, int r, int 
 
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: TY consumer warps (one tile row each) + 1 producer warp
 template <typename T, bool HAS_D3, int TY, int NST, int DIF>
-__global__ void __launch_bounds__((TY + 1) * 32, sizeof(T) == 4 ? (TY == 8 ? 3 : 2) : (TY == 8 ? 2 : 1))
+__global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (TY == 8 ? 72 : 56) : 96)
     fdtd_update_interp_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                            const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                            T* __restrict__ Pn, T d1, T d2, T d3, T d4, int X, int Y, int z_begin, int z_end, int chunk,
@@ -244,18 +244,15 @@ int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occup
 template <typename T, bool HAS_D3>
 int dispatch_interp(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
   // tile variants shared with the 7-point kernel: only the one-row-per-warp shapes apply here
-  if (a.dif_order > 0) {
-    if (a.dif_order <= 2) {
-      switch (tile) {
-        case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, 2>(a, m, chunk, occ);
-        case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4, 2>(a, m, chunk, occ);
-      }
-    } else {
-      switch (tile) {
-        case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, 4>(a, m, chunk, occ);
-        case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4, 4>(a, m, chunk, occ);
-      }
+  if (a.dif_order > 0) {   // filter boundaries: the 128x8 shape, one kernel per order
+    switch (a.dif_order) {
+      case 1: return launch_interp_t<T, HAS_D3, 8, 4, 1>(a, m, chunk, occ);
+      case 2: return launch_interp_t<T, HAS_D3, 8, 4, 2>(a, m, chunk, occ);
+      case 3: return launch_interp_t<T, HAS_D3, 8, 4, 3>(a, m, chunk, occ);
+      case 4: return launch_interp_t<T, HAS_D3, 8, 4, 4>(a, m, chunk, occ);
     }
+    set_error("filter order %d is not supported", a.dif_order);
+    return PFDTD_ERR_INVALID;
   }
   switch (tile) {
     case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, 0>(a, m, chunk, occ);

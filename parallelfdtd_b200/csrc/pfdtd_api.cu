@@ -826,7 +826,7 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
     }
     if (p.use_tma) {
       int64_t want_tile = s->opt_tma_tile;
-      if (s->opt_dif_order > 0 && s->scheme != SCH_INTERP && want_tile == 0) want_tile = s->dtype == PFDTD_F32 ? 3 : 1;
+      if (s->opt_dif_order > 0) want_tile = 1;   // the filter kernels exist for the 128x8 one-row-per-warp tile only
       if (s->scheme == SCH_INTERP && want_tile == 0) want_tile = 1;   // 128x8, one row per warp (profiles/r01_sweep.md)
       PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->X, (int)s->Y, nplanes, p.device, want_tile, s->opt_tma_chunk,
                              &p.cfg_full));

@@ -62,7 +62,49 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
   return p;
 }
 
+// ---- the same operations on 32-bit shared-window addresses (hot loops keep integer addresses in registers
+// instead of re-deriving them from generic pointers every iteration) ----
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
 template <typename T> struct V4 { T v[4]; };
+
+__device__ __forceinline__ void lds4_a(uint32_t a, V4<float>& o) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.v[0]), "=f"(o.v[1]), "=f"(o.v[2]), "=f"(o.v[3]) : "r"(a));
+}
+__device__ __forceinline__ void lds4_a(uint32_t a, V4<double>& o) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o.v[0]), "=d"(o.v[1]) : "r"(a));
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(o.v[2]), "=d"(o.v[3]) : "r"(a));
+}
+__device__ __forceinline__ float lds1_a(uint32_t a, float) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds1_a(uint32_t a, double) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32_a(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 
 __device__ __forceinline__ void lds4(const float* p, V4<float>& o) {
   float4 t = *reinterpret_cast<const float4*>(p);

@@ -68,10 +68,23 @@ int launch_update_plain(const UpdateArgs& a) {
 // =====================================================================================================
 // TMA z-march kernel
 // =====================================================================================================
+// Register budget per variant.  Registers are allocated per SM sub-partition (4 x 16384), so k resident warps cost
+// ceil(k/4) warps' worth on the fullest one.  The default 128x8 one-row-per-warp shape (9 warps, 42.5 / 79 KiB of
+// stages): fp32 forward fits four CTAs per SM in 56 registers, the centred scheme and the filter kernels three in
+// 72, fp64 two in 96; the other shapes just have to fit one CTA.
+constexpr int tma_max_regs(size_t esize, int scheme, int ty, int rpw, int dif) {
+  if (ty == 8 && rpw == 1) return esize == 4 ? ((dif || scheme == SCH_CENTRED) ? 72 : 56) : 96;
+  if (ty == 16 && rpw == 1 && esize == 4 && scheme != SCH_CENTRED) return 56;   // two CTAs of 17 warps
+  const int warps = ty / rpw + 1;
+  const int fit = (16384 / (32 * ((warps + 3) / 4))) & ~7;
+  return fit > 255 ? 255 : fit;
+}
+
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: (TY/RPW + 1) warps (last warp = TMA producer)
-// DIF = 0: frequency-independent boundaries; 2 / 4: digital impedance filters up to that order
+// DIF = 0: frequency-independent boundaries; 1..4: digital impedance filters of that order
+// (one-row-per-warp 128x8 tile: three resident CTAs per SM in fp32, two in fp64)
 template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF>
-__global__ void __launch_bounds__((TY / RPW + 1) * 32)
+__global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(sizeof(T), SCHEME, TY, RPW, DIF))
     fdtd_update_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                     const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                     T* __restrict__ Pn, T lam2, T a_air, int X, int Y, int z_begin, int z_end, int chunk, int hints,
@@ -140,29 +153,36 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
   }
 
   // --------------------------------- consumers ---------------------------------------------------
+  // Shared memory is addressed through 32-bit window addresses kept in registers, and the plane loop is unrolled
+  // over the NST stages so that every stage offset and barrier parity is a compile-time constant or one XOR:
+  // the per-plane instruction count is what bounds this kernel once the boundary filters are switched on.
   const int r0 = warp * RPW;                 // first tile row of this warp
   const int xl = 4 * lane;                   // x offset inside the tile
   const int gx = x0 + xl;
   const bool x_ok = gx < X;                  // X is a multiple of 4 on this path
   const int64_t XY = (int64_t)X * Y;
+  constexpr uint32_t ES = (uint32_t)sizeof(T);
+  constexpr uint32_t ROW = (uint32_t)G::PW * ES;           // bytes per halo-tile row
+  const uint32_t sm = smem_u32(smem_raw);
+  const uint32_t bf = smem_u32(bar_full), be = smem_u32(bar_empty);
+  const uint32_t a_ctr = sm + G::PT_OFF + ((uint32_t)(r0 + 1) * G::PW + G::HX + xl) * ES;   // centre of the warp's first row
+  const uint32_t a_old = sm + G::PO_OFF + ((uint32_t)r0 * TX + xl) * ES;
+  const uint32_t a_cls = sm + G::PS_OFF + (uint32_t)r0 * TX + xl;
+  const uint32_t a_row = sm + G::PT_OFF + (uint32_t)(r0 + 1) * ROW;                          // x = -HX of the first row
 
   V4<T> down[RPW], cur[RPW], up[RPW];
 
   // prologue: plane z_lo-1 (centre only), then plane z_lo (kept resident for its xy-neighbours)
-  {
-    mbar_wait(&bar_full[0], 0);
-    const T* pt = reinterpret_cast<const T*>(smem_raw + G::PT_OFF);
+  mbar_wait_a(bf, 0);
 #pragma unroll
-    for (int k = 0; k < RPW; k++) lds4(pt + (r0 + k + 1) * G::PW + G::HX + xl, down[k]);
-    // stage 0 is NOT handed back here: a shared-memory load that has been issued but not yet performed is not
-    // ordered before the mbarrier arrive, so the producer's next TMA write into the stage could overtake it
-    // (seen on B200 with two CTAs per SM: `down` picked up bytes of plane z_lo+3).  Every release below comes
-    // after a global store that depends on the loaded values, which orders it behind the loads.
-    mbar_wait(&bar_full[1 % NST], (uint32_t)((1 / NST) & 1));
-    const T* pt1 = reinterpret_cast<const T*>(smem_raw + (size_t)(1 % NST) * G::STAGE_BYTES + G::PT_OFF);
+  for (int k = 0; k < RPW; k++) lds4_a(a_ctr + k * ROW, down[k]);
+  // stage 0 is NOT handed back here: a shared-memory load that has been issued but not yet performed is not
+  // ordered before the mbarrier arrive, so the producer's next TMA write into the stage could overtake it
+  // (seen on B200 with two CTAs per SM: `down` picked up bytes of plane z_lo+3).  Every release below comes
+  // after a global store that depends on the loaded values, which orders it behind the loads.
+  mbar_wait_a(bf + 8 * (1 % NST), (uint32_t)((1 / NST) & 1));
 #pragma unroll
-    for (int k = 0; k < RPW; k++) lds4(pt1 + (r0 + k + 1) * G::PW + G::HX + xl, cur[k]);
-  }
+  for (int k = 0; k < RPW; k++) lds4_a(a_ctr + (1 % NST) * G::STAGE_BYTES + k * ROW, cur[k]);
 
   constexpr uint32_t AIR4 = CLS_AIR * 0x01010101u;
   // DIF (one row per warp): lane l holds the rowbase entry of plane (j & ~31) + l of the warp's row; st_nxt / st_cur
@@ -178,94 +198,97 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32)
     dif_fetch<T, DMO>(dif, __shfl_sync(0xffffffffu, rowbases, 0), lane, st_nxt);
   }
 
-  for (int j = 0; j < n; j++) {
-    const int i2 = j + 2;
-    const int s2 = i2 % NST;
-    const int s1 = (j + 1) % NST;
-    mbar_wait(&bar_full[s2], (uint32_t)((i2 / NST) & 1));
-    const unsigned char* st2 = smem_raw + (size_t)s2 * G::STAGE_BYTES;
-    const T* pt2 = reinterpret_cast<const T*>(st2 + G::PT_OFF);
-    const T* po2 = reinterpret_cast<const T*>(st2 + G::PO_OFF);
-    const unsigned char* ps2 = st2 + G::PS_OFF;
-    const T* pt1 = reinterpret_cast<const T*>(smem_raw + (size_t)s1 * G::STAGE_BYTES + G::PT_OFF);
-    const int z = z_lo + j;
-    uint32_t dif_entry = 0u;
-    if (DIF) {   // this plane's states were fetched an iteration ago; start the next plane's fetch now
-      dif_entry = __shfl_sync(0xffffffffu, rowbases, j & 31);
-#pragma unroll
-      for (int i = 0; i < DMO; i++) st_cur[i] = st_nxt[i];
-      if (j + 1 < n) {
-        if (((j + 1) & 31) == 0) rowbases = dif_load_rowbases<T>(dif, z + 1, z_hi, y0 + r0, Y, lane);
-        dif_fetch<T, DMO>(dif, __shfl_sync(0xffffffffu, rowbases, (j + 1) & 31), lane, st_nxt);
-      }
-    }
+  T* out = Pn + (int64_t)z_lo * XY + (int64_t)(y0 + r0) * X + gx;   // this lane's four voxels of the warp's first row
+  uint32_t par = 0;                                                    // parity of the round that starts at plane jb
 
-    V4<T> old[RPW];
-    uint32_t pw[RPW];
+  for (int jb = 0; jb < n; jb += NST, par ^= 1u) {
 #pragma unroll
-    for (int k = 0; k < RPW; k++) {
-      lds4(pt2 + (r0 + k + 1) * G::PW + G::HX + xl, up[k]);
-      lds4(po2 + (r0 + k) * TX + xl, old[k]);
-      pw[k] = *reinterpret_cast<const uint32_t*>(ps2 + (r0 + k) * TX + xl);
-    }
-    V4<T> ym0, yp1;   // y-1 of the warp's first row, y+1 of its last row: from the shared tile of plane z
-    lds4(pt1 + (r0) * G::PW + G::HX + xl, ym0);
-    lds4(pt1 + (r0 + RPW + 1) * G::PW + G::HX + xl, yp1);
+    for (int u = 0; u < NST; u++) {
+      const int j = jb + u;
+      if (j >= n) break;
+      constexpr int dummy = 0; (void)dummy;
+      const uint32_t s2 = (uint32_t)((u + 2) % NST) * G::STAGE_BYTES;   // stage of plane z+1 (and P_old / classes of z)
+      const uint32_t s1 = (uint32_t)((u + 1) % NST) * G::STAGE_BYTES;   // stage of plane z
+      mbar_wait_a(bf + 8 * ((u + 2) % NST), par ^ ((u + 2) >= NST ? 1u : 0u));
 
+      uint32_t dif_entry = 0u;
+      if (DIF) {   // this plane's states were fetched an iteration ago; start the next plane's fetch now
+        dif_entry = __shfl_sync(0xffffffffu, rowbases, j & 31);
 #pragma unroll
-    for (int k = 0; k < RPW; k++) {
-      const V4<T>& cc = cur[k];
-      T xm_edge = __shfl_up_sync(0xffffffffu, cc.v[3], 1);
-      T xp_edge = __shfl_down_sync(0xffffffffu, cc.v[0], 1);
-      if (lane == 0) xm_edge = pt1[(r0 + k + 1) * G::PW + G::HX - 1];
-      if (lane == 31) xp_edge = pt1[(r0 + k + 1) * G::PW + G::HX + TX];
-      const int gy = y0 + r0 + k;
-      const bool active = x_ok && gy < Y;
-      V4<T> res;
-      if (active) {
-        const V4<T>& ym = (k == 0) ? ym0 : cur[k - 1 < 0 ? 0 : k - 1];
-        const V4<T>& yp = (k == RPW - 1) ? yp1 : cur[k + 1 >= RPW ? RPW - 1 : k + 1];
-        T S[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          T xm = (q == 0) ? xm_edge : cc.v[q - 1 < 0 ? 0 : q - 1];
-          T xp = (q == 3) ? xp_edge : cc.v[q + 1 > 3 ? 3 : q + 1];
-          S[q] = (SCHEME == SCH_CENTRED) ? sum6_centred<T>(up[k].v[q], down[k].v[q], yp.v[q], ym.v[q], xp, xm)
-                                         : sum6_forward<T>(up[k].v[q], down[k].v[q], yp.v[q], ym.v[q], xp, xm);
+        for (int i = 0; i < DMO; i++) st_cur[i] = st_nxt[i];
+        if (j + 1 < n) {
+          if (((j + 1) & 31) == 0) rowbases = dif_load_rowbases<T>(dif, z_lo + j + 1, z_hi, y0 + r0, Y, lane);
+          dif_fetch<T, DMO>(dif, __shfl_sync(0xffffffffu, rowbases, (j + 1) & 31), lane, st_nxt);
         }
-        if (pw[k] == AIR4) {
+      }
+
+      V4<T> old[RPW];
+      uint32_t pw[RPW];
 #pragma unroll
-          for (int q = 0; q < 4; q++)
-            res.v[q] = (SCHEME == SCH_CENTRED) ? voxel_centred_air<T>(cc.v[q], S[q], old[k].v[q], lam2, a_air)
-                                               : voxel_forward_air<T>(cc.v[q], S[q], old[k].v[q], lam2, a_air);
-        } else {
+      for (int k = 0; k < RPW; k++) {
+        lds4_a(a_ctr + s2 + k * ROW, up[k]);
+        lds4_a(a_old + s2 + k * (TX * ES), old[k]);
+        pw[k] = lds_u32_a(a_cls + s2 + k * TX);
+      }
+      V4<T> ym0, yp1;   // y-1 of the warp's first row, y+1 of its last row: from the shared tile of plane z
+      lds4_a(a_ctr + s1 - ROW, ym0);
+      lds4_a(a_ctr + s1 + RPW * ROW, yp1);
+
+#pragma unroll
+      for (int k = 0; k < RPW; k++) {
+        const V4<T>& cc = cur[k];
+        T xm_edge = __shfl_up_sync(0xffffffffu, cc.v[3], 1);
+        T xp_edge = __shfl_down_sync(0xffffffffu, cc.v[0], 1);
+        if (lane == 0) xm_edge = lds1_a(a_row + s1 + k * ROW + (G::HX - 1) * ES, (T)0);
+        if (lane == 31) xp_edge = lds1_a(a_row + s1 + k * ROW + (G::HX + TX) * ES, (T)0);
+        const bool active = x_ok && (y0 + r0 + k) < Y;
+        V4<T> res;
+        if (active) {
+          const V4<T>& ym = (k == 0) ? ym0 : cur[k - 1 < 0 ? 0 : k - 1];
+          const V4<T>& yp = (k == RPW - 1) ? yp1 : cur[k + 1 >= RPW ? RPW - 1 : k + 1];
+          T S[4];
 #pragma unroll
           for (int q = 0; q < 4; q++) {
-            const ClassEntry<T> ce = s_table[(pw[k] >> (8 * q)) & 0xffu];
-            if (SCHEME == SCH_CENTRED) {
-              T xm = (q == 0) ? xm_edge : cc.v[q - 1 < 0 ? 0 : q - 1];
-              T xp = (q == 3) ? xp_edge : cc.v[q + 1 > 3 ? 3 : q + 1];
-              res.v[q] = ((pw[k] >> (8 * q)) & 0xffu) == CLS_AIR
-                             ? voxel_centred_air<T>(cc.v[q], S[q], old[k].v[q], lam2, a_air)
-                             : voxel_centred_cls<T>(ce, cc.v[q], S[q], up[k].v[q], down[k].v[q], yp.v[q], ym.v[q], xp, xm,
-                                                    old[k].v[q], lam2, a_air);
-            } else {
-              res.v[q] = voxel_forward_cls<T>(ce, cc.v[q], S[q], old[k].v[q], lam2);
+            T xm = (q == 0) ? xm_edge : cc.v[q - 1 < 0 ? 0 : q - 1];
+            T xp = (q == 3) ? xp_edge : cc.v[q + 1 > 3 ? 3 : q + 1];
+            S[q] = (SCHEME == SCH_CENTRED) ? sum6_centred<T>(up[k].v[q], down[k].v[q], yp.v[q], ym.v[q], xp, xm)
+                                           : sum6_forward<T>(up[k].v[q], down[k].v[q], yp.v[q], ym.v[q], xp, xm);
+          }
+          if (pw[k] == AIR4) {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+              res.v[q] = (SCHEME == SCH_CENTRED) ? voxel_centred_air<T>(cc.v[q], S[q], old[k].v[q], lam2, a_air)
+                                                 : voxel_forward_air<T>(cc.v[q], S[q], old[k].v[q], lam2, a_air);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const ClassEntry<T> ce = s_table[(pw[k] >> (8 * q)) & 0xffu];
+              if (SCHEME == SCH_CENTRED) {
+                T xm = (q == 0) ? xm_edge : cc.v[q - 1 < 0 ? 0 : q - 1];
+                T xp = (q == 3) ? xp_edge : cc.v[q + 1 > 3 ? 3 : q + 1];
+                res.v[q] = ((pw[k] >> (8 * q)) & 0xffu) == CLS_AIR
+                               ? voxel_centred_air<T>(cc.v[q], S[q], old[k].v[q], lam2, a_air)
+                               : voxel_centred_cls<T>(ce, cc.v[q], S[q], up[k].v[q], down[k].v[q], yp.v[q], ym.v[q], xp, xm,
+                                                      old[k].v[q], lam2, a_air);
+              } else {
+                res.v[q] = voxel_forward_cls<T>(ce, cc.v[q], S[q], old[k].v[q], lam2);
+              }
             }
           }
         }
+        if (DIF && (dif_entry & DIF_HAS)) dif_apply_row<T, DMO>(res.v, old[k].v, pw[k], active, lane, dif_entry, st_cur, dif, s_dif);
+        if (active) stg4(out + (int64_t)k * X, res);
       }
-      if (DIF && (dif_entry & DIF_HAS)) dif_apply_row<T, DMO>(res.v, old[k].v, pw[k], active, lane, dif_entry, st_cur, dif, s_dif);
-      if (active) stg4(Pn + (int64_t)z * XY + (int64_t)gy * X + gx, res);
-    }
-    // every read of stage s1 (plane z tile, plus P_old/node bytes of plane z-1 read last iteration) is done
-    __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(&bar_empty[s1]);
-      if (j == 0) mbar_arrive(&bar_empty[0]);   // plane z_lo-1, read in the prologue
-    }
+      out += XY;
+      // every read of stage s1 (plane z tile, plus P_old/node bytes of plane z-1 read last iteration) is done
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_a(be + 8 * ((u + 1) % NST));
+        if (j == 0) mbar_arrive_a(be);   // plane z_lo-1, read in the prologue
+      }
 #pragma unroll
-    for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
+      for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
+    }
   }
 }
 
@@ -357,19 +380,14 @@ int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupanc
 
 template <typename T, int SCHEME>
 int dispatch_tile(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
-  if (a.dif_order > 0) {   // filter boundaries: the one-row-per-warp shapes only
-    if (a.dif_order <= 2) {
-      switch (tile) {
-        case 0: return launch_tma_t<T, SCHEME, 8, 1, 4, 2>(a, m, chunk, occ);
-        case 2: return launch_tma_t<T, SCHEME, 16, 1, 4, 2>(a, m, chunk, occ);
-      }
-    } else {
-      switch (tile) {
-        case 0: return launch_tma_t<T, SCHEME, 8, 1, 4, 4>(a, m, chunk, occ);
-        case 2: return launch_tma_t<T, SCHEME, 16, 1, 4, 4>(a, m, chunk, occ);
-      }
+  if (a.dif_order > 0) {   // filter boundaries: the 128x8 one-row-per-warp shape, one kernel per order
+    switch (a.dif_order) {
+      case 1: return launch_tma_t<T, SCHEME, 8, 1, 4, 1>(a, m, chunk, occ);
+      case 2: return launch_tma_t<T, SCHEME, 8, 1, 4, 2>(a, m, chunk, occ);
+      case 3: return launch_tma_t<T, SCHEME, 8, 1, 4, 3>(a, m, chunk, occ);
+      case 4: return launch_tma_t<T, SCHEME, 8, 1, 4, 4>(a, m, chunk, occ);
     }
-    set_error("tile variant %d is not available with filter (DIF) boundaries", tile);
+    set_error("filter order %d is not supported", a.dif_order);
     return PFDTD_ERR_INVALID;
   }
   switch (tile) {
@@ -419,7 +437,8 @@ int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void
 
 int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk,
                     TmaConfig* out) {
-  int tile = (opt_tile > 0 && opt_tile <= kNumTiles) ? (int)opt_tile - 1 : (dtype == PFDTD_F32 ? 2 : 0);
+  // default: 128x8, one row per warp, 4 stages -- 3 resident CTAs per SM in fp32 (<= 72 registers), 2 in fp64
+  int tile = (opt_tile > 0 && opt_tile <= kNumTiles) ? (int)opt_tile - 1 : 0;
   if (Y <= 8 && kTiles[tile].ty > 8) tile = 0;
   UpdateArgs probe{};
   probe.dtype = dtype;
@@ -444,7 +463,9 @@ int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device
     // Measured on B200 (profiles/r01_sweep.md): when the launch is many waves deep, short chunks win even
     // though every chunk re-reads two planes (those re-reads hit L2, and the fine grain evens out the
     // SMs' finishing times); when the whole launch is only a wave or two, wave quantisation dominates.
-    const int lo = dtype == PFDTD_F32 ? 12 : 20, hi = dtype == PFDTD_F32 ? 16 : 28;
+    // (fp32 forward: 8-14 planes; fp64, the centred scheme and the 27-point kernels: 20-28)
+    const bool light = dtype == PFDTD_F32 && scheme == SCH_FORWARD;
+    const int lo = light ? 12 : 20, hi = light ? 16 : 28;
     const bool deep = tiles * (int64_t)((nplanes + lo - 1) / lo) >= 4 * resident;
     double best = -1;
     for (int gz = 1; gz <= nplanes; gz++) {

@@ -169,66 +169,75 @@ __device__ __forceinline__ uint32_t dif_load_rowbases(const DifArgs<T>& d, int z
 
 // The filter states are the only dependent global loads of the march.  They are fetched one plane ahead, coalesced:
 // lane l reads the states of the segment's l-th boundary voxel (rank l, x order) into registers; dif_apply_row
-// hands each voxel its states with a shuffle.  MO = compiled maximum order (2 or 4).  Values of ranks beyond the
-// segment's own voxels belong to other rows and are never used.
-template <typename T, int MO>
-__device__ __forceinline__ void dif_fetch(const DifArgs<T>& d, uint32_t entry, int lane, T (&st)[MO]) {
+// hands each voxel its states with a shuffle.  ORD = filter order the kernel is compiled for.  Values of ranks
+// beyond the segment's own voxels belong to other rows and are never used.
+template <typename T, int ORD>
+__device__ __forceinline__ void dif_fetch(const DifArgs<T>& d, uint32_t entry, int lane, T (&st)[ORD]) {
 #pragma unroll
-  for (int i = 0; i < MO; i++) st[i] = (T)0;
+  for (int i = 0; i < ORD; i++) st[i] = (T)0;
   if (entry & DIF_HAS) {
     const uint32_t idx = (entry & ~DIF_HAS) + (uint32_t)lane;
     if (idx < d.nb) {
+      const T* sp = d.state + idx;
 #pragma unroll
-      for (int i = 0; i < MO; i++)
-        if (i < d.order) st[i] = d.state[(size_t)i * d.nb + idx];
+      for (int i = 0; i < ORD; i++) st[i] = sp[(size_t)i * d.nb];
     }
   }
 }
 
+template <typename T>
+__device__ __forceinline__ T sel4(const T (&v)[4], int q) { return q == 0 ? v[0] : (q == 1 ? v[1] : (q == 2 ? v[2] : v[3])); }
+
 // Warp-convergent: every lane of the warp calls it for its four x-adjacent voxels of one row segment whose
 // rowbase entry (uniform across the warp) has DIF_HAS set.  pw = the four class bytes, st = dif_fetch of this
-// plane; ranks follow x order.  A segment where a single lane has boundary voxels (a wall crossing the row) skips
-// the cross-lane prefix.  Per voxel (transposed direct form II, see above):
+// plane; ranks follow x order.  The lossy boundary classes are the highest class ids, so "is a filter voxel" is
+// an unsigned byte compare, done for the four bytes at once.  The warp then makes as many passes as the busiest
+// lane has filter voxels (one for a wall crossing the row, four for a row lying in a wall); a segment where a
+// single lane has them skips the cross-lane prefix.  Per voxel (transposed direct form II, see above):
 //     p_new = val0 - c3*s_1 ; u = p_new - p_old ; y = b0*u + s_1 ; s_i <- b_i*u - a_i*y + s_(i+1)
-template <typename T, int MO>
+template <typename T, int ORD>
 __device__ __forceinline__ void dif_apply_row(T (&res)[4], const T (&old)[4], uint32_t pw, bool active, int lane, uint32_t entry,
-                                              const T (&st)[MO], const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif) {
-  uint32_t mine = 0;   // bit q: voxel q of this lane is a lossy boundary voxel
+                                              const T (&st)[ORD], const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif) {
+  uint32_t ge = 0;   // bit 8q+7: voxel q of this lane is a lossy boundary voxel
   if (active && pw != CLS_AIR * 0x01010101u) {
-#pragma unroll
-    for (int q = 0; q < 4; q++) mine |= (((pw >> (8 * q)) & 0xffu) - d.dif_lo < (uint32_t)d.n_dif) ? (1u << q) : 0u;
+    const uint32_t k = d.dif_lo * 0x01010101u;
+    const uint32_t t = (pw | 0x80808080u) - (k & 0x7f7f7f7fu);
+    ge = ((pw & ~k) | (~(pw ^ k) & t)) & 0x80808080u;
   }
-  const uint32_t lanes = __ballot_sync(0xffffffffu, mine != 0u);
+  const uint32_t lanes = __ballot_sync(0xffffffffu, ge != 0u);
+  const uint32_t cnt = __popc(ge);
   uint32_t rank = 0;
-  if (lanes & (lanes - 1u)) {   // several lanes: rank = boundary voxels of the lanes below (x order)
+  if (lanes & (lanes - 1u)) {   // several lanes: rank = boundary voxels of the lanes below (x order), cnt is 0..4
     const uint32_t below = (1u << lane) - 1u;
-#pragma unroll
-    for (int q = 0; q < 4; q++) rank += __popc(__ballot_sync(0xffffffffu, (mine >> q) & 1u) & below);
+    rank = __popc(__ballot_sync(0xffffffffu, cnt & 1u) & below) + 2u * __popc(__ballot_sync(0xffffffffu, cnt & 2u) & below) +
+           4u * __popc(__ballot_sync(0xffffffffu, cnt & 4u) & below);
   }
-  const uint32_t qmask = __reduce_or_sync(0xffffffffu, mine);   // voxel positions that occur anywhere in the warp
+  const uint32_t passes = __reduce_max_sync(0xffffffffu, cnt);
   const uint32_t base = entry & ~DIF_HAS;
+  for (uint32_t it = 0; it < passes; it++, rank++) {   // uniform trip count
+    T s[ORD + 1];
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    if (!((qmask >> q) & 1u)) continue;   // uniform
-    T s[MO + 1];
-#pragma unroll
-    for (int i = 0; i < MO; i++) s[i] = __shfl_sync(0xffffffffu, st[i], (int)(rank & 31u));
-    s[MO] = (T)0;
-    if ((mine >> q) & 1u) {
-      T* sp = d.state + base + rank;
+    for (int i = 0; i < ORD; i++) s[i] = __shfl_sync(0xffffffffu, st[i], (int)(rank & 31u));
+    s[ORD] = (T)0;
+    if (it < cnt) {
+      const int bit = __ffs((int)ge) - 1;   // 7, 15, 23 or 31
+      ge &= ge - 1u;
+      const int q = bit >> 3;
+      T* sp = d.state + (base + rank);
       if (rank >= 32u) {   // beyond the prefetched window (rows lying in a wall plane)
 #pragma unroll
-        for (int i = 0; i < MO; i++) s[i] = i < d.order ? sp[(size_t)i * d.nb] : (T)0;
+        for (int i = 0; i < ORD; i++) s[i] = sp[(size_t)i * d.nb];
       }
-      const DifEntry<T>& e = s_dif[((pw >> (8 * q)) & 0xffu) - d.dif_lo];
-      const T p_new = Ar<T>::fma(-e.c3, s[0], res[q]);
-      const T u = Ar<T>::add(p_new, -old[q]);
+      const DifEntry<T>& e = s_dif[((pw >> (bit - 7)) & 0xffu) - d.dif_lo];
+      const T p_new = Ar<T>::fma(-e.c3, s[0], sel4<T>(res, q));
+      const T u = Ar<T>::add(p_new, -sel4<T>(old, q));
       const T y = Ar<T>::fma(e.b0, u, s[0]);
 #pragma unroll
-      for (int i = 0; i < MO; i++)
-        if (i < d.order) sp[(size_t)i * d.nb] = Ar<T>::fma(e.b[i], u, Ar<T>::fma(-e.a[i], y, s[i + 1]));
-      res[q] = p_new;
-      rank++;
+      for (int i = 0; i < ORD; i++) sp[(size_t)i * d.nb] = Ar<T>::fma(e.b[i], u, Ar<T>::fma(-e.a[i], y, s[i + 1]));
+      if (q == 0) res[0] = p_new;
+      else if (q == 1) res[1] = p_new;
+      else if (q == 2) res[2] = p_new;
+      else res[3] = p_new;
     }
   }
 }
