@@ -153,6 +153,18 @@ int pfdtd_export_partition_pressure(pfdtd_solver* s, uint32_t k, int which, void
 int pfdtd_get_device_pointers(pfdtd_solver* s, uint32_t k, void** d_pressure, void** d_pressure_past,
                               uint8_t** d_position_idx, uint8_t** d_material_idx);
 
+/* ---- captures (the step either side of launchFDTD3dStep in App::executeStep, src/App.cpp:421-431) ----
+ * captureSliceFast (src/kernels/visualizationUtils.cu:127-254): pressure (+ optionally the position byte)
+ * of one axis-aligned slice of the CURRENT field, gathered on the device(s) from the planes each partition
+ * owns, only the slice copied to the host.  orientation 0: xy at z = slice -> [dimY][dimX];
+ * 1: xz at y = slice -> [dimZ][dimX]; 2: yz at x = slice -> [dimZ][dimY].  h_pressure holds elements of
+ * the solver dtype; h_position may be NULL.  A slice beyond the dimension is PFDTD_ERR_RANGE (the
+ * reference logs and skips the capture). */
+int pfdtd_capture_slice(pfdtd_solver* s, uint32_t slice, uint32_t orientation, void* h_pressure, uint8_t* h_position);
+/* captureMesh (visualizationUtils.cu:111-125): the whole current field, [dimZ][dimY][dimX] of the dtype,
+ * assembled from the planes each partition owns (the reference copies partition 0 only). */
+int pfdtd_capture_mesh(pfdtd_solver* s, void* h_field);
+
 /* ---- single samples (CudaMesh::setSample/addSample/getSample, cudaMesh.h:321-404,497-584) -- */
 int pfdtd_set_sample(pfdtd_solver* s, uint32_t x, uint32_t y, uint32_t z, double value);
 int pfdtd_add_sample(pfdtd_solver* s, uint32_t x, uint32_t y, uint32_t z, double value);

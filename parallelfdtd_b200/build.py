@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpfdtd_b200.so")
-SOURCES = ["pfdtd_api.cu", "update_kernels.cu", "interp_kernels.cu", "mesh_kernels.cu", "srcrec_kernels.cu"]
+SOURCES = ["pfdtd_api.cu", "update_kernels.cu", "interp_kernels.cu", "mesh_kernels.cu", "srcrec_kernels.cu", "capture_kernels.cu"]
 HEADERS = ["pfdtd_internal.h", "update_math.cuh", "tma_common.cuh", "update_host.cuh", os.path.join("..", "..", "include", "pfdtd.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -78,6 +78,31 @@ def build_host(force: bool = False) -> str:
     return HOST_LIB
 
 
+PY_MODULE_SRC = os.path.join(HOST_DIR, "AppPy.cpp")
+
+
+def py_module_path() -> str:
+    import sysconfig
+    return os.path.join(HERE, "libPyFDTD" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_py_module(force: bool = False) -> str:
+    """The Python module `libPyFDTD` (API of the reference's boost::python module, src/AppPy.cpp) -> in-tree
+    CPython extension linked against libpfdtd_host.so / libpfdtd_b200.so."""
+    import sysconfig
+    import pybind11
+    build_host()
+    out = py_module_path()
+    deps = [PY_MODULE_SRC, HOST_LIB, os.path.join(HOST_DIR, "App.h")]
+    if force or any(_newer(d, out) for d in deps):
+        subprocess.check_call([_host_cxx(), "-std=c++17", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall",
+                               "-I", HOST_DIR, "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
+                               "-o", out, PY_MODULE_SRC, "-L", HERE, "-l:libpfdtd_host.so", "-l:libpfdtd_b200.so",
+                               "-Wl,-rpath,$ORIGIN"])
+    return out
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose=True))
     print(build_host(force="--force" in sys.argv))
+    print(build_py_module(force="--force" in sys.argv))

@@ -181,6 +181,22 @@ class Solver:
         _check(lib().pfdtd_export_partition_pressure(self._h, C.c_uint32(k), C.c_int(which), _ptr(out)))
         return out
 
+    def capture_slice(self, slice_idx, orientation, with_position=False):
+        """captureSliceFast (reference visualizationUtils.cu:127-254): [Y][X] / [Z][X] / [Z][Y] for orientation 0 / 1 / 2."""
+        X, Y, Z = self.dims()
+        shape = {0: (Y, X), 1: (Z, X), 2: (Z, Y)}.get(int(orientation), (0, 0))
+        out = np.empty(shape, dtype=self.np_dtype)
+        pos = np.empty(shape, dtype=np.uint8) if with_position else None
+        _check(lib().pfdtd_capture_slice(self._h, C.c_uint32(slice_idx), C.c_uint32(orientation), _ptr(out), _ptr(pos)))
+        return (out, pos) if with_position else out
+
+    def capture_mesh(self):
+        """captureMesh (reference visualizationUtils.cu:111-125): the whole current field [Z][Y][X]."""
+        X, Y, Z = self.dims()
+        out = np.empty((Z, Y, X), dtype=self.np_dtype)
+        _check(lib().pfdtd_capture_mesh(self._h, _ptr(out)))
+        return out
+
     def set_sample(self, x, y, z, v):
         _check(lib().pfdtd_set_sample(self._h, C.c_uint32(x), C.c_uint32(y), C.c_uint32(z), C.c_double(v)))
 

@@ -919,6 +919,78 @@ int pfdtd_export_partition_pressure(pfdtd_solver* s, uint32_t k, int which, void
   return PFDTD_OK;
 }
 
+// planes of partition k that belong to it (halo planes belong to the neighbours): local [lo, hi)
+static void owned_planes(const pfdtd_solver* s, size_t k, int64_t* lo, int64_t* hi) {
+  *lo = k == 0 ? 0 : 1;
+  *hi = k + 1 == s->parts.size() ? s->parts[k].size : s->parts[k].size - 1;
+}
+
+int pfdtd_capture_slice(pfdtd_solver* s, uint32_t slice, uint32_t orientation, void* h_pressure, uint8_t* h_position) {
+  PF_CHECK(s && h_pressure, PFDTD_ERR_INVALID, "null argument");
+  PF_CHECK(!s->parts.empty(), PFDTD_ERR_INVALID, "pfdtd_capture_slice before pfdtd_make_partition");
+  PF_CHECK(orientation <= 2, PFDTD_ERR_INVALID, "orientation %u (0 xy, 1 xz, 2 yz)", orientation);
+  const uint32_t lim = orientation == 0 ? s->Z : (orientation == 1 ? s->Y : s->X);
+  PF_CHECK(slice < lim, PFDTD_ERR_RANGE, "slice %u out of bounds %u", slice, lim);
+  PF_TRY(sync_all(s));
+  const size_t es = esize(s);
+  const size_t XY = (size_t)s->X * s->Y;
+  if (orientation == 0) {                                  // one contiguous plane of the first partition that holds z
+    for (size_t k = 0; k < s->parts.size(); k++) {
+      Partition& p = s->parts[k];
+      if ((int64_t)slice < p.first || (int64_t)slice >= p.first + p.size) continue;
+      PF_CUDA(cudaSetDevice(p.device));
+      const size_t off = (size_t)(slice - p.first) * XY;
+      PF_CUDA(cudaMemcpy(h_pressure, (const char*)p.P[s->cur] + off * es, XY * es, cudaMemcpyDeviceToHost));
+      if (h_position) PF_CUDA(cudaMemcpy(h_position, p.pos + off, XY, cudaMemcpyDeviceToHost));
+      return PFDTD_OK;
+    }
+    PF_CHECK(false, PFDTD_ERR_RANGE, "slice %u is in no partition", slice);
+  }
+  const size_t w = orientation == 1 ? s->X : s->Y;
+  for (size_t k = 0; k < s->parts.size(); k++) {
+    Partition& p = s->parts[k];
+    int64_t lo, hi;
+    owned_planes(s, k, &lo, &hi);
+    if (hi <= lo) continue;
+    PF_CUDA(cudaSetDevice(p.device));
+    const size_t n = w * (size_t)(hi - lo);
+    void* d_p = nullptr;
+    uint8_t* d_pos = nullptr;
+    PF_CUDA(cudaMalloc(&d_p, n * es));
+    if (h_position) PF_CUDA(cudaMalloc((void**)&d_pos, n));
+    int rc = launch_capture_slice(s->dtype, p.P[s->cur], p.pos, d_p, d_pos, s->X, s->Y, (uint32_t)lo, (uint32_t)(hi - lo), slice,
+                                  (int)orientation, p.s_main);
+    s->launch_count++;
+    cudaError_t e = rc == PFDTD_OK ? cudaStreamSynchronize(p.s_main) : cudaSuccess;
+    const size_t row0 = (size_t)(p.first + lo) * w;
+    if (rc == PFDTD_OK && e == cudaSuccess) e = cudaMemcpy((char*)h_pressure + row0 * es, d_p, n * es, cudaMemcpyDeviceToHost);
+    if (rc == PFDTD_OK && e == cudaSuccess && h_position) e = cudaMemcpy(h_position + row0, d_pos, n, cudaMemcpyDeviceToHost);
+    cudaFree(d_p);
+    if (d_pos) cudaFree(d_pos);
+    if (rc != PFDTD_OK) return rc;
+    PF_CUDA(e);
+  }
+  return PFDTD_OK;
+}
+
+int pfdtd_capture_mesh(pfdtd_solver* s, void* h_field) {
+  PF_CHECK(s && h_field, PFDTD_ERR_INVALID, "null argument");
+  PF_CHECK(!s->parts.empty(), PFDTD_ERR_INVALID, "pfdtd_capture_mesh before pfdtd_make_partition");
+  PF_TRY(sync_all(s));
+  const size_t es = esize(s);
+  const size_t XY = (size_t)s->X * s->Y;
+  for (size_t k = 0; k < s->parts.size(); k++) {
+    Partition& p = s->parts[k];
+    int64_t lo, hi;
+    owned_planes(s, k, &lo, &hi);
+    if (hi <= lo) continue;
+    PF_CUDA(cudaSetDevice(p.device));
+    PF_CUDA(cudaMemcpy((char*)h_field + (size_t)(p.first + lo) * XY * es, (const char*)p.P[s->cur] + (size_t)lo * XY * es,
+                       (size_t)(hi - lo) * XY * es, cudaMemcpyDeviceToHost));
+  }
+  return PFDTD_OK;
+}
+
 int pfdtd_get_device_pointers(pfdtd_solver* s, uint32_t k, void** d_pressure, void** d_pressure_past, uint8_t** d_position_idx,
                               uint8_t** d_material_idx) {
   PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");

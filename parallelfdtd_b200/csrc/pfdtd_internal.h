@@ -112,6 +112,10 @@ int launch_update_interp_tma(const UpdateArgs& a, const TmaMaps& maps, const Tma
 int launch_update_interp_plain(const UpdateArgs& a);
 const char* tma_tile_name(int dtype, int tile);
 
+// ---- capture kernel (capture_kernels.cu): planes [z_lo, z_lo+nz) of a partition, orientation 1 (xz) or 2 (yz)
+int launch_capture_slice(int dtype, const void* P, const uint8_t* pos, void* out_p, uint8_t* out_pos, uint32_t X, uint32_t Y,
+                         uint32_t z_lo, uint32_t nz, uint32_t slice, int orientation, cudaStream_t stream);
+
 // ---- source / receiver kernel (srcrec_kernels.cu) -------------------------------------------------
 struct SrcRecArgs {
   int dtype;

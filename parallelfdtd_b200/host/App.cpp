@@ -139,34 +139,57 @@ void App::executeStep() {
 }
 
 // slice / mesh captures at the listed steps (reference visualizationUtils.cu:111-254 captureSliceFast /
-// captureMesh): the current pressure field is gathered from all slabs (halo planes dropped)
+// captureMesh, called from executeStep, App.cpp:421-431): the slice is gathered on the device(s) from the planes
+// each slab owns and only the slice crosses PCIe.  A slice beyond the mesh is logged and skipped like the reference.
 void App::captureIfDue_() {
-  bool due = false;
-  for (size_t i = 0; i < step_to_capture_.size(); i++) due |= step_to_capture_[i] == current_step_;
-  for (size_t i = 0; i < mesh_to_capture_.size(); i++) due |= mesh_to_capture_[i] == current_step_;
-  if (!due) return;
   const unsigned int X = m_mesh.getDimX(), Y = m_mesh.getDimY(), Z = m_mesh.getDimZ();
-  std::vector<float> field((size_t)X * Y * Z, 0.f);
-  const unsigned int np = m_mesh.getNumberOfPartitions();
-  for (unsigned int k = 0; k < np; k++) {
-    const unsigned int first = m_mesh.getFirstSliceIdx((int)k), nz = m_mesh.getPartitionSize((int)k);
-    std::vector<float> slab((size_t)nz * X * Y);
-    pfdtd_safe(pfdtd_export_partition_pressure(m_mesh.handle(), k, 0, &slab[0]), "App::capture");
-    const unsigned int lo = k == 0 ? 0 : 1, hi = k + 1 == np ? nz : nz - 1;   // own planes; halos belong to the neighbours
-    for (unsigned int z = lo; z < hi; z++)
-      std::copy(slab.begin() + (size_t)z * X * Y, slab.begin() + (size_t)(z + 1) * X * Y, field.begin() + (size_t)(first + z) * X * Y);
-  }
   for (size_t i = 0; i < step_to_capture_.size(); i++) {
     if (step_to_capture_[i] != current_step_) continue;
     const unsigned int s = slice_to_capture_[i], o = slice_orientation_[i];
-    std::vector<float> img;
-    if (o == 0) { img.assign(field.begin() + (size_t)s * X * Y, field.begin() + (size_t)(s + 1) * X * Y); }                  // xy at z = s
-    else if (o == 1) { img.resize((size_t)X * Z); for (unsigned int z = 0; z < Z; z++) for (unsigned int x = 0; x < X; x++) img[(size_t)z * X + x] = field[((size_t)z * Y + s) * X + x]; }   // xz at y = s
-    else { img.resize((size_t)Y * Z); for (unsigned int z = 0; z < Z; z++) for (unsigned int y = 0; y < Y; y++) img[(size_t)z * Y + y] = field[((size_t)z * Y + y) * X + s]; }            // yz at x = s
+    const unsigned int lim = o == 0 ? Z : (o == 1 ? Y : X);
+    if (o > 2 || s >= lim) {
+      log_msg<LOG_INFO>(L"App::capture - slice %u out of bounds %u, no capture made") % s % lim;
+      continue;
+    }
+    CaptureShape sh;
+    sh.cols = o == 2 ? Y : X; sh.rows = o == 0 ? Y : Z; sh.slice = s; sh.orientation = o; sh.step = current_step_;
+    std::vector<float> img((size_t)sh.rows * sh.cols);
+    std::vector<unsigned char> pos((size_t)sh.rows * sh.cols);
+    m_mesh.captureSlice<float>(s, o, &img[0], &pos[0]);
     slice_captures_.push_back(img);
+    slice_positions_.push_back(pos);
+    slice_shapes_.push_back(sh);
   }
-  for (size_t i = 0; i < mesh_to_capture_.size(); i++)
-    if (mesh_to_capture_[i] == current_step_) mesh_captures_.push_back(field);
+  for (size_t i = 0; i < mesh_to_capture_.size(); i++) {
+    if (mesh_to_capture_[i] != current_step_) continue;
+    mesh_captures_.push_back(std::vector<float>((size_t)X * Y * Z));
+    m_mesh.captureMesh<float>(&mesh_captures_.back()[0]);
+  }
+}
+
+// the pixel mapping of the reference's capture callback (App::saveBitmap, App.cpp:492-567) without the TGA writer:
+// solid nodes white, air/boundary nodes green for positive and blue for negative pressure on a log scale of
+// capture_db_ / 10 decades.  RGBA, row-major like the capture.
+std::vector<unsigned char> App::getSliceCaptureRGBA(unsigned int i) {
+  const std::vector<float>& d = slice_captures_.at(i);
+  const std::vector<unsigned char>& pos = slice_positions_.at(i);
+  std::vector<unsigned char> px(d.size() * 4, 0);
+  const float dB = capture_db_ / 10.f;
+  for (size_t e = 0; e < d.size(); e++) {
+    unsigned char* q = &px[4 * e];
+    q[3] = 255;
+    const unsigned char c_pos = pos[e];
+    const bool centred = m_parameters.getUpdateType() == SRL;
+    // forward schemes: switch bit clear = solid; the reference paints "switch set and K != 6" white, which marks the
+    // boundary shell; the centred scheme's position byte has no neighbour count, so there solid (switch clear) is white
+    const bool white = centred ? (c_pos >> 7) == 0 : ((c_pos >> 7) == 1 && (c_pos & 0x7F) != 6);
+    if (white) { q[0] = q[1] = q[2] = 255; continue; }
+    const float c = d[e];
+    float v = (std::log10(c * c) + dB) / dB;
+    v = v > 0.f ? (v < 1.f ? v : 1.f) : 0.f;
+    if (c >= 0.f) q[1] = (unsigned char)(v * 255); else q[2] = (unsigned char)(v * 255);
+  }
+  return px;
 }
 
 void App::resetPressureMesh() { m_mesh.resetPressures(); current_step_ = 0; }

@@ -60,6 +60,10 @@ class App {
     step_to_capture_.push_back(step); slice_to_capture_.push_back(slice); slice_orientation_.push_back(orientation); }
   void addMeshToCapture(unsigned int step) { mesh_to_capture_.push_back(step); }
   const std::vector<float>& getSliceCaptureAt(unsigned int i) { return slice_captures_.at(i); }
+  const std::vector<unsigned char>& getSlicePositionCaptureAt(unsigned int i) { return slice_positions_.at(i); }
+  struct CaptureShape { unsigned int rows, cols, slice, orientation, step; };
+  CaptureShape getSliceCaptureShapeAt(unsigned int i) { return slice_shapes_.at(i); }
+  std::vector<unsigned char> getSliceCaptureRGBA(unsigned int i);
   unsigned int getNumberOfSliceCaptures() { return (unsigned int)slice_captures_.size(); }
 
   float getVolume();
@@ -97,6 +101,8 @@ class App {
   std::vector<double> responses_double_;
   std::vector<std::vector<float> > mesh_captures_;
   std::vector<std::vector<float> > slice_captures_;
+  std::vector<std::vector<unsigned char> > slice_positions_;
+  std::vector<CaptureShape> slice_shapes_;
   float time_per_step_;
   unsigned int num_elements_;
   std::vector<unsigned char> vol_bid_, vol_mat_;

@@ -2,6 +2,9 @@
 // src/base/GeometryHandler.h: vertices/indices, bounding box, per-triangle surface area).  Header-only.
 #pragma once
 #include <cmath>
+#include <iterator>
+#include <map>
+#include <string>
 #include <stdexcept>
 #include <vector>
 #include "../math/geomMath.h"
@@ -31,6 +34,24 @@ class GeometryHandler {
   nv::Vec3f getBoundingBoxMin() const { return bb_min_; }
   nv::Vec3f getBoundingBoxMax() const { return bb_max_; }
   float getSurfaceAreaAt(unsigned int t) const { return areas_.at(t); }
+  // named triangle groups (reference GeometryHandler.h:95-133, GeometryHandler.cpp:177-201): a list holding an index
+  // below zero or beyond the triangle count is ignored
+  void setLayerIndices(std::vector<int> indices, std::string name) {
+    for (size_t i = 0; i < indices.size(); i++)
+      if (indices[i] < 0 || indices[i] >= (int)getNumberOfTriangles()) return;
+    layers_[name] = indices;
+  }
+  unsigned int getNumberOfLayers() const { return (unsigned int)layers_.size(); }
+  std::string getLayerNameAt(int idx) const {
+    if (idx < 0 || idx >= (int)layers_.size()) return std::string();
+    std::map<std::string, std::vector<int> >::const_iterator it = layers_.begin();
+    std::advance(it, idx);
+    return it->first;
+  }
+  std::vector<int> getLayerIndices(const std::string& name) const {
+    std::map<std::string, std::vector<int> >::const_iterator it = layers_.find(name);
+    return it == layers_.end() ? std::vector<int>() : it->second;
+  }
   float getTotalSurfaceArea() const { float s = 0.f; for (size_t i = 0; i < areas_.size(); i++) s += areas_[i]; return s; }
 
  private:
@@ -54,5 +75,6 @@ class GeometryHandler {
   std::vector<unsigned int> indices_;
   std::vector<float> vertices_;
   std::vector<float> areas_;
+  std::map<std::string, std::vector<int> > layers_;
   nv::Vec3f bb_min_, bb_max_;
 };

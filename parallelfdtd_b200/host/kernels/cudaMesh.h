@@ -4,6 +4,7 @@
 // streams; this class only keeps the call shapes so App, the MEX gateway and the reference's tests
 // compile against it unchanged.
 #pragma once
+#include <cstdlib>
 #include <vector>
 #include "cudaUtils.h"
 
@@ -118,6 +119,27 @@ class CudaMesh {
     double v = 0; pfdtd_safe(pfdtd_get_sample(solver_, x, y, z, &v), "CudaMesh::getSample"); return (T)v; }
   template <typename T> T getSampleAt(unsigned int x, unsigned int y, unsigned int z, unsigned int partition) {
     double v = 0; pfdtd_safe(pfdtd_get_sample_at(solver_, x, y, z, partition, &v), "CudaMesh::getSampleAt"); return (T)v; }
+
+  // ---- slices (reference cudaMesh.h:600-646 getSlice / getPositionSlice; malloc'ed, caller frees, orientation 0
+  // only as in the reference -- the other orientations go through captureSlice)
+  template <typename T> T* getSlice(unsigned int slice, unsigned int orientation) {
+    if (orientation != 0 || (sizeof(T) == 8) != double_) return (T*)0;
+    T* data = (T*)std::malloc((size_t)getDimXY() * sizeof(T));
+    pfdtd_safe(pfdtd_capture_slice(solver_, slice, 0, data, 0), "CudaMesh::getSlice");
+    return data;
+  }
+  unsigned char* getPositionSlice(unsigned int slice, unsigned int orientation) {
+    if (orientation != 0) return (unsigned char*)0;
+    const size_t n = getDimXY();
+    std::vector<unsigned char> scratch(n * (double_ ? 8 : 4));
+    unsigned char* data = (unsigned char*)std::malloc(n);
+    pfdtd_safe(pfdtd_capture_slice(solver_, slice, 0, &scratch[0], data), "CudaMesh::getPositionSlice");
+    return data;
+  }
+  // captureSliceFast / captureMesh of visualizationUtils.cu:111-254 as members: device-side gather, slice-sized D2H
+  template <typename T> void captureSlice(unsigned int slice, unsigned int orientation, T* pressure, unsigned char* position) {
+    pfdtd_safe(pfdtd_capture_slice(solver_, slice, orientation, pressure, position), "CudaMesh::captureSlice"); }
+  template <typename T> void captureMesh(T* field) { pfdtd_safe(pfdtd_capture_mesh(solver_, field), "CudaMesh::captureMesh"); }
 
   // ---- step pieces (reference cudaMesh.h:755-791)
   void switchHalos() { pfdtd_safe(pfdtd_switch_halos(solver_), "CudaMesh::switchHalos"); }
