@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_plane(const T* __restrict__ pt, int r, int 
 
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: TY consumer warps (one tile row each) + 1 producer warp
 template <typename T, bool HAS_D3, int TY, int NST, int DIF>
-__global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (TY == 8 ? 72 : 56) : 96)
+__global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (TY == 7 ? 64 : (TY == 8 ? 72 : 56)) : (TY == 7 ? 128 : 96))
     fdtd_update_interp_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                            const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                            T* __restrict__ Pn, T d1, T d2, T d3, T d4, int X, int Y, int z_begin, int z_end, int chunk,
@@ -117,6 +117,11 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
   const int64_t XY = (int64_t)X * Y;
   constexpr uint32_t AIR4 = CLS_AIR * 0x01010101u;
 
+  // filter boundaries: entries and prefetched states of this warp's row (update_math.cuh DifRow), started before the
+  // first wait on the pipeline so that the entry -> state round trips overlap the first planes' TMA loads
+  constexpr int DMO = DIF ? DIF : 1;
+  DifRow<T, DMO> drow;
+  if (DIF) drow.start(dif, z_lo, z_hi, gy, Y, lane);
   Plane3<T> pm, pc, pp;                      // planes z-1, z, z+1
   {
     mbar_wait(&bar_full[0], 0);
@@ -128,30 +133,9 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
     // write into the stage could overtake it (update_kernels.cu has the B200 observation).
   }
 
-  // DIF: lane l holds the rowbase entry of plane (j & ~31) + l of this warp's row; st_nxt / st_cur are the filter
-  // states fetched for the next / this plane (dif_fetch)
-  constexpr int DMO = DIF ? DIF : 1;
-  uint32_t rowbases = 0u;
-  T st_cur[DMO], st_nxt[DMO];
-#pragma unroll
-  for (int i = 0; i < DMO; i++) st_cur[i] = st_nxt[i] = (T)0;
-  if (DIF) {
-    rowbases = dif_load_rowbases<T>(dif, z_lo, z_hi, gy, Y, lane);
-    dif_fetch<T, DMO>(dif, __shfl_sync(0xffffffffu, rowbases, 0), lane, st_nxt);
-  }
   for (int j = 0; j < n; j++) {
     const int i2 = j + 2;
     const int s2 = i2 % NST;
-    uint32_t dif_entry = 0u;
-    if (DIF) {   // this plane's states were fetched an iteration ago; start the next plane's fetch now
-      dif_entry = __shfl_sync(0xffffffffu, rowbases, j & 31);
-#pragma unroll
-      for (int i = 0; i < DMO; i++) st_cur[i] = st_nxt[i];
-      if (j + 1 < n) {
-        if (((j + 1) & 31) == 0) rowbases = dif_load_rowbases<T>(dif, z_lo + j + 1, z_hi, gy, Y, lane);
-        dif_fetch<T, DMO>(dif, __shfl_sync(0xffffffffu, rowbases, (j + 1) & 31), lane, st_nxt);
-      }
-    }
     mbar_wait(&bar_full[s2], (uint32_t)((i2 / NST) & 1));
     const unsigned char* st2 = smem_raw + (size_t)s2 * G::STAGE_BYTES;
     load_plane<T, TY, HAS_D3>(reinterpret_cast<const T*>(st2 + G::PT_OFF), r, lane, pp);
@@ -174,7 +158,7 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
         }
       }
     }
-    if (DIF && (dif_entry & DIF_HAS)) dif_apply_row<T, DMO>(res.v, old.v, pw, active, lane, dif_entry, st_cur, dif, s_dif);
+    if (DIF) drow.apply(j, res.v, old.v, pw, active, lane, dif, s_dif);
     if (active) stg4(Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx, res);
     // the store above consumed everything read from stage s2 (and, at j == 0, from the two prologue stages)
     __syncwarp();
@@ -182,6 +166,7 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
       mbar_arrive(&bar_empty[s2]);
       if (j == 0) { mbar_arrive(&bar_empty[0]); mbar_arrive(&bar_empty[1 % NST]); }
     }
+    if (DIF) drow.next(dif, j, n, z_lo, z_hi, gy, Y, lane);
     pm = pc;
     pc = pp;
   }
@@ -244,12 +229,13 @@ int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occup
 template <typename T, bool HAS_D3>
 int dispatch_interp(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
   // tile variants shared with the 7-point kernel: only the one-row-per-warp shapes apply here
-  if (a.dif_order > 0) {   // filter boundaries: the 128x8 shape, one kernel per order
+  if (a.dif_order > 0) {   // filter boundaries: one kernel per order; fp32 128x8, fp64 128x7, five stages
+    constexpr int DTY = sizeof(T) == 4 ? 8 : 7, DNST = 5;
     switch (a.dif_order) {
-      case 1: return launch_interp_t<T, HAS_D3, 8, 4, 1>(a, m, chunk, occ);
-      case 2: return launch_interp_t<T, HAS_D3, 8, 4, 2>(a, m, chunk, occ);
-      case 3: return launch_interp_t<T, HAS_D3, 8, 4, 3>(a, m, chunk, occ);
-      case 4: return launch_interp_t<T, HAS_D3, 8, 4, 4>(a, m, chunk, occ);
+      case 1: return launch_interp_t<T, HAS_D3, DTY, DNST, 1>(a, m, chunk, occ);
+      case 2: return launch_interp_t<T, HAS_D3, DTY, DNST, 2>(a, m, chunk, occ);
+      case 3: return launch_interp_t<T, HAS_D3, DTY, DNST, 3>(a, m, chunk, occ);
+      case 4: return launch_interp_t<T, HAS_D3, DTY, DNST, 4>(a, m, chunk, occ);
     }
     set_error("filter order %d is not supported", a.dif_order);
     return PFDTD_ERR_INVALID;
@@ -257,6 +243,8 @@ int dispatch_interp(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, 
   switch (tile) {
     case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, 0>(a, m, chunk, occ);
     case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4, 0>(a, m, chunk, occ);
+    case 6: case 7: return launch_interp_t<T, HAS_D3, 7, 5, 0>(a, m, chunk, occ);
+    case 8: return launch_interp_t<T, HAS_D3, 8, 5, 0>(a, m, chunk, occ);
   }
   set_error("tile variant %d is not available for the interpolated schemes", tile);
   return PFDTD_ERR_INVALID;

@@ -187,13 +187,24 @@ __global__ void count_dif_segments_kernel(const uint8_t* __restrict__ cls, int X
     const int sx = (int)(w % segs);
     const int64_t row = w / segs;             // z*Y + y
     const int z = (int)(row / Y);
-    uint32_t c = 0;
+    uint32_t m = 0;                             // bit q: voxel q of this lane is a filter voxel
     if (z >= 1 && z < nz - 1) {
       const int x = sx * 128 + 4 * lane;
       for (int q = 0; q < 4; q++)
-        if (x + q < X) c += cls[row * X + x + q] >= dif_lo;
+        if (x + q < X && cls[row * X + x + q] >= dif_lo) m |= 1u << q;
     }
+    uint32_t c = __popc(m);
     for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    const uint32_t lanes = __ballot_sync(0xffffffffu, m != 0u);
+    const int first = lanes ? __ffs((int)lanes) - 1 : 0;
+    const uint32_t mf = __shfl_sync(0xffffffffu, m, first);
+    if (lanes) {   // x offset of the first filter voxel; bit 15: they form one contiguous run
+      const int last = 31 - __clz((int)lanes);
+      const uint32_t ml = __shfl_sync(0xffffffffu, m, last);
+      const int xf = 4 * first + __ffs((int)mf) - 1, xl = 4 * last + (31 - __clz((int)ml));
+      c |= (uint32_t)xf << 8;
+      if ((uint32_t)(xl - xf + 1) == (c & 0xffu)) c |= 1u << 15;
+    }
     if (lane == 0) counts[w] = c;
   }
 }

@@ -521,6 +521,9 @@ int pfdtd_device_mem_mb(int device, int* out_total_mb, int* out_free_mb) {
 int pfdtd_create(pfdtd_solver** out) {
   PF_CHECK(out != nullptr, PFDTD_ERR_INVALID, "null out pointer");
   *out = new pfdtd_solver();
+  // tuning knobs for sweeps: defaults of PFDTD_OPT_TMA_TILE / PFDTD_OPT_TMA_CHUNK (pfdtd_set_option still overrides)
+  if (const char* e = getenv("PFDTD_TMA_TILE")) (*out)->opt_tma_tile = atoll(e);
+  if (const char* e = getenv("PFDTD_TMA_CHUNK")) (*out)->opt_tma_chunk = atoll(e);
   return PFDTD_OK;
 }
 
@@ -808,17 +811,35 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       PF_CHECK(s->n_lossy <= 64, PFDTD_ERR_INVALID, "filter (DIF) boundaries support <= 64 lossy node classes, mesh has %u", s->n_lossy);
       const int segs = ((int)s->X + 127) / 128;
       const size_t n_seg = (size_t)p.size * s->Y * segs;
-      PF_CUDA(cudaMalloc(&p.dif_rowbase, n_seg * sizeof(uint32_t)));
+      PF_CUDA(cudaMalloc(&p.dif_rowbase, n_seg * 2 * sizeof(uint32_t)));
       PF_TRY(launch_count_dif_segments(p.cls, (int)s->X, (int)s->Y, (int)p.size, s->dif_lo, p.dif_rowbase, 0));
-      std::vector<uint32_t> cnt(n_seg);
+      std::vector<uint32_t> cnt(n_seg), ent(2 * n_seg);
       PF_CUDA(cudaMemcpy(cnt.data(), p.dif_rowbase, n_seg * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      if (const char* dbg = getenv("PFDTD_DEBUG_DIF_KEEP")) {   // timing experiments only: 0 none, 1 singles, 2 multi
+        const int keep = atoi(dbg);
+        for (size_t i = 0; i < n_seg; i++) {
+          const uint32_t c = cnt[i] & 0xffu;
+          if (keep == 0 || (keep == 1 && c != 1) || (keep == 2 && c == 1)) cnt[i] = 0;
+        }
+      }
       uint64_t run = 0;
-      // entry = index of the segment's first boundary voxel | bit 31 when the segment has any (DIF_HAS, update_math.cuh)
-      for (size_t i = 0; i < n_seg; i++) { const uint32_t c = cnt[i]; cnt[i] = (uint32_t)run | (c ? 0x80000000u : 0u); run += c; }
+      // entry = {index of the segment's first filter voxel, flags}: DIF_HAS | DIF_SINGLE | DIF_RUN, x offset of the first
+      // voxel in bits 0..6, their number in bits 8..15 (update_math.cuh)
+      // filter voxels are numbered z-fastest within a row segment: a wall crossing the rows gives every (row, segment)
+      // column consecutive indices along the march
+      for (size_t ys = 0; ys < (size_t)s->Y * segs; ys++)
+        for (size_t z = 0; z < (size_t)p.size; z++) {
+          const size_t i = z * (size_t)s->Y * segs + ys;
+          const uint32_t c = cnt[i] & 0xffu, xoff = (cnt[i] >> 8) & 0x7fu;
+          ent[2 * i] = (uint32_t)run;
+          const bool is_run = (cnt[i] >> 15) & 1u;
+          ent[2 * i + 1] = c == 0 ? 0u : (c == 1 ? (0xC0000000u | xoff) : (is_run ? (0xA0000000u | (c << 8) | xoff) : 0x80000000u));
+          run += c;
+        }
       PF_CHECK(run < 0x7fffffffull, PFDTD_ERR_INVALID, "too many boundary voxels in one slab");
       p.dif_nb = (uint32_t)run;
-      PF_CUDA(cudaMemcpy(p.dif_rowbase, cnt.data(), n_seg * sizeof(uint32_t), cudaMemcpyHostToDevice));
-      const size_t sb = (size_t)std::max<uint32_t>(p.dif_nb, 1) * s->opt_dif_order * es;
+      PF_CUDA(cudaMemcpy(p.dif_rowbase, ent.data(), ent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      const size_t sb = (size_t)std::max<uint32_t>(p.dif_nb, 1) * dif_state_pad((int)s->opt_dif_order) * es;
       PF_CUDA(cudaMalloc(&p.dif_state, sb));
       PF_CUDA(cudaMemset(p.dif_state, 0, sb));
       PF_CUDA(cudaMalloc(&p.dif_table, std::max<uint32_t>(s->n_lossy, 1) * dif_entry_bytes(s->dtype)));
@@ -826,11 +847,9 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
     }
     if (p.use_tma) {
       int64_t want_tile = s->opt_tma_tile;
-      if (s->opt_dif_order > 0) want_tile = 1;   // the filter kernels exist for the 128x8 one-row-per-warp tile only
-      if (s->scheme == SCH_INTERP && want_tile == 0) want_tile = 1;   // 128x8, one row per warp (profiles/r01_sweep.md)
-      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->X, (int)s->Y, nplanes, p.device, want_tile, s->opt_tma_chunk,
+      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->opt_dif_order, (int)s->X, (int)s->Y, nplanes, p.device, want_tile, s->opt_tma_chunk,
                              &p.cfg_full));
-      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->X, (int)s->Y, std::max(1, nplanes - 2), p.device,
+      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->opt_dif_order, (int)s->X, (int)s->Y, std::max(1, nplanes - 2), p.device,
                              p.cfg_full.tile + 1, s->opt_tma_chunk, &p.cfg_int));
       p.cfg_edge = TmaConfig{p.cfg_full.tile, 1};
       for (int c = 0; c < 2; c++)
@@ -1101,7 +1120,7 @@ int pfdtd_reset_pressures(pfdtd_solver* s) {
     const size_t n = (size_t)p.size * s->X * s->Y * esize(s);
     PF_CUDA(cudaMemset(p.P[0], 0, n));
     PF_CUDA(cudaMemset(p.P[1], 0, n));
-    if (p.dif_state) PF_CUDA(cudaMemset(p.dif_state, 0, (size_t)std::max<uint32_t>(p.dif_nb, 1) * s->opt_dif_order * esize(s)));
+    if (p.dif_state) PF_CUDA(cudaMemset(p.dif_state, 0, (size_t)std::max<uint32_t>(p.dif_nb, 1) * dif_state_pad((int)s->opt_dif_order) * esize(s)));
   }
   return PFDTD_OK;
 }

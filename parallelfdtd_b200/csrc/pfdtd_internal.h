@@ -79,8 +79,8 @@ struct UpdateArgs {
   int matidx_as_written;
   // digital impedance filters (0 = off)
   int dif_order;
-  void* dif_state;              // [order][dif_nb] of the dtype
-  const uint32_t* dif_rowbase;  // [nz][Y][ceil(X/128)]
+  void* dif_state;              // [dif_nb][dif_state_pad(order)] of the dtype
+  const uint32_t* dif_rowbase;  // [nz][Y][ceil(X/128)][2]: index of the segment's first filter voxel, flags (update_math.cuh)
   const void* dif_table;        // DifEntry<T>[n_dif]
   uint32_t dif_nb;
   uint32_t dif_lo;
@@ -102,9 +102,12 @@ int build_class_table(const UpdateArgs& a, const uint32_t* d_keys, int n_classes
 size_t class_entry_bytes(int dtype);
 size_t dif_entry_bytes(int dtype);
 int build_dif_table(const UpdateArgs& a, const uint32_t* d_keys /* keys of the lossy classes */, int n_dif, void* d_table);
-// per 128-voxel row segment: number of voxels whose class id is >= dif_lo, planes [1, nz-1) only
+// per 128-voxel row segment: number of voxels whose class id is >= dif_lo (bits 0..7) and the x offset of the
+// first of them inside the segment (bits 8..14), planes [1, nz-1) only
+inline int dif_state_pad(int order) { return order <= 1 ? 1 : (order == 2 ? 2 : 4); }
 int launch_count_dif_segments(const uint8_t* d_cls, int X, int Y, int nz, uint32_t dif_lo, uint32_t* d_counts, cudaStream_t stream);
-int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk, TmaConfig* out);
+int tma_pick_config(int dtype, int scheme, int dif_order, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk,
+                    TmaConfig* out);
 int launch_update_tma(const UpdateArgs& a, const TmaMaps& maps, const TmaConfig& cfg);
 int launch_update_plain(const UpdateArgs& a);
 // 27-point kernels (interp_kernels.cu); the TMA variant shares TmaMaps / TmaConfig with the 7-point one

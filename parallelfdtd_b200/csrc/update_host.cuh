@@ -27,7 +27,7 @@ template <typename T>
 inline DifArgs<T> make_dif(const UpdateArgs& a) {
   DifArgs<T> d;
   d.state = (T*)a.dif_state;
-  d.rowbase = a.dif_rowbase;
+  d.rowbase = (const uint2*)a.dif_rowbase;
   d.table = (const DifEntry<T>*)a.dif_table;
   d.nb = a.dif_nb;
   d.order = a.dif_order;

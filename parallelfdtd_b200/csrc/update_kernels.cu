@@ -72,7 +72,10 @@ int launch_update_plain(const UpdateArgs& a) {
 // ceil(k/4) warps' worth on the fullest one.  The default 128x8 one-row-per-warp shape (9 warps, 42.5 / 79 KiB of
 // stages): fp32 forward fits four CTAs per SM in 56 registers, the centred scheme and the filter kernels three in
 // 72, fp64 two in 96; the other shapes just have to fit one CTA.
-constexpr int tma_max_regs(size_t esize, int scheme, int ty, int rpw, int dif) {
+constexpr int tma_max_regs(size_t esize, int scheme, int ty, int rpw, int nst, int dif) {
+  // 128x7: seven consumer warps + the producer = 8 warps, two per sub-partition and CTA: 64 registers with four
+  // resident CTAs (fp32), 80 with three, 128 with two (fp64)
+  if (ty == 7 && rpw == 1) return esize == 4 ? (nst >= 6 ? 80 : 64) : 128;
   if (ty == 8 && rpw == 1) return esize == 4 ? ((dif || scheme == SCH_CENTRED) ? 72 : 56) : 96;
   if (ty == 16 && rpw == 1 && esize == 4 && scheme != SCH_CENTRED) return 56;   // two CTAs of 17 warps
   const int warps = ty / rpw + 1;
@@ -84,7 +87,7 @@ constexpr int tma_max_regs(size_t esize, int scheme, int ty, int rpw, int dif) {
 // DIF = 0: frequency-independent boundaries; 1..4: digital impedance filters of that order
 // (one-row-per-warp 128x8 tile: three resident CTAs per SM in fp32, two in fp64)
 template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF>
-__global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(sizeof(T), SCHEME, TY, RPW, DIF))
+__global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(sizeof(T), SCHEME, TY, RPW, NST, DIF))
     fdtd_update_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                     const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                     T* __restrict__ Pn, T lam2, T a_air, int X, int Y, int z_begin, int z_end, int chunk, int hints,
@@ -170,6 +173,13 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
   const uint32_t a_cls = sm + G::PS_OFF + (uint32_t)r0 * TX + xl;
   const uint32_t a_row = sm + G::PT_OFF + (uint32_t)(r0 + 1) * ROW;                          // x = -HX of the first row
 
+  // filter boundaries (one row per warp): entries and prefetched states (update_math.cuh DifRow).  Started before the
+  // first wait on the pipeline so that the entry -> state round trips overlap the first planes' TMA loads.
+  static_assert(!DIF || RPW == 1, "filter boundaries use the one-row-per-warp tile shapes");
+  constexpr int DMO = DIF ? DIF : 1;
+  DifRow<T, DMO> drow;
+  if (DIF) drow.start(dif, z_lo, z_hi, y0 + r0, Y, lane);
+
   V4<T> down[RPW], cur[RPW], up[RPW];
 
   // prologue: plane z_lo-1 (centre only), then plane z_lo (kept resident for its xy-neighbours)
@@ -185,19 +195,6 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
   for (int k = 0; k < RPW; k++) lds4_a(a_ctr + (1 % NST) * G::STAGE_BYTES + k * ROW, cur[k]);
 
   constexpr uint32_t AIR4 = CLS_AIR * 0x01010101u;
-  // DIF (one row per warp): lane l holds the rowbase entry of plane (j & ~31) + l of the warp's row; st_nxt / st_cur
-  // are the filter states fetched for the next / this plane (dif_fetch)
-  static_assert(!DIF || RPW == 1, "filter boundaries use the one-row-per-warp tile shapes");
-  constexpr int DMO = DIF ? DIF : 1;
-  uint32_t rowbases = 0u;
-  T st_cur[DMO], st_nxt[DMO];
-#pragma unroll
-  for (int i = 0; i < DMO; i++) st_cur[i] = st_nxt[i] = (T)0;
-  if (DIF) {
-    rowbases = dif_load_rowbases<T>(dif, z_lo, z_hi, y0 + r0, Y, lane);
-    dif_fetch<T, DMO>(dif, __shfl_sync(0xffffffffu, rowbases, 0), lane, st_nxt);
-  }
-
   T* out = Pn + (int64_t)z_lo * XY + (int64_t)(y0 + r0) * X + gx;   // this lane's four voxels of the warp's first row
   uint32_t par = 0;                                                    // parity of the round that starts at plane jb
 
@@ -210,17 +207,6 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
       const uint32_t s2 = (uint32_t)((u + 2) % NST) * G::STAGE_BYTES;   // stage of plane z+1 (and P_old / classes of z)
       const uint32_t s1 = (uint32_t)((u + 1) % NST) * G::STAGE_BYTES;   // stage of plane z
       mbar_wait_a(bf + 8 * ((u + 2) % NST), par ^ ((u + 2) >= NST ? 1u : 0u));
-
-      uint32_t dif_entry = 0u;
-      if (DIF) {   // this plane's states were fetched an iteration ago; start the next plane's fetch now
-        dif_entry = __shfl_sync(0xffffffffu, rowbases, j & 31);
-#pragma unroll
-        for (int i = 0; i < DMO; i++) st_cur[i] = st_nxt[i];
-        if (j + 1 < n) {
-          if (((j + 1) & 31) == 0) rowbases = dif_load_rowbases<T>(dif, z_lo + j + 1, z_hi, y0 + r0, Y, lane);
-          dif_fetch<T, DMO>(dif, __shfl_sync(0xffffffffu, rowbases, (j + 1) & 31), lane, st_nxt);
-        }
-      }
 
       V4<T> old[RPW];
       uint32_t pw[RPW];
@@ -276,7 +262,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
             }
           }
         }
-        if (DIF && (dif_entry & DIF_HAS)) dif_apply_row<T, DMO>(res.v, old[k].v, pw[k], active, lane, dif_entry, st_cur, dif, s_dif);
+        if (DIF) drow.apply(j, res.v, old[k].v, pw[k], active, lane, dif, s_dif);
         if (active) stg4(out + (int64_t)k * X, res);
       }
       out += XY;
@@ -286,6 +272,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
         mbar_arrive_a(be + 8 * ((u + 1) % NST));
         if (j == 0) mbar_arrive_a(be);   // plane z_lo-1, read in the prologue
       }
+      if (DIF) drow.next(dif, j, n, z_lo, z_hi, y0 + r0, Y, lane);
 #pragma unroll
       for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
     }
@@ -347,6 +334,9 @@ const TileDef kTiles[] = {
     {8, 1, 6, "128x8 r1 s6"},
     {16, 2, 3, "128x16 r2 s3"},
     {32, 2, 3, "128x32 r2 s3"},
+    {7, 1, 5, "128x7 r1 s5"},
+    {7, 1, 6, "128x7 r1 s6"},
+    {8, 1, 5, "128x8 r1 s5"},
 };
 constexpr int kNumTiles = (int)(sizeof(kTiles) / sizeof(kTiles[0]));
 
@@ -380,12 +370,15 @@ int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupanc
 
 template <typename T, int SCHEME>
 int dispatch_tile(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
-  if (a.dif_order > 0) {   // filter boundaries: the 128x8 one-row-per-warp shape, one kernel per order
+  if (a.dif_order > 0) {
+    // filter boundaries: one kernel per order on the shape tma_pick_config selects for them -- fp32: 128x8 with six
+    // stages (72 registers, three CTAs per SM); fp64: 128x7 with five (eight warps per CTA leave 128 registers)
+    constexpr int DTY = sizeof(T) == 4 ? 8 : 7, DNST = sizeof(T) == 4 ? 6 : 5;
     switch (a.dif_order) {
-      case 1: return launch_tma_t<T, SCHEME, 8, 1, 4, 1>(a, m, chunk, occ);
-      case 2: return launch_tma_t<T, SCHEME, 8, 1, 4, 2>(a, m, chunk, occ);
-      case 3: return launch_tma_t<T, SCHEME, 8, 1, 4, 3>(a, m, chunk, occ);
-      case 4: return launch_tma_t<T, SCHEME, 8, 1, 4, 4>(a, m, chunk, occ);
+      case 1: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 1>(a, m, chunk, occ);
+      case 2: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 2>(a, m, chunk, occ);
+      case 3: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 3>(a, m, chunk, occ);
+      case 4: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 4>(a, m, chunk, occ);
     }
     set_error("filter order %d is not supported", a.dif_order);
     return PFDTD_ERR_INVALID;
@@ -397,6 +390,9 @@ int dispatch_tile(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, in
     case 3: return launch_tma_t<T, SCHEME, 8, 1, 6>(a, m, chunk, occ);
     case 4: return launch_tma_t<T, SCHEME, 16, 2, 3>(a, m, chunk, occ);
     case 5: return launch_tma_t<T, SCHEME, 32, 2, 3>(a, m, chunk, occ);
+    case 6: return launch_tma_t<T, SCHEME, 7, 1, 5>(a, m, chunk, occ);
+    case 7: return launch_tma_t<T, SCHEME, 7, 1, 6>(a, m, chunk, occ);
+    case 8: return launch_tma_t<T, SCHEME, 8, 1, 5>(a, m, chunk, occ);
   }
   set_error("unknown TMA tile variant %d", tile);
   return PFDTD_ERR_INVALID;
@@ -435,14 +431,20 @@ int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void
   return PFDTD_OK;
 }
 
-int tma_pick_config(int dtype, int scheme, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk,
+int tma_pick_config(int dtype, int scheme, int dif_order, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk,
                     TmaConfig* out) {
-  // default: 128x8, one row per warp, 4 stages -- 3 resident CTAs per SM in fp32 (<= 72 registers), 2 in fp64
-  int tile = (opt_tile > 0 && opt_tile <= kNumTiles) ? (int)opt_tile - 1 : 0;
+  // Defaults (B200, profiles/r01_sweep.md): the 128x7 one-row-per-warp shapes -- eight warps per CTA divide evenly
+  // over the four sub-partitions, which leaves 64 (fp32, four CTAs per SM) / 128 (fp64, two) registers per thread
+  // and room for a fifth or sixth stage.  The filter kernels have one shape per dtype (dispatch_tile).
+  int tile;
+  if (dif_order > 0) tile = dtype == PFDTD_F64 ? 6 : (scheme == SCH_INTERP ? 8 : 3);
+  else if (opt_tile > 0 && opt_tile <= kNumTiles) tile = (int)opt_tile - 1;
+  else tile = (dtype == PFDTD_F32 && scheme == SCH_FORWARD) ? 7 : 6;
   if (Y <= 8 && kTiles[tile].ty > 8) tile = 0;
   UpdateArgs probe{};
   probe.dtype = dtype;
   probe.scheme = scheme;
+  probe.dif_order = dif_order;
   TmaMaps dummy{};
   int occ = 0;
   if (scheme == SCH_INTERP) {

@@ -147,8 +147,8 @@ struct DifEntry {
 };
 template <typename T>
 struct DifArgs {
-  T* state;                      // [order][nb] filter states of this slab's boundary voxels
-  const uint32_t* rowbase;       // [nz][Y][segs]: index of the first boundary voxel of each 128-voxel row segment
+  T* state;                      // [nb][P] filter states of this slab's boundary voxels, P = order rounded up to 1, 2 or 4
+  const uint2* rowbase;          // [nz][Y][segs] row-segment entries (below)
   const DifEntry<T>* table;      // [n_dif] per lossy class
   uint32_t nb;
   int order;
@@ -157,90 +157,177 @@ struct DifArgs {
   int segs;                      // row segments per row = ceil(X / 128)
 };
 
-// rowbase entries of one (row, tile column) for 32 consecutive planes, one per lane: a single load per 32 planes
-// instead of a dependent global load per plane; the kernels pick the entry of a plane with a shuffle.
-// Entry = index of the segment's first boundary voxel | (segment has boundary voxels ? DIF_HAS : 0).
+// Row-segment entry (one per plane, row and 128-voxel tile column): x = index of the segment's first filter voxel
+// (its voxels are numbered consecutively in x order), y = flags:
+//   DIF_HAS     the segment has filter voxels at all
+//   DIF_SINGLE  exactly one -- a wall crossing the row, by far the most common case; bits 0..6 = its x offset
+//   DIF_RUN     two or more forming one contiguous run -- a row lying in a wall; bits 0..6 = x offset of the first,
+//               bits 8..15 = their number
+//   neither     anything else (the row crosses several walls inside one segment)
 constexpr uint32_t DIF_HAS = 0x80000000u;
-template <typename T>
-__device__ __forceinline__ uint32_t dif_load_rowbases(const DifArgs<T>& d, int z_first, int z_end, int gy, int Y, int lane) {
-  const int z = z_first + lane;
-  return (gy < Y && z < z_end) ? __ldg(d.rowbase + ((size_t)z * Y + gy) * d.segs + blockIdx.x) : 0u;
-}
+constexpr uint32_t DIF_SINGLE = 0x40000000u;
+constexpr uint32_t DIF_RUN = 0x20000000u;
+constexpr uint32_t DIF_ANY = 0x10000000u;      // in-register only: the 32-plane block this entry belongs to has filter voxels
 
-// The filter states are the only dependent global loads of the march.  They are fetched one plane ahead, coalesced:
-// lane l reads the states of the segment's l-th boundary voxel (rank l, x order) into registers; dif_apply_row
-// hands each voxel its states with a shuffle.  ORD = filter order the kernel is compiled for.  Values of ranks
-// beyond the segment's own voxels belong to other rows and are never used.
+__host__ __device__ constexpr int dif_pad(int order) { return order <= 1 ? 1 : (order == 2 ? 2 : 4); }
+
+// the states of one voxel are P consecutive elements, moved with one (fp64 order 3-4: two) vector access
+template <typename T, int N>
+struct alignas(sizeof(T) * N > 16 ? 16 : sizeof(T) * N) DifVec { T v[N]; };
 template <typename T, int ORD>
-__device__ __forceinline__ void dif_fetch(const DifArgs<T>& d, uint32_t entry, int lane, T (&st)[ORD]) {
+__device__ __forceinline__ void dif_ld(const T* p, T (&s)[ORD]) {
+  const DifVec<T, dif_pad(ORD)> t = *reinterpret_cast<const DifVec<T, dif_pad(ORD)>*>(p);
 #pragma unroll
-  for (int i = 0; i < ORD; i++) st[i] = (T)0;
-  if (entry & DIF_HAS) {
-    const uint32_t idx = (entry & ~DIF_HAS) + (uint32_t)lane;
-    if (idx < d.nb) {
-      const T* sp = d.state + idx;
+  for (int i = 0; i < ORD; i++) s[i] = t.v[i];
+}
+template <typename T, int ORD>
+__device__ __forceinline__ void dif_st(T* p, const T (&s)[ORD]) {
+  DifVec<T, dif_pad(ORD)> t;
 #pragma unroll
-      for (int i = 0; i < ORD; i++) st[i] = sp[(size_t)i * d.nb];
-    }
-  }
+  for (int i = 0; i < dif_pad(ORD); i++) t.v[i] = i < ORD ? s[i] : (T)0;
+  *reinterpret_cast<DifVec<T, dif_pad(ORD)>*>(p) = t;
 }
 
 template <typename T>
 __device__ __forceinline__ T sel4(const T (&v)[4], int q) { return q == 0 ? v[0] : (q == 1 ? v[1] : (q == 2 ? v[2] : v[3])); }
+template <typename T>
+__device__ __forceinline__ void put4(T (&v)[4], int q, T x) {
+  if (q == 0) v[0] = x;
+  else if (q == 1) v[1] = x;
+  else if (q == 2) v[2] = x;
+  else v[3] = x;
+}
 
-// Warp-convergent: every lane of the warp calls it for its four x-adjacent voxels of one row segment whose
-// rowbase entry (uniform across the warp) has DIF_HAS set.  pw = the four class bytes, st = dif_fetch of this
-// plane; ranks follow x order.  The lossy boundary classes are the highest class ids, so "is a filter voxel" is
-// an unsigned byte compare, done for the four bytes at once.  The warp then makes as many passes as the busiest
-// lane has filter voxels (one for a wall crossing the row, four for a row lying in a wall); a segment where a
-// single lane has them skips the cross-lane prefix.  Per voxel (transposed direct form II, see above):
-//     p_new = val0 - c3*s_1 ; u = p_new - p_old ; y = b0*u + s_1 ; s_i <- b_i*u - a_i*y + s_(i+1)
+template <typename T> struct Quad { T v[4]; };
+
 template <typename T, int ORD>
-__device__ __forceinline__ void dif_apply_row(T (&res)[4], const T (&old)[4], uint32_t pw, bool active, int lane, uint32_t entry,
-                                              const T (&st)[ORD], const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif) {
-  uint32_t ge = 0;   // bit 8q+7: voxel q of this lane is a lossy boundary voxel
-  if (active && pw != CLS_AIR * 0x01010101u) {
-    const uint32_t k = d.dif_lo * 0x01010101u;
-    const uint32_t t = (pw | 0x80808080u) - (k & 0x7f7f7f7fu);
-    ge = ((pw & ~k) | (~(pw ^ k) & t)) & 0x80808080u;
-  }
-  const uint32_t lanes = __ballot_sync(0xffffffffu, ge != 0u);
-  const uint32_t cnt = __popc(ge);
-  uint32_t rank = 0;
-  if (lanes & (lanes - 1u)) {   // several lanes: rank = boundary voxels of the lanes below (x order), cnt is 0..4
-    const uint32_t below = (1u << lane) - 1u;
-    rank = __popc(__ballot_sync(0xffffffffu, cnt & 1u) & below) + 2u * __popc(__ballot_sync(0xffffffffu, cnt & 2u) & below) +
-           4u * __popc(__ballot_sync(0xffffffffu, cnt & 4u) & below);
-  }
-  const uint32_t passes = __reduce_max_sync(0xffffffffu, cnt);
-  const uint32_t base = entry & ~DIF_HAS;
-  for (uint32_t it = 0; it < passes; it++, rank++) {   // uniform trip count
-    T s[ORD + 1];
+__device__ __forceinline__ void dif_filter(const DifEntry<T>& e, const T (&s)[ORD], T val0, T p_old, T& p_new, T (&ns)[ORD]) {
+  p_new = Ar<T>::fma(-e.c3, s[0], val0);
+  const T u = Ar<T>::add(p_new, -p_old);
+  const T y = Ar<T>::fma(e.b0, u, s[0]);
 #pragma unroll
-    for (int i = 0; i < ORD; i++) s[i] = __shfl_sync(0xffffffffu, st[i], (int)(rank & 31u));
-    s[ORD] = (T)0;
-    if (it < cnt) {
+  for (int i = 0; i < ORD; i++) ns[i] = Ar<T>::fma(e.b[i], u, Ar<T>::fma(-e.a[i], y, i + 1 < ORD ? s[i + 1 < ORD ? i + 1 : 0] : (T)0));
+}
+
+// the two less common kinds of row segment (see DifRow): contiguous runs and the general case
+template <typename T, int ORD>
+__device__ __noinline__ Quad<T> dif_apply_multi(Quad<T> res_q, const Quad<T> old_q, uint32_t pw, bool active, int lane, uint32_t fl,
+                                                uint32_t base, const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif) {
+  constexpr int P = dif_pad(ORD);
+  T (&res)[4] = res_q.v;
+  const T (&old)[4] = old_q.v;
+    if (fl & DIF_RUN) {
+      const uint32_t cnt = (fl >> 8) & 0xffu;
+      const int r0 = 4 * lane - (int)(fl & 127u);               // rank of this lane's voxel 0 (negative left of the run)
+      T* sp = d.state + ((int64_t)base + r0) * P;                // only dereferenced for ranks inside the run
+      T s[4][ORD];
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if ((uint32_t)(r0 + q) < cnt) dif_ld<T, ORD>(sp + q * P, s[q]);
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if ((uint32_t)(r0 + q) < cnt) {
+          const DifEntry<T>& e = s_dif[((pw >> (8 * q)) & 0xffu) - d.dif_lo];
+          T ns[ORD], p_new;
+          dif_filter<T, ORD>(e, s[q], res[q], old[q], p_new, ns);
+          dif_st<T, ORD>(sp + q * P, ns);
+          res[q] = p_new;
+        }
+      return res_q;
+    }
+    // General case.  The lossy boundary classes are the highest class ids, so "is a filter voxel" is an unsigned
+    // byte compare, done for the four bytes at once.  Ranks follow x order.
+    uint32_t ge = 0;   // bit 8q+7: voxel q of this lane is a filter voxel
+    if (active && pw != CLS_AIR * 0x01010101u) {
+      const uint32_t k = d.dif_lo * 0x01010101u;
+      const uint32_t t = (pw | 0x80808080u) - (k & 0x7f7f7f7fu);
+      ge = ((pw & ~k) | (~(pw ^ k) & t)) & 0x80808080u;
+    }
+    const uint32_t cnt = __popc(ge);
+    const uint32_t below = (1u << lane) - 1u;
+    uint32_t rank = __popc(__ballot_sync(0xffffffffu, cnt & 1u) & below) + 2u * __popc(__ballot_sync(0xffffffffu, cnt & 2u) & below) +
+                    4u * __popc(__ballot_sync(0xffffffffu, cnt & 4u) & below);
+    for (uint32_t it = 0; it < cnt; it++, rank++) {
       const int bit = __ffs((int)ge) - 1;   // 7, 15, 23 or 31
       ge &= ge - 1u;
       const int q = bit >> 3;
-      T* sp = d.state + (base + rank);
-      if (rank >= 32u) {   // beyond the prefetched window (rows lying in a wall plane)
-#pragma unroll
-        for (int i = 0; i < ORD; i++) s[i] = sp[(size_t)i * d.nb];
-      }
+      T* sp = d.state + ((size_t)base + rank) * P;
+      T s[ORD], ns[ORD], p_new;
+      dif_ld<T, ORD>(sp, s);
       const DifEntry<T>& e = s_dif[((pw >> (bit - 7)) & 0xffu) - d.dif_lo];
-      const T p_new = Ar<T>::fma(-e.c3, s[0], sel4<T>(res, q));
-      const T u = Ar<T>::add(p_new, -sel4<T>(old, q));
-      const T y = Ar<T>::fma(e.b0, u, s[0]);
-#pragma unroll
-      for (int i = 0; i < ORD; i++) sp[(size_t)i * d.nb] = Ar<T>::fma(e.b[i], u, Ar<T>::fma(-e.a[i], y, s[i + 1]));
-      if (q == 0) res[0] = p_new;
-      else if (q == 1) res[1] = p_new;
-      else if (q == 2) res[2] = p_new;
-      else res[3] = p_new;
+      dif_filter<T, ORD>(e, s, sel4<T>(res, q), sel4<T>(old, q), p_new, ns);
+      dif_st<T, ORD>(sp, ns);
+      put4<T>(res, q, p_new);
     }
-  }
+  return res_q;
 }
+
+// Filter-boundary bookkeeping of one consumer warp (one tile row, 128 voxels, marching in z).  ORD = the filter
+// order the kernel is compiled for.  The filter states are the only dependent global loads of the march, and an
+// L2 round trip is longer than a plane's worth of work:
+//   * entries: lane l keeps the entry of plane 32*b + l of the current block of 32 planes (one load per block);
+//     DIF_ANY says whether the block has a filter voxel in this row segment at all -- segments in open air skip
+//     everything with one test per plane.
+//   * single-voxel planes: lane l also loads the states of plane 32*b + l's voxel right away, up to a whole block
+//     ahead (filter voxels are numbered z-fastest within a row segment, so a wall crossing the rows makes this one
+//     coalesced access); the plane's turn hands them to the voxel's lane by shuffle.  Nothing else stays in
+//     registers between planes.
+//   * runs (rows lying in a wall): every lane loads the states of its own (up to four) voxels when the plane's turn
+//     comes -- one exposed round trip per plane, in the few warps that own such rows.
+//   * anything else: ranked by ballots, one pass per voxel of the busiest lane.
+// Per voxel (transposed direct form II, see above):
+//     p_new = val0 - c3*s_1 ; u = p_new - p_old ; y = b0*u + s_1 ; s_i <- b_i*u - a_i*y + s_(i+1)
+template <typename T, int ORD>
+struct DifRow {
+  static constexpr int P = dif_pad(ORD);
+  uint2 ent;            // lane l: entry of plane 32*b + l; DIF_ANY is set in every lane's flags when any plane of the block has voxels
+  T st_blk[ORD];        // lane l: states of the single filter voxel of plane 32*b + l
+
+  __device__ __forceinline__ void load_block(const DifArgs<T>& d, int z_first, int z_end, int gy, int Y, int lane) {
+    const int z = z_first + lane;
+    ent = (gy < Y && z < z_end) ? __ldg(d.rowbase + ((size_t)z * Y + gy) * d.segs + blockIdx.x) : make_uint2(0u, 0u);
+    if (ent.y & DIF_SINGLE) dif_ld<T, ORD>(d.state + (size_t)ent.x * P, st_blk);
+    if (__ballot_sync(0xffffffffu, (ent.y & DIF_HAS) != 0u)) ent.y |= DIF_ANY;
+  }
+  __device__ __forceinline__ void start(const DifArgs<T>& d, int z_lo, int z_hi, int gy, int Y, int lane) {
+#pragma unroll
+    for (int i = 0; i < ORD; i++) st_blk[i] = (T)0;
+    load_block(d, z_lo, z_hi, gy, Y, lane);
+  }
+  // end of plane j (of n): the next block of entries is due
+  __device__ __forceinline__ void next(const DifArgs<T>& d, int j, int n, int z_lo, int z_hi, int gy, int Y, int lane) {
+    if (((j + 1) & 31) == 0 && j + 1 < n) load_block(d, z_lo + j + 1, z_hi, gy, Y, lane);
+  }
+
+  // Warp-convergent, plane j of the chunk.  res = the frequency-independent results of this lane's four voxels
+  // (updated in place), pw = their class bytes.
+  __device__ __forceinline__ void apply(int j, T (&res)[4], const T (&old)[4], uint32_t pw, bool active, int lane, const DifArgs<T>& d,
+                                        const DifEntry<T>* __restrict__ s_dif) {
+    if (!(ent.y & DIF_ANY)) return;   // the same in every lane
+    const uint32_t fl = __shfl_sync(0xffffffffu, ent.y, j & 31);
+    if (!(fl & DIF_HAS)) return;
+    const uint32_t base = __shfl_sync(0xffffffffu, ent.x, j & 31);
+    if (fl & DIF_SINGLE) {
+      T s[ORD];
+#pragma unroll
+      for (int i = 0; i < ORD; i++) s[i] = __shfl_sync(0xffffffffu, st_blk[i], j & 31);
+      if ((uint32_t)lane == ((fl & 127u) >> 2)) {
+        const int q = (int)(fl & 3u);
+        const DifEntry<T>& e = s_dif[((pw >> (8 * q)) & 0xffu) - d.dif_lo];
+        T ns[ORD], p_new;
+        dif_filter<T, ORD>(e, s, sel4<T>(res, q), sel4<T>(old, q), p_new, ns);
+        dif_st<T, ORD>(d.state + (size_t)base * P, ns);
+        put4<T>(res, q, p_new);
+      }
+      return;
+    }
+    // rows lying in a wall and everything else: out of line, so that their register needs stay out of the march
+    Quad<T> r{{res[0], res[1], res[2], res[3]}}, o{{old[0], old[1], old[2], old[3]}};
+    r = dif_apply_multi<T, ORD>(r, o, pw, active, lane, fl, base, d, s_dif);
+#pragma unroll
+    for (int q = 0; q < 4; q++) res[q] = r.v[q];
+  }
+};
 
 template <typename T, int SCHEME>
 __device__ __forceinline__ ClassEntry<T> make_class_entry(uint32_t pos, uint32_t m, const UpdConst<T>& c) {
