@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (per-GPU voxel dims x, y, z ; materials ; description)
-    "c2": ((512, 512, 512), 6, "shoebox 512x512x512 per GPU, 6 materials (BASELINE config 2, frequency-independent admittance)"),
+    "c2": ((512, 512, 512), 6, "shoebox 512x512x512 per GPU, 6 wall materials (BASELINE config 2)"),
     "c4": ((1024, 1024, 960), 6, "shoebox 1024x1024x960 (1.007e9 voxels) per GPU (BASELINE config 4)"),
     "c1": ((64, 64, 64), 1, "shoebox 64x64x64 (BASELINE config 1)"),
     "c2half": ((512, 512, 256), 6, "shoebox 512x512x256 per GPU"),
@@ -53,9 +53,10 @@ def parse_args():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--update-type", type=int, default=0, choices=[0, 1, 2, 3, 4])
-    ap.add_argument("--dif-order", type=int, default=0, choices=[0, 1, 2, 3, 4],
-                    help="frequency-dependent boundaries: order of the per-material digital impedance filters (0 = the "
-                         "reference's frequency-independent admittance, the only boundary the reference arm can run)")
+    ap.add_argument("--dif-order", type=int, default=2, choices=[0, 1, 2, 3, 4],
+                    help="frequency-dependent boundaries: order of the per-material digital impedance filters (BASELINE config 2 "
+                         "asks for them; 0 = the reference's frequency-independent admittance, the only boundary the reference "
+                         "arm can run)")
     ap.add_argument("--no-variants", action="store_true",
                     help="N=1 only: skip the short device-resident runs of the other BASELINE config-2 variants (DIF order 2, "
                          "fp64, IISO) that are appended to the JSON line as `variants`")
@@ -267,6 +268,12 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     achieved = slab_updates * ALGO_BYTES[args.dtype] / (kern_ms_per_step * 1e-3) / 1e9 if kern_ms_per_step > 0 else 0.0
     traffic = ncu_traffic(args.workload, args.dtype, args.update_type, args.dif_order)
+    dif_addon = None
+    if args.dif_order:   # reported next to, not inside, the 13 B / 25 B per voxel update
+        _, _, n_bnd = s.counts()
+        pad = 1 if args.dif_order == 1 else (2 if args.dif_order == 2 else 4)
+        dif_addon = {"filter_voxels": int(n_bnd), "state_bytes_read_plus_written": int(2 * n_bnd * pad * prm.itemsize),
+                     "row_segment_entries_bytes": int(8 * nz * Y * ((X + 127) // 128))}
     ss.close()
 
     # ---- end-to-end through the C ABI with HOST buffers ------------------------------------------------
@@ -316,7 +323,8 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_voxel_update": ALGO_BYTES[args.dtype], "voxel_updates_per_step_per_gpu": slab_updates,
                          "kernel_ms_per_step": kern_ms_per_step, "update_launches_per_step": n_k / max(steps_timed_k, 1),
-                         "how": f"CUDA events around every update launch over {steps_timed_k} steps right after the timed region"},
+                         "how": f"CUDA events around every update launch over {steps_timed_k} steps right after the timed region",
+                         "addon_bytes_per_step_not_in_achieved": dif_addon},
             "cpu_baseline": cpu,
         }
         if world == 1 and not args.no_variants:
@@ -329,23 +337,26 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-VARIANTS = [("f32 SRL_FORWARD + DIF order 2", ["--dtype", "f32", "--dif-order", "2"]),
-            ("f64 SRL_FORWARD", ["--dtype", "f64"]),
-            ("f64 SRL_FORWARD + DIF order 2", ["--dtype", "f64", "--dif-order", "2"]),
-            ("f32 IISO (27-point)", ["--dtype", "f32", "--update-type", "3"]),
-            ("f32 IISO + DIF order 2", ["--dtype", "f32", "--update-type", "3", "--dif-order", "2"])]
+VARIANTS = [("f32 SRL_FORWARD, frequency-independent admittance (the reference's boundary; parity pinned bit-exact)", "f32", 0, 0),
+            ("f32 SRL_FORWARD + DIF order 2", "f32", 0, 2),
+            ("f64 SRL_FORWARD + DIF order 2", "f64", 0, 2),
+            ("f64 SRL_FORWARD, frequency-independent", "f64", 0, 0),
+            ("f32 SRL (centred boundary) + DIF order 2", "f32", 2, 2),
+            ("f32 IISO (27-point), frequency-independent", "f32", 3, 0),
+            ("f32 IISO + DIF order 2", "f32", 3, 2),
+            ("f64 IISO + DIF order 2", "f64", 3, 2)]
 
 
 def run_variants(args):
-    """The other variants BASELINE config 2 names (frequency-dependent DIF boundaries, fp64) and the interpolated scheme,
-    each as a short device-resident run of this same script in a child process (same workload, 200 steps)."""
+    """The other variants BASELINE config 2 names (fp64, the reference's frequency-independent boundary) and the
+    interpolated scheme, each as a short device-resident run of this same script in a child process (same workload,
+    200 steps)."""
     out = []
-    for name, flags in VARIANTS:
-        if flags == (["--dtype", args.dtype] + (["--dif-order", str(args.dif_order)] if args.dif_order else [])
-                     + (["--update-type", str(args.update_type)] if args.update_type else [])):
+    for name, dtype, ut, order in VARIANTS:
+        if (dtype, ut, order) == (args.dtype, args.update_type, args.dif_order):
             continue
         cmd = [sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--steps", "200", "--warmup", "10", "--no-e2e",
-               "--no-cpu-baseline", "--no-variants"] + flags
+               "--no-cpu-baseline", "--no-variants", "--dtype", dtype, "--update-type", str(ut), "--dif-order", str(order)]
         try:
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
             d = json.loads(r.stdout.strip().splitlines()[-1])
@@ -436,6 +447,8 @@ def run_reference(args):
         line = dict(base, value=value, ms_per_step=wall / K * 1e3,
                     config={"workload": f"{wdesc}; global {gdims[0]}x{gdims[1]}x{gdims[2]} -> padded {X}x{Y}x{Z}",
                             "update_type": UPDATE_NAMES[args.update_type], "materials": n_mat, "slabs": n,
+                            "boundaries": "frequency-independent admittance per material: the reference contains no digital impedance "
+                                          "filter (SURVEY section 0), so its arm runs the boundary it has on the same room",
                             "what": "reference src/kernels/{kernels3d,cudaMesh,cudaUtils}.cu + host classes compiled unmodified for sm_100 "
                                     "(oracle/Makefile), driven like its own tests: setupMesh -> makePartition -> launchFDTD3d"},
                     cpu_baseline={"value": value, "unit": "Mvox/s", "cores": 1, "kind": "reference",

@@ -218,6 +218,61 @@ int launch_count_dif_segments(const uint8_t* d_cls, int X, int Y, int nz, uint32
   return PFDTD_OK;
 }
 
+// ---- row-segment entries of the filter boundaries (update_math.cuh): filter voxels are numbered z-fastest within a
+// (row, tile column) column, so the index of a segment's first voxel is an exclusive prefix over (column, z) ----
+// one thread per column: number of filter voxels of the column over all planes
+__global__ void dif_column_totals_kernel(const uint32_t* __restrict__ counts, int n_cols, int nz, uint32_t* __restrict__ totals) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cols) return;
+  uint32_t t = 0;
+  for (int z = 0; z < nz; z++) t += counts[(size_t)z * n_cols + c] & 0xffu;
+  totals[c] = t;
+}
+// single block: exclusive scan of the column totals in place, grand total to *nb
+__global__ void dif_scan_columns_kernel(uint32_t* __restrict__ totals, int n_cols, unsigned long long* __restrict__ nb) {
+  __shared__ unsigned long long s_part[1024];
+  const int t = threadIdx.x, per = (n_cols + blockDim.x - 1) / blockDim.x;
+  const int lo = min(t * per, n_cols), hi = min(lo + per, n_cols);
+  unsigned long long sum = 0;
+  for (int i = lo; i < hi; i++) sum += totals[i];
+  s_part[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < (int)blockDim.x; i++) { const unsigned long long v = s_part[i]; s_part[i] = run; run += v; }
+    *nb = run;
+  }
+  __syncthreads();
+  unsigned long long run = s_part[t];
+  for (int i = lo; i < hi; i++) { const uint32_t v = totals[i]; totals[i] = (uint32_t)run; run += v; }
+}
+// one thread per column walks the planes: entry = {index of the first filter voxel, DIF_HAS | DIF_SINGLE | DIF_RUN | count << 8 | x offset}
+__global__ void dif_build_entries_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ col_base, int n_cols, int nz,
+                                         uint2* __restrict__ entries) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cols) return;
+  uint32_t run = col_base[c];
+  for (int z = 0; z < nz; z++) {
+    const size_t i = (size_t)z * n_cols + c;
+    const uint32_t w = counts[i], n = w & 0xffu, xoff = (w >> 8) & 0x7fu;
+    uint32_t fl = 0u;
+    if (n == 1) fl = 0xC0000000u | xoff;
+    else if (n > 1) fl = ((w >> 15) & 1u) ? (0xA0000000u | (n << 8) | xoff) : 0x80000000u;
+    entries[i] = make_uint2(run, fl);
+    run += n;
+  }
+}
+
+int launch_build_dif_entries(const uint32_t* d_counts, int n_cols, int nz, uint32_t* d_col_scratch, unsigned long long* d_nb,
+                             uint32_t* d_entries, cudaStream_t stream) {
+  const int th = 128, bl = (n_cols + th - 1) / th;
+  dif_column_totals_kernel<<<bl, th, 0, stream>>>(d_counts, n_cols, nz, d_col_scratch);
+  dif_scan_columns_kernel<<<1, 1024, 0, stream>>>(d_col_scratch, n_cols, d_nb);
+  dif_build_entries_kernel<<<bl, th, 0, stream>>>(d_counts, d_col_scratch, n_cols, nz, reinterpret_cast<uint2*>(d_entries));
+  PF_CUDA(cudaGetLastError());
+  return PFDTD_OK;
+}
+
 static int class_blocks(uint64_t n) {
   int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
   return blocks < 1 ? 1 : blocks;

@@ -811,34 +811,25 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       PF_CHECK(s->n_lossy <= 64, PFDTD_ERR_INVALID, "filter (DIF) boundaries support <= 64 lossy node classes, mesh has %u", s->n_lossy);
       const int segs = ((int)s->X + 127) / 128;
       const size_t n_seg = (size_t)p.size * s->Y * segs;
+      // per-segment counts -> entries, on the device (three small kernels); only the total comes back
+      const int n_cols = (int)s->Y * segs;
+      uint32_t* d_counts = nullptr;
+      uint32_t* d_cols = nullptr;
+      unsigned long long* d_nb = nullptr;
       PF_CUDA(cudaMalloc(&p.dif_rowbase, n_seg * 2 * sizeof(uint32_t)));
-      PF_TRY(launch_count_dif_segments(p.cls, (int)s->X, (int)s->Y, (int)p.size, s->dif_lo, p.dif_rowbase, 0));
-      std::vector<uint32_t> cnt(n_seg), ent(2 * n_seg);
-      PF_CUDA(cudaMemcpy(cnt.data(), p.dif_rowbase, n_seg * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-      if (const char* dbg = getenv("PFDTD_DEBUG_DIF_KEEP")) {   // timing experiments only: 0 none, 1 singles, 2 multi
-        const int keep = atoi(dbg);
-        for (size_t i = 0; i < n_seg; i++) {
-          const uint32_t c = cnt[i] & 0xffu;
-          if (keep == 0 || (keep == 1 && c != 1) || (keep == 2 && c == 1)) cnt[i] = 0;
-        }
-      }
-      uint64_t run = 0;
-      // entry = {index of the segment's first filter voxel, flags}: DIF_HAS | DIF_SINGLE | DIF_RUN, x offset of the first
-      // voxel in bits 0..6, their number in bits 8..15 (update_math.cuh)
-      // filter voxels are numbered z-fastest within a row segment: a wall crossing the rows gives every (row, segment)
-      // column consecutive indices along the march
-      for (size_t ys = 0; ys < (size_t)s->Y * segs; ys++)
-        for (size_t z = 0; z < (size_t)p.size; z++) {
-          const size_t i = z * (size_t)s->Y * segs + ys;
-          const uint32_t c = cnt[i] & 0xffu, xoff = (cnt[i] >> 8) & 0x7fu;
-          ent[2 * i] = (uint32_t)run;
-          const bool is_run = (cnt[i] >> 15) & 1u;
-          ent[2 * i + 1] = c == 0 ? 0u : (c == 1 ? (0xC0000000u | xoff) : (is_run ? (0xA0000000u | (c << 8) | xoff) : 0x80000000u));
-          run += c;
-        }
+      PF_CUDA(cudaMalloc(&d_counts, n_seg * sizeof(uint32_t)));
+      PF_CUDA(cudaMalloc(&d_cols, (size_t)n_cols * sizeof(uint32_t)));
+      PF_CUDA(cudaMalloc(&d_nb, sizeof(unsigned long long)));
+      PF_TRY(launch_count_dif_segments(p.cls, (int)s->X, (int)s->Y, (int)p.size, s->dif_lo, d_counts, 0));
+      PF_TRY(launch_build_dif_entries(d_counts, n_cols, (int)p.size, d_cols, d_nb, p.dif_rowbase, 0));
+      unsigned long long run = 0;
+      PF_CUDA(cudaMemcpy(&run, d_nb, sizeof(run), cudaMemcpyDeviceToHost));
+      PF_CUDA(cudaFree(d_counts));
+      PF_CUDA(cudaFree(d_cols));
+      PF_CUDA(cudaFree(d_nb));
       PF_CHECK(run < 0x7fffffffull, PFDTD_ERR_INVALID, "too many boundary voxels in one slab");
       p.dif_nb = (uint32_t)run;
-      PF_CUDA(cudaMemcpy(p.dif_rowbase, ent.data(), ent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      s->launch_count += 3;
       const size_t sb = (size_t)std::max<uint32_t>(p.dif_nb, 1) * dif_state_pad((int)s->opt_dif_order) * es;
       PF_CUDA(cudaMalloc(&p.dif_state, sb));
       PF_CUDA(cudaMemset(p.dif_state, 0, sb));

@@ -106,6 +106,10 @@ int build_dif_table(const UpdateArgs& a, const uint32_t* d_keys /* keys of the l
 // first of them inside the segment (bits 8..14), planes [1, nz-1) only
 inline int dif_state_pad(int order) { return order <= 1 ? 1 : (order == 2 ? 2 : 4); }
 int launch_count_dif_segments(const uint8_t* d_cls, int X, int Y, int nz, uint32_t dif_lo, uint32_t* d_counts, cudaStream_t stream);
+// counts [nz][n_cols] (launch_count_dif_segments) -> entries [nz][n_cols][2], total number of filter voxels to *d_nb;
+// d_col_scratch: n_cols words
+int launch_build_dif_entries(const uint32_t* d_counts, int n_cols, int nz, uint32_t* d_col_scratch, unsigned long long* d_nb,
+                             uint32_t* d_entries, cudaStream_t stream);
 int tma_pick_config(int dtype, int scheme, int dif_order, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk,
                     TmaConfig* out);
 int launch_update_tma(const UpdateArgs& a, const TmaMaps& maps, const TmaConfig& cfg);

@@ -35,7 +35,7 @@ def test_interp_partition_invariance_and_tiles(capi, gpu, name):
     for n in (2, 5):
         r, _, _ = fc.run_ours(capi, case, n_parts=n, matidx=0)
         assert np.array_equal(r, base), n
-    for tile in (1, 3):
+    for tile in (1, 3, 7, 9):
         for chunk in (0, 1, 7):
             r, _, info = fc.run_ours(capi, case, n_parts=1, matidx=0, kernel=capi.KERNEL_TMA,
                                      opts=[(capi.OPT_TMA_TILE, tile), (capi.OPT_TMA_CHUNK, chunk)])

@@ -101,7 +101,7 @@ def test_tma_and_plain_kernels_agree_on_fields(capi, gpu):
     assert np.array_equal(fields[0][0], fields[1][0]) and np.array_equal(fields[0][1], fields[1][1])
 
 
-@pytest.mark.parametrize("tile", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("tile", [1, 2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("double", [False, True])
 def test_every_tma_tile_variant(capi, gpu, tile, double):
     case = CASES["shoebox_48x40x49_ctr_f64_6mat_5parts" if double else "shoebox_48x40x49_fwd_f32_6mat_2parts"]

@@ -1,0 +1,54 @@
+"""CPU: the Python module `libPyFDTD` builds, imports without a GPU, exposes every method of the reference's
+boost::python module (reference src/AppPy.cpp:106-133) and fails loudly without a device."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# the .def(...) names of BOOST_PYTHON_MODULE(libPyFDTD), reference src/AppPy.cpp:106-133
+REFERENCE_APP_METHODS = [
+    "initializeDevices", "initializeGeometryFromFile", "initializeGeometryPy", "setLayerIndices", "addSource", "addSourceDataFloat",
+    "addSourceDataDouble", "addReceiver", "addSurfaceMaterials", "setSpatialFs", "setNumSteps", "setUpdateType", "setUniform",
+    "runVisualization", "runSimulation", "runCapture", "setUniformMaterial", "getResponse", "getResponseDouble", "forcePartitionTo",
+    "addSliceToCapture", "setDouble", "setCapturedB", "close", "getMvox", "getNumElems"]
+
+
+@pytest.fixture(scope="module")
+def pf():
+    from parallelfdtd_b200 import build
+    path = build.build_py_module()
+    assert os.path.exists(path)
+    sys.path.insert(0, os.path.dirname(path))
+    import libPyFDTD
+    return libPyFDTD
+
+
+def test_module_exposes_the_reference_api(pf):
+    app = pf.App()
+    missing = [m for m in REFERENCE_APP_METHODS if not hasattr(app, m)]
+    assert not missing, missing
+
+
+def test_host_side_setters_work_without_a_device(pf, capi):
+    app = pf.App()
+    app.initializeGeometryPy([0, 1, 2, 0, 2, 3], [0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 1, 0])
+    app.setLayerIndices([0, 1], "floor")
+    app.setUpdateType(0)
+    app.setNumSteps(10)
+    app.setSpatialFs(7000)
+    app.addSurfaceMaterials([0.5] * 40, 2, 20)
+    app.addSource(0.5, 0.5, 0.5, 0, 0, 0)
+    app.addReceiver(0.6, 0.6, 0.6)
+    app.addSourceDataFloat([0.0, 1.0, 0.0], 3, 1)
+    app.addSourceDataDouble([0.0, 1.0, 0.0], 3, 1)
+    with pytest.raises(IndexError):
+        app.addSourceDataFloat([0.0], 3, 1)
+    if capi.device_count() == 0:
+        with pytest.raises(RuntimeError):                # no CPU fallback behind the module either
+            app.initializeDevices()
+        with pytest.raises(RuntimeError):
+            app.runSimulation()
+    with pytest.raises(RuntimeError):
+        app.initializeGeometryFromFile("x.vtk")
