@@ -166,7 +166,7 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
       mbar_arrive(&bar_empty[s2]);
       if (j == 0) { mbar_arrive(&bar_empty[0]); mbar_arrive(&bar_empty[1 % NST]); }
     }
-    if (DIF) drow.next(dif, j, n, z_lo, z_hi, gy, Y, lane);
+    if (DIF) drow.next(dif, j, n, z_lo, z_hi, gy, Y, lane, Pn + (int64_t)z_lo * XY + (int64_t)gy * X + x0, XY, s_dif);
     pm = pc;
     pc = pp;
   }

@@ -5,6 +5,7 @@
 //   calcBoundaries                      src/kernels/cudaMesh.cu:500-514
 #include "pfdtd_internal.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace pfdtd {
 
@@ -179,7 +180,7 @@ __global__ void assign_classes_kernel(const uint8_t* __restrict__ pos, const uin
 
 // one warp per 128-voxel row segment (4 class bytes per lane)
 __global__ void count_dif_segments_kernel(const uint8_t* __restrict__ cls, int X, int Y, int nz, uint32_t dif_lo,
-                                          uint32_t* __restrict__ counts) {
+                                          uint32_t* __restrict__ counts, int keep) {
   const int segs = (X + 127) / 128;
   const int64_t n_seg = (int64_t)nz * Y * segs;
   const int lane = threadIdx.x & 31;
@@ -205,6 +206,8 @@ __global__ void count_dif_segments_kernel(const uint8_t* __restrict__ cls, int X
       c |= (uint32_t)xf << 8;
       if ((uint32_t)(xl - xf + 1) == (c & 0xffu)) c |= 1u << 15;
     }
+    // timing probes only (PFDTD_DEBUG_DIF_KEEP): 0 drops every filter voxel, 1 keeps single-voxel segments, 2 the others
+    if (keep >= 0 && (keep == 0 || (keep == 1 && (c & 0xffu) != 1u) || (keep == 2 && (c & 0xffu) == 1u))) c = 0;
     if (lane == 0) counts[w] = c;
   }
 }
@@ -213,7 +216,8 @@ int launch_count_dif_segments(const uint8_t* d_cls, int X, int Y, int nz, uint32
   const int64_t n_seg = (int64_t)nz * Y * ((X + 127) / 128);
   int blocks = (int)std::min<int64_t>((n_seg * 32 + 255) / 256, 148 * 16);
   if (blocks < 1) blocks = 1;
-  count_dif_segments_kernel<<<blocks, 256, 0, stream>>>(d_cls, X, Y, nz, dif_lo, d_counts);
+  const char* dbg = getenv("PFDTD_DEBUG_DIF_KEEP");
+  count_dif_segments_kernel<<<blocks, 256, 0, stream>>>(d_cls, X, Y, nz, dif_lo, d_counts, dbg ? atoi(dbg) : -1);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }

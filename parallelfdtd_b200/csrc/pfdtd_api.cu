@@ -85,7 +85,7 @@ struct Partition {
   void* class_table = nullptr;          // ClassEntry<T>[n_classes]
   uint32_t* d_class_keys = nullptr;
   // digital impedance filters
-  void* dif_state = nullptr;            // [order][dif_nb]
+  void* dif_state = nullptr;            // [dif_nb][P]
   uint32_t* dif_rowbase = nullptr;      // [size][Y][ceil(X/128)]
   void* dif_table = nullptr;            // DifEntry<T>[n_lossy]
   uint32_t dif_nb = 0;

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
         mbar_arrive_a(be + 8 * ((u + 1) % NST));
         if (j == 0) mbar_arrive_a(be);   // plane z_lo-1, read in the prologue
       }
-      if (DIF) drow.next(dif, j, n, z_lo, z_hi, y0 + r0, Y, lane);
+      if (DIF) drow.next(dif, j, n, z_lo, z_hi, y0 + r0, Y, lane, Pn + (int64_t)z_lo * XY + (int64_t)(y0 + r0) * X + x0, XY, s_dif);
 #pragma unroll
       for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
     }
@@ -466,7 +466,7 @@ int tma_pick_config(int dtype, int scheme, int dif_order, int X, int Y, int npla
     // though every chunk re-reads two planes (those re-reads hit L2, and the fine grain evens out the
     // SMs' finishing times); when the whole launch is only a wave or two, wave quantisation dominates.
     // (fp32 forward: 8-14 planes; fp64, the centred scheme and the 27-point kernels: 20-28)
-    const bool light = dtype == PFDTD_F32 && scheme == SCH_FORWARD;
+    const bool light = dtype == PFDTD_F32 && scheme == SCH_FORWARD && dif_order == 0;
     const int lo = light ? 12 : 20, hi = light ? 16 : 28;
     const bool deep = tiles * (int64_t)((nplanes + lo - 1) / lo) >= 4 * resident;
     double best = -1;
