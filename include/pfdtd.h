@@ -127,6 +127,21 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
                             uint32_t block_x, uint32_t block_y, uint32_t block_z,
                             uint32_t element_type, int dtype,
                             const void* params, const void* material_coefs, uint32_t n_unique_materials);
+/* ---- voxelisation (the step before setupMesh in App::initializeMesh, src/App.cpp:181-190) ----
+ * voxelizeGeometry (src/kernels/voxelizationUtils.cu:47-146; the reference hands this to the un-vendored third-party
+ * Voxelizer): solid voxelisation of a closed triangle mesh on the device.  vertices [n_vertices][3] metres,
+ * indices [n_triangles][3], triangle_material [n_triangles] unique-material index per triangle (NULL = all 0),
+ * dx = voxel edge.  Output: voxelizer-style volumes [vz][vy][vx], `bid` 0 (solid) / 27 (air) / 1..26 (boundary by
+ * air-neighbour set) and the material index of the nearest triangle for boundary voxels; voxel (i,j,k) samples the
+ * point ((i-1)dx, (j-1)dx, (k-1)dx), dims = ceil(max/dx) + 3.  The _device form returns cudaMalloc'ed volumes on
+ * `device` (-1 = current) that pfdtd_setup_mesh_device adopts; the host form copies them out (call
+ * pfdtd_voxelize_dims first to size the buffers). */
+int pfdtd_voxelize_dims(const float* vertices, uint32_t n_vertices, float dx, uint32_t* vx, uint32_t* vy, uint32_t* vz);
+int pfdtd_voxelize_device(int device, const float* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_triangles,
+                          const uint8_t* triangle_material, float dx, uint8_t** d_bid, uint8_t** d_mat,
+                          uint32_t* vx, uint32_t* vy, uint32_t* vz);
+int pfdtd_voxelize(const float* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_triangles,
+                   const uint8_t* triangle_material, float dx, uint8_t* h_bid, uint8_t* h_mat);
 /* CudaMesh::makePartition (src/kernels/cudaMesh.h:648-751). device_list may be NULL (= 0..n-1). */
 int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t* device_list);
 

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpfdtd_b200.so")
-SOURCES = ["pfdtd_api.cu", "update_kernels.cu", "interp_kernels.cu", "mesh_kernels.cu", "srcrec_kernels.cu", "capture_kernels.cu"]
+SOURCES = ["pfdtd_api.cu", "update_kernels.cu", "interp_kernels.cu", "mesh_kernels.cu", "srcrec_kernels.cu", "capture_kernels.cu", "voxelize_kernels.cu"]
 HEADERS = ["pfdtd_internal.h", "update_math.cuh", "tma_common.cuh", "update_host.cuh", os.path.join("..", "..", "include", "pfdtd.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -75,6 +75,20 @@ def device_count() -> int:
     return n.value if rc == 0 else 0
 
 
+def voxelize(vertices, indices, dx, triangle_material=None):
+    """voxelizeGeometry (reference src/kernels/voxelizationUtils.cu:47-146) on the device: closed triangle mesh ->
+    voxelizer-style ``bid`` and material volumes ``[vz][vy][vx]``."""
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
+    m = None if triangle_material is None else np.ascontiguousarray(triangle_material, dtype=np.uint8)
+    vx, vy, vz = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    _check(lib().pfdtd_voxelize_dims(_ptr(v), C.c_uint32(len(v)), C.c_float(dx), C.byref(vx), C.byref(vy), C.byref(vz)))
+    bid = np.empty((vz.value, vy.value, vx.value), dtype=np.uint8)
+    mat = np.empty_like(bid)
+    _check(lib().pfdtd_voxelize(_ptr(v), C.c_uint32(len(v)), _ptr(t), C.c_uint32(len(t)), _ptr(m), C.c_float(dx), _ptr(bid), _ptr(mat)))
+    return bid, mat
+
+
 def partition_indexing(dim_z: int, n: int):
     """CudaMesh::getPartitionIndexing (reference src/kernels/cudaMesh.h:280-307)."""
     first = (C.c_uint32 * n)()

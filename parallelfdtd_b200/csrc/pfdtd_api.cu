@@ -717,6 +717,41 @@ int pfdtd_setup_mesh(pfdtd_solver* s, const uint8_t* h_bid, const uint8_t* h_mat
                                  material_coefs, n_unique_materials);
 }
 
+int pfdtd_voxelize_dims(const float* vertices, uint32_t n_vertices, float dx, uint32_t* vx, uint32_t* vy, uint32_t* vz) {
+  PF_CHECK(vertices && n_vertices > 0 && vx && vy && vz, PFDTD_ERR_INVALID, "null argument");
+  PF_CHECK(dx > 0.f, PFDTD_ERR_INVALID, "voxel size must be positive");
+  float mx[3] = {vertices[0], vertices[1], vertices[2]};
+  for (uint32_t v = 1; v < n_vertices; v++)
+    for (int a = 0; a < 3; a++) mx[a] = std::max(mx[a], vertices[3 * v + a]);
+  *vx = (uint32_t)std::ceil(mx[0] / dx) + 3; *vy = (uint32_t)std::ceil(mx[1] / dx) + 3; *vz = (uint32_t)std::ceil(mx[2] / dx) + 3;
+  return PFDTD_OK;
+}
+
+int pfdtd_voxelize_device(int device, const float* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_triangles,
+                          const uint8_t* triangle_material, float dx, uint8_t** d_bid, uint8_t** d_mat, uint32_t* vx, uint32_t* vy,
+                          uint32_t* vz) {
+  PF_CHECK(d_bid && d_mat && vx && vy && vz, PFDTD_ERR_INVALID, "null argument");
+  int n = 0;
+  PF_TRY(pfdtd_device_count(&n));
+  PF_CHECK(n > 0, PFDTD_ERR_NO_DEVICE, "no CUDA device: the voxeliser has no CPU path");
+  return voxelize_to_device(device, vertices, n_vertices, indices, n_triangles, triangle_material, dx, d_bid, d_mat, vx, vy, vz, nullptr);
+}
+
+int pfdtd_voxelize(const float* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_triangles,
+                   const uint8_t* triangle_material, float dx, uint8_t* h_bid, uint8_t* h_mat) {
+  PF_CHECK(h_bid && h_mat, PFDTD_ERR_INVALID, "null argument");
+  uint8_t *d_bid = nullptr, *d_mat = nullptr;
+  uint32_t vx = 0, vy = 0, vz = 0;
+  PF_TRY(pfdtd_voxelize_device(-1, vertices, n_vertices, indices, n_triangles, triangle_material, dx, &d_bid, &d_mat, &vx, &vy, &vz));
+  const size_t nvox = (size_t)vx * vy * vz;
+  cudaError_t e = cudaMemcpy(h_bid, d_bid, nvox, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(h_mat, d_mat, nvox, cudaMemcpyDeviceToHost);
+  cudaFree(d_bid);
+  cudaFree(d_mat);
+  PF_CUDA(e);
+  return PFDTD_OK;
+}
+
 int pfdtd_partition_indexing(uint32_t dim_z, uint32_t n_partitions, uint32_t* first_slice, uint32_t* n_slices) {
   PF_CHECK(n_partitions >= 1 && first_slice && n_slices, PFDTD_ERR_INVALID, "bad argument");
   std::vector<int64_t> f, sz;

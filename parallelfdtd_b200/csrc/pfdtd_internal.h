@@ -123,6 +123,12 @@ const char* tma_tile_name(int dtype, int tile);
 int launch_capture_slice(int dtype, const void* P, const uint8_t* pos, void* out_p, uint8_t* out_pos, uint32_t X, uint32_t Y,
                          uint32_t z_lo, uint32_t nz, uint32_t slice, int orientation, cudaStream_t stream);
 
+// ---- voxeliser (voxelize_kernels.cu): closed triangle mesh -> device `bid` / material volumes (cudaMalloc'ed, with the
+// slice + row + 1 bytes of slack the reference gives them), dims = ceil(max / dx) + 3 per axis
+int voxelize_to_device(int device, const float* h_vertices, uint32_t n_vertices, const uint32_t* h_indices, uint32_t n_triangles,
+                       const uint8_t* h_tri_material, float dx, uint8_t** d_bid_out, uint8_t** d_mat_out, uint32_t* vx_out, uint32_t* vy_out,
+                       uint32_t* vz_out, uint64_t* launches);
+
 // ---- source / receiver kernel (srcrec_kernels.cu) -------------------------------------------------
 struct SrcRecArgs {
   int dtype;

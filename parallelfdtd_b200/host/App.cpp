@@ -8,7 +8,6 @@
 #include <cstdio>
 
 #include "kernels/kernels3d.h"
-#include "voxelize.h"
 
 namespace FDTD {
 
@@ -66,22 +65,34 @@ void App::setVoxelVolumes(const unsigned char* bid, const unsigned char* mat, un
 
 void App::initializeMesh(unsigned int number_of_partitions) {
   if (number_of_devices_ == 0) queryDevices();
-  if (vol_bid_.empty()) {
-    if (m_geometry.getNumberOfTriangles() == 0) { c_log_msg(LOG_ERROR, "App::initializeMesh - no geometry"); throw(-1); }
-    pfdtd_host::VoxelVolumes v = pfdtd_host::voxelize(m_geometry, m_parameters.getDx(), m_materials.getMaterialIdxPtr());
-    vol_bid_.swap(v.bid); vol_mat_.swap(v.mat);
-    vol_dim_[0] = v.vx; vol_dim_[1] = v.vy; vol_dim_[2] = v.vz;
-  }
   if (m_materials.getNumberOfUniqueMaterials() == 0) m_materials.setGlobalMaterial(uniform_surfaces_(), 0.f);
-  const uint3 dim = make_uint3(vol_dim_[0], vol_dim_[1], vol_dim_[2]);
   const uint3 block = make_uint3(32, 4, 1);                     // reference App.cpp:193
   const unsigned int type = (unsigned int)m_parameters.getUpdateType();
-  if (m_mesh.isDouble())
-    m_mesh.setupMeshHost(&vol_bid_[0], &vol_mat_[0], m_materials.getNumberOfUniqueMaterials(), m_materials.getMaterialCoefficientPtrDouble(),
-                         m_parameters.getParameterPtrDouble(), dim, block, type);
-  else
-    m_mesh.setupMeshHost(&vol_bid_[0], &vol_mat_[0], m_materials.getNumberOfUniqueMaterials(), m_materials.getMaterialCoefficientPtr(),
-                         m_parameters.getParameterPtr(), dim, block, type);
+  if (vol_bid_.empty()) {
+    // triangle mesh -> node volumes on the device (reference App.cpp:181-190 voxelizeGeometry), adopted by setupMesh
+    if (m_geometry.getNumberOfTriangles() == 0) { c_log_msg(LOG_ERROR, "App::initializeMesh - no geometry"); throw(-1); }
+    unsigned char *d_bid = 0, *d_mat = 0;
+    unsigned int vx = 0, vy = 0, vz = 0;
+    pfdtd_safe(pfdtd_voxelize_device(-1, m_geometry.getVerticePtr(), m_geometry.getNumberOfVertices(), m_geometry.getIndexPtr(),
+                                     m_geometry.getNumberOfTriangles(), m_materials.getMaterialIdxPtr(), m_parameters.getDx(), &d_bid, &d_mat,
+                                     &vx, &vy, &vz), "App::initializeMesh - voxelizeGeometry");
+    vol_dim_[0] = vx; vol_dim_[1] = vy; vol_dim_[2] = vz;
+    const uint3 dim = make_uint3(vx, vy, vz);
+    if (m_mesh.isDouble())
+      m_mesh.setupMeshDouble(d_bid, d_mat, m_materials.getNumberOfUniqueMaterials(), m_materials.getMaterialCoefficientPtrDouble(),
+                             m_parameters.getParameterPtrDouble(), dim, block, type);
+    else
+      m_mesh.setupMesh(d_bid, d_mat, m_materials.getNumberOfUniqueMaterials(), m_materials.getMaterialCoefficientPtr(),
+                       m_parameters.getParameterPtr(), dim, block, type);
+  } else {
+    const uint3 dim = make_uint3(vol_dim_[0], vol_dim_[1], vol_dim_[2]);
+    if (m_mesh.isDouble())
+      m_mesh.setupMeshHost(&vol_bid_[0], &vol_mat_[0], m_materials.getNumberOfUniqueMaterials(), m_materials.getMaterialCoefficientPtrDouble(),
+                           m_parameters.getParameterPtrDouble(), dim, block, type);
+    else
+      m_mesh.setupMeshHost(&vol_bid_[0], &vol_mat_[0], m_materials.getNumberOfUniqueMaterials(), m_materials.getMaterialCoefficientPtr(),
+                           m_parameters.getParameterPtr(), dim, block, type);
+  }
   num_elements_ = m_mesh.getNumberOfElements();
   // Partition count.  The reference splits in two above 90e6 (45e6 double) voxels because of Kepler-era memory
   // (App.cpp:217-233); here one partition is used whenever the mesh fits the device, otherwise as many slabs

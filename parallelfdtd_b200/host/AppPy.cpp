@@ -124,6 +124,7 @@ PYBIND11_MODULE(libPyFDTD, m) {
       .def("getNumberOfMeshCaptures", &FDTD::App::getNumberOfMeshCaptures)
       .def("getMeshCapture", &getMeshCapture)
       .def("getTimePerStep", &FDTD::App::getTimePerStep)
+      .def("getDx", [](FDTD::App& a) { return a.m_parameters.getDx(); })
       .def("getDims", [](FDTD::App& a) { return py::make_tuple(a.m_mesh.getDimX(), a.m_mesh.getDimY(), a.m_mesh.getDimZ()); })
       .def("getVolume", &FDTD::App::getVolume)
       .def("getSabine", &FDTD::App::getSabine)

@@ -12,7 +12,7 @@
 
 #include "App.h"
 #include "kernels/kernels3d.h"
-#include "voxelize.h"
+#include "voxelize_ref.h"
 
 static int g_fail = 0, g_checks = 0;
 #define CHECK(c) do { g_checks++; if (!(c)) { g_fail++; std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c); } } while (0)
@@ -184,6 +184,35 @@ static void shoebox_bid(unsigned vx, unsigned vy, unsigned vz, std::vector<unsig
   }
 }
 
+// device voxeliser (pfdtd_voxelize) against the host restatement (voxelize_ref.h), bit for bit: box, off-grid box with
+// per-face materials, and a room with a pillar (rows that cross the surface four times)
+static void test_voxelizer_gpu() {
+  struct Case { float lx, ly, lz, dx; bool pillar; };
+  const Case cases[] = {{1.f, 1.f, 1.f, 0.1f, false}, {1.37f, 0.93f, 1.11f, 0.043f, false}, {2.f, 1.5f, 1.f, 0.05f, true}};
+  for (const Case& c : cases) {
+    std::vector<unsigned> idx; std::vector<float> v; box_mesh(c.lx, c.ly, c.lz, idx, v);
+    if (c.pillar) {   // a box-shaped pillar from floor to ceiling inside the room: a second closed surface (parity fill makes it solid)
+      std::vector<unsigned> pi; std::vector<float> pv; box_mesh(0.3f, 0.3f, c.lz, pi, pv);
+      const unsigned base = (unsigned)(v.size() / 3);
+      for (size_t i = 0; i < pv.size(); i += 3) { v.push_back(pv[i] + 0.8f); v.push_back(pv[i + 1] + 0.6f); v.push_back(pv[i + 2]); }
+      for (size_t i = 0; i < pi.size(); i++) idx.push_back(pi[i] + base);
+    }
+    GeometryHandler g; g.initialize(idx, v);
+    std::vector<unsigned char> tm(g.getNumberOfTriangles());
+    for (size_t t = 0; t < tm.size(); t++) tm[t] = (unsigned char)(t / 2 % 7);
+    pfdtd_host::VoxelVolumes ref = pfdtd_host::voxelize(g, c.dx, &tm[0]);
+    unsigned vx = 0, vy = 0, vz = 0;
+    CHECK_EQ(pfdtd_voxelize_dims(&v[0], (unsigned)(v.size() / 3), c.dx, &vx, &vy, &vz), 0);
+    CHECK_EQ(vx, ref.vx); CHECK_EQ(vy, ref.vy); CHECK_EQ(vz, ref.vz);
+    std::vector<unsigned char> bid((size_t)vx * vy * vz, 255), mat(bid.size(), 255);
+    CHECK_EQ(pfdtd_voxelize(&v[0], (unsigned)(v.size() / 3), &idx[0], g.getNumberOfTriangles(), &tm[0], c.dx, &bid[0], &mat[0]), 0);
+    CHECK(bid == ref.bid);
+    CHECK(mat == ref.mat);
+    size_t air = 0; for (size_t e = 0; e < bid.size(); e++) air += bid[e] == 27;
+    CHECK(air > 0);
+  }
+}
+
 static bool never(void) { return false; }
 static void quiet(int, int, float) {}
 
@@ -276,7 +305,7 @@ static void test_cuda_mesh_gpu() {
 int main(int argc, char** argv) {
   const std::string what = argc > 1 ? argv[1] : "cpu";
   if (what == "cpu") { test_simulation_parameters(); test_srcrec(); test_material_handler(); test_partition_indexing(); test_geometry_and_voxelizer(); }
-  else if (what == "gpu") test_cuda_mesh_gpu();
+  else if (what == "gpu") { test_cuda_mesh_gpu(); test_voxelizer_gpu(); }
   std::printf("%s: %d checks, %d failures\n", what.c_str(), g_checks, g_fail);
   return g_fail ? 1 : 0;
 }

@@ -1,4 +1,6 @@
-// voxelize.h -- host-side solid voxelisation of a closed triangle mesh into the voxelizer-style node
+// voxelize_ref.h -- TEST INFRASTRUCTURE: host restatement of the device voxeliser
+// (parallelfdtd_b200/csrc/voxelize_kernels.cu, pfdtd_voxelize*), operation by operation, used by tests/cpp/host_tests.cpp
+// to check it bit for bit.  Solid voxelisation of a closed triangle mesh into the voxelizer-style node
 // volumes the solver consumes: `bid` (0 solid, 27 air, 1..26 boundary codes, SURVEY Appendix B /
 // reference src/kernels/cudaMesh.cu:372-476) and a material index per boundary voxel.
 //
