@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_plane(const T* __restrict__ pt, int r, int 
 
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: TY consumer warps (one tile row each) + 1 producer warp
 template <typename T, bool HAS_D3, int TY, int NST, int DIF>
-__global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (TY == 7 ? 64 : (TY == 8 ? 72 : 56)) : (TY == 7 ? 128 : 96))
+__global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (TY == 7 ? (NST >= 6 ? 80 : 64) : (TY == 8 ? 72 : 56)) : (TY == 7 ? 128 : 96))
     fdtd_update_interp_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                            const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                            T* __restrict__ Pn, T d1, T d2, T d3, T d4, int X, int Y, int z_begin, int z_end, int chunk,
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
       mbar_arrive(&bar_empty[s2]);
       if (j == 0) { mbar_arrive(&bar_empty[0]); mbar_arrive(&bar_empty[1 % NST]); }
     }
-    if (DIF) drow.next(dif, j, n, z_lo, z_hi, gy, Y, lane, Pn + (int64_t)z_lo * XY + (int64_t)gy * X + x0, XY, s_dif);
+    if (DIF) drow.next(dif, j, n, z_lo, z_hi, gy, Y, lane);
     pm = pc;
     pc = pp;
   }
@@ -229,8 +229,8 @@ int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occup
 template <typename T, bool HAS_D3>
 int dispatch_interp(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
   // tile variants shared with the 7-point kernel: only the one-row-per-warp shapes apply here
-  if (a.dif_order > 0) {   // filter boundaries: one kernel per order; fp32 128x8, fp64 128x7, five stages
-    constexpr int DTY = sizeof(T) == 4 ? 8 : 7, DNST = 5;
+  if (a.dif_order > 0) {   // filter boundaries: one kernel per order on the 128x7 shape; fp32 six stages, fp64 five
+    constexpr int DTY = 7, DNST = sizeof(T) == 4 ? 6 : 5;   // fp32: 80 registers, three CTAs per SM
     switch (a.dif_order) {
       case 1: return launch_interp_t<T, HAS_D3, DTY, DNST, 1>(a, m, chunk, occ);
       case 2: return launch_interp_t<T, HAS_D3, DTY, DNST, 2>(a, m, chunk, occ);

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
         mbar_arrive_a(be + 8 * ((u + 1) % NST));
         if (j == 0) mbar_arrive_a(be);   // plane z_lo-1, read in the prologue
       }
-      if (DIF) drow.next(dif, j, n, z_lo, z_hi, y0 + r0, Y, lane, Pn + (int64_t)z_lo * XY + (int64_t)(y0 + r0) * X + x0, XY, s_dif);
+      if (DIF) drow.next(dif, j, n, z_lo, z_hi, y0 + r0, Y, lane);
 #pragma unroll
       for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
     }
@@ -437,7 +437,7 @@ int tma_pick_config(int dtype, int scheme, int dif_order, int X, int Y, int npla
   // over the four sub-partitions, which leaves 64 (fp32, four CTAs per SM) / 128 (fp64, two) registers per thread
   // and room for a fifth or sixth stage.  The filter kernels have one shape per dtype (dispatch_tile).
   int tile;
-  if (dif_order > 0) tile = dtype == PFDTD_F64 ? 6 : (scheme == SCH_INTERP ? 8 : 3);
+  if (dif_order > 0) tile = dtype == PFDTD_F64 ? 6 : (scheme == SCH_INTERP ? 7 : 3);
   else if (opt_tile > 0 && opt_tile <= kNumTiles) tile = (int)opt_tile - 1;
   else tile = (dtype == PFDTD_F32 && scheme == SCH_FORWARD) ? 7 : 6;
   if (Y <= 8 && kTiles[tile].ty > 8) tile = 0;

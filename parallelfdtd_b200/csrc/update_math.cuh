@@ -270,8 +270,7 @@ __device__ __noinline__ Quad<T> dif_apply_multi(Quad<T> res_q, const Quad<T> old
 //     everything with one test per plane.
 //   * single-voxel planes: lane l also loads the states of plane 32*b + l's voxel right away, up to a whole block
 //     ahead (filter voxels are numbered z-fastest within a row segment, so a wall crossing the rows makes this one
-//     coalesced access).  At the plane's turn the voxel's inputs are shuffled to lane l (three shuffles, no
-//     divergence); the filter itself runs once per block for all 32 planes at once (flush), all lanes busy.
+//     coalesced access); the plane's turn hands them to the voxel's lane by shuffle.
 //   * runs (rows lying in a wall): every lane loads the states of its own (up to four) voxels when the plane's turn
 //     comes -- one exposed round trip per plane, in the few warps that own such rows.
 //   * anything else: ranked by ballots, one pass per voxel of the busiest lane.
@@ -282,8 +281,6 @@ struct DifRow {
   static constexpr int P = dif_pad(ORD);
   uint2 ent;            // lane l: entry of plane 32*b + l; DIF_ANY is set in every lane's flags when any plane of the block has voxels
   T st_blk[ORD];        // lane l: states of the single filter voxel of plane 32*b + l
-  T cv, co;             // lane l: that voxel's frequency-independent result and past value, collected at the plane's turn
-  uint32_t cc;          //         and its class byte
 
   __device__ __forceinline__ void load_block(const DifArgs<T>& d, int z_first, int z_end, int gy, int Y, int lane) {
     const int z = z_first + lane;
@@ -300,36 +297,11 @@ struct DifRow {
   __device__ __forceinline__ void start(const DifArgs<T>& d, int z_lo, int z_hi, int gy, int Y, int lane) {
 #pragma unroll
     for (int i = 0; i < ORD; i++) st_blk[i] = (T)0;
-    cv = co = (T)0;
-    cc = 0u;
     load_block(d, z_lo, z_hi, gy, Y, lane);
   }
-  // The single voxels of a block of planes are filtered together, one plane per lane: states (st_blk), inputs (cv, co,
-  // cc) and entry (ent) of plane 32*b + l all sit in lane l.  The new states go back with one coalesced store; the
-  // voxel's pressure, written as the frequency-independent value by the row's 128-bit store at its plane's turn, is
-  // overwritten with the filtered one (the __syncwarp of every plane orders the two stores).
-  __device__ __forceinline__ void flush(const DifArgs<T>& d, int block, int n, T* __restrict__ row0, int64_t XY, int lane,
-                                        const DifEntry<T>* __restrict__ s_dif) {
-    if (!(ent.y & DIF_ANY)) return;
-    const int jl = 32 * block + lane;
-    if ((ent.y & DIF_SINGLE) && jl < n) {
-      const DifEntry<T>& e = s_dif[cc - d.dif_lo];
-      T ns[ORD], p_new;
-      dif_filter<T, ORD>(e, st_blk, cv, co, p_new, ns);
-      dif_st<T, ORD>(d.state + (size_t)ent.x * P, ns);
-      row0[(int64_t)jl * XY + (ent.y & 127u)] = p_new;
-    }
-  }
-  // end of plane j (of n): at the end of a block of 32 planes (or of the chunk) the block's single voxels are
-  // filtered and the next block of entries is fetched.  row0 = the row's first voxel of this tile column in the
-  // chunk's first plane.
-  __device__ __forceinline__ void next(const DifArgs<T>& d, int j, int n, int z_lo, int z_hi, int gy, int Y, int lane, T* __restrict__ row0,
-                                       int64_t XY, const DifEntry<T>* __restrict__ s_dif) {
-    const bool last = j + 1 >= n;
-    if (((j + 1) & 31) == 0 || last) {
-      flush(d, j >> 5, n, row0, XY, lane, s_dif);
-      if (!last) load_block(d, z_lo + j + 1, z_hi, gy, Y, lane);
-    }
+  // end of plane j (of n): the next block of entries is due
+  __device__ __forceinline__ void next(const DifArgs<T>& d, int j, int n, int z_lo, int z_hi, int gy, int Y, int lane) {
+    if (((j + 1) & 31) == 0 && j + 1 < n) load_block(d, z_lo + j + 1, z_hi, gy, Y, lane);
   }
 
   // Warp-convergent, plane j of the chunk.  res = the frequency-independent results of this lane's four voxels
@@ -339,13 +311,19 @@ struct DifRow {
     if (!(ent.y & DIF_ANY)) return;   // the same in every lane
     const uint32_t fl = __shfl_sync(0xffffffffu, ent.y, j & 31);
     if (!(fl & DIF_HAS)) return;
-    if (fl & DIF_SINGLE) {   // hand the voxel's inputs to the lane that keeps this plane's entry and states (see flush)
-      const int q = (int)(fl & 3u);
-      const int src = (int)((fl & 127u) >> 2);
-      const T v = __shfl_sync(0xffffffffu, sel4<T>(res, q), src);
-      const T o = __shfl_sync(0xffffffffu, sel4<T>(old, q), src);
-      const uint32_t c = __shfl_sync(0xffffffffu, pw >> (8 * q), src) & 0xffu;
-      if (lane == (j & 31)) { cv = v; co = o; cc = c; }
+    if (fl & DIF_SINGLE) {   // the states were fetched with the block's entries; hand them to the voxel's lane
+      T s[ORD];
+#pragma unroll
+      for (int i = 0; i < ORD; i++) s[i] = __shfl_sync(0xffffffffu, st_blk[i], j & 31);
+      const uint32_t base = __shfl_sync(0xffffffffu, ent.x, j & 31);
+      if ((uint32_t)lane == ((fl & 127u) >> 2)) {
+        const int q = (int)(fl & 3u);
+        const DifEntry<T>& e = s_dif[((pw >> (8 * q)) & 0xffu) - d.dif_lo];
+        T ns[ORD], p_new;
+        dif_filter<T, ORD>(e, s, sel4<T>(res, q), sel4<T>(old, q), p_new, ns);
+        dif_st<T, ORD>(d.state + (size_t)base * P, ns);
+        put4<T>(res, q, p_new);
+      }
       return;
     }
     // rows lying in a wall and everything else: out of line, so that their register needs stay out of the march
