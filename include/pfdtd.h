@@ -81,7 +81,10 @@ enum {
    * material m, [b0 .. bN, a1 .. aN] (a0 = 1), the octave index is ignored, and every boundary node carries N
    * filter states updated in the same kernel pass.  N = 0 (default): the reference's scalar admittance
    * materials[m*20 + octave].  Order-0 filters reproduce that path bit for bit.  Set before pfdtd_make_partition. */
-  PFDTD_OPT_DIF_ORDER = 13
+  PFDTD_OPT_DIF_ORDER = 13,
+  /* slabs in one process: the edge launches store their plane straight into the neighbour slab's halo plane
+   * (peer-mapped stores; default 1).  0 = copy the planes with cudaMemcpyPeerAsync after the edge launches. */
+  PFDTD_OPT_PEER_STORES = 14
 };
 
 typedef int (*pfdtd_interrupt_cb)(void);                      /* kernels3d.h: bool (*)(void) */

@@ -151,6 +151,9 @@ struct pfdtd_solver {
   float last_total_ms = 0, last_kernel_ms = 0, last_halo_ms = 0;
   uint32_t last_kernel_launches = 0;
   uint64_t launch_count = 0;
+  std::vector<char> halo_sent_up, halo_sent_down;   // per step: interfaces served by the edge launches' peer stores
+  std::vector<char> peer_ok;                        // [np*np]: partition a's device can address partition b's memory
+  int64_t opt_peer_stores = 1;
   // graph
   cudaGraphExec_t graph_exec = nullptr;
   uint32_t graph_steps = 0;
@@ -270,6 +273,7 @@ static UpdateArgs make_update_args(pfdtd_solver* s, Partition& p, int z_begin, i
   a.class_table = p.class_table;
   a.n_classes = (int)s->class_keys.size();
   a.tma_hints = (int)s->opt_tma_hints;
+  a.peer_plane = nullptr;
   a.dif_order = p.dif_rowbase ? (int)s->opt_dif_order : 0;
   a.dif_state = p.dif_state;
   a.dif_rowbase = p.dif_rowbase;
@@ -310,9 +314,10 @@ static int ensure_class_tables(pfdtd_solver* s) {
 }
 
 static int launch_update(pfdtd_solver* s, Partition& p, int z_begin, int z_end, const TmaConfig& cfg, cudaStream_t st,
-                         bool timed) {
+                         bool timed, void* peer_plane = nullptr) {
   if (z_end <= z_begin) return PFDTD_OK;
   UpdateArgs a = make_update_args(s, p, z_begin, z_end, st);
+  a.peer_plane = peer_plane;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed) {
     PF_CUDA(cudaEventCreate(&e0));
@@ -399,6 +404,11 @@ static int enqueue_halo_external(pfdtd_solver* s, int b) {
   return PFDTD_OK;
 }
 
+static bool can_store_to(const pfdtd_solver* s, size_t a, size_t b) {
+  const size_t np = s->parts.size();
+  return s->opt_peer_stores && s->peer_ok.size() == np * np && s->peer_ok[a * np + b];
+}
+
 // One time step for all partitions: source(n) -> update -> flip -> halo, receiver(n) is recorded by the
 // next step's srcrec launch (or the final flush).  Edge planes are computed first on the edge stream,
 // their halo transfer overlaps the interior update on the main stream.
@@ -414,6 +424,9 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
     s->cur = 1 - c;
     return PFDTD_OK;
   }
+  const size_t plane_bytes = (size_t)s->X * s->Y * esize(s);
+  s->halo_sent_up.assign(np, 0);      // interface k|k+1: partition k's top plane already stored into k+1's plane 0
+  s->halo_sent_down.assign(np, 0);    //                  partition k+1's plane 1 already stored into k's last plane
   // phase 1: sources/receivers + edge planes on the edge stream
   for (size_t k = 0; k < np; k++) {
     Partition& p = s->parts[k];
@@ -434,8 +447,21 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
     int ib = zb, ie = ze;
     const bool split = s->opt_overlap && (ze - zb) >= 4;
     if (split) {
-      if (lo_nb) { PF_TRY(launch_update(s, p, zb, zb + 1, p.cfg_edge, p.s_edge, timed)); ib = zb + 1; }
-      if (hi_nb) { PF_TRY(launch_update(s, p, ze - 1, ze, p.cfg_edge, p.s_edge, timed)); ie = ze - 1; }
+      // local neighbours whose memory this device can address get their halo plane from the edge launch itself
+      // (peer-mapped stores); otherwise the plane is copied / sent below
+      void* peer_lo = nullptr;
+      void* peer_hi = nullptr;
+      if (p.use_tma && k > 0 && can_store_to(s, k, k - 1)) {
+        Partition& nb = s->parts[k - 1];
+        peer_lo = (char*)nb.P[1 - c] + (size_t)(nb.size - 1) * plane_bytes;
+        s->halo_sent_down[k - 1] = 1;
+      }
+      if (p.use_tma && k + 1 < np && can_store_to(s, k, k + 1)) {
+        peer_hi = s->parts[k + 1].P[1 - c];
+        s->halo_sent_up[k] = 1;
+      }
+      if (lo_nb) { PF_TRY(launch_update(s, p, zb, zb + 1, p.cfg_edge, p.s_edge, timed, peer_lo)); ib = zb + 1; }
+      if (hi_nb) { PF_TRY(launch_update(s, p, ze - 1, ze, p.cfg_edge, p.s_edge, timed, peer_hi)); ie = ze - 1; }
       // interior on the main stream, concurrently with the halo traffic below
       PF_CUDA(cudaStreamWaitEvent(p.s_main, p.ev_src, 0));
       PF_TRY(launch_update(s, p, ib, ie, p.cfg_int, p.s_main, timed));
@@ -448,8 +474,8 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
   // phase 2: halo traffic of the new field (index 1-c) on the edge streams
   if (time_halo && s->ev_h0) { PF_CUDA(cudaSetDevice(s->parts[0].device)); PF_CUDA(cudaEventRecord(s->ev_h0, s->parts[0].s_edge)); }
   for (size_t k = 0; k + 1 < np; k++) {
-    PF_TRY(enqueue_halo_local_up(s, k, 1 - c));
-    PF_TRY(enqueue_halo_local_down(s, k, 1 - c));
+    if (!s->halo_sent_up[k]) PF_TRY(enqueue_halo_local_up(s, k, 1 - c));
+    if (!s->halo_sent_down[k]) PF_TRY(enqueue_halo_local_down(s, k, 1 - c));
   }
   PF_TRY(enqueue_halo_external(s, 1 - c));
   if (time_halo && s->ev_h1) { PF_CUDA(cudaSetDevice(s->parts[0].device)); PF_CUDA(cudaEventRecord(s->ev_h1, s->parts[0].s_edge)); }
@@ -553,6 +579,7 @@ static int64_t* option_slot(pfdtd_solver* s, int option) {
     case PFDTD_OPT_TIME_KERNELS: return &s->opt_time_kernels;
     case PFDTD_OPT_TMA_HINTS: return &s->opt_tma_hints;
     case PFDTD_OPT_DIF_ORDER: return &s->opt_dif_order;
+    case PFDTD_OPT_PEER_STORES: return &s->opt_peer_stores;
   }
   return nullptr;
 }
@@ -779,16 +806,32 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
     p.first = first[k];
     p.size = size[k];
   }
-  // peer access between devices that share an interface (NVLink P2P; the reference never enables it)
+  // peer access between devices that share an interface (NVLink P2P; the reference never enables it).  peer_ok says
+  // whether a kernel running for partition a may store into partition b's memory (same device, or peer access on).
+  s->peer_ok.assign((size_t)n_partitions * n_partitions, 0);
+  for (uint32_t k = 0; k < n_partitions; k++) s->peer_ok[(size_t)k * n_partitions + k] = 1;
   for (uint32_t k = 0; k + 1 < n_partitions; k++) {
-    int a = s->parts[k].device, b = s->parts[k + 1].device;
-    if (a == b) continue;
-    int can = 0;
-    cudaDeviceCanAccessPeer(&can, a, b);
-    if (can) {
-      cudaSetDevice(a); cudaError_t e = cudaDeviceEnablePeerAccess(b, 0); if (e != cudaSuccess) cudaGetLastError();
-      cudaSetDevice(b); e = cudaDeviceEnablePeerAccess(a, 0); if (e != cudaSuccess) cudaGetLastError();
+    const int a = s->parts[k].device, b = s->parts[k + 1].device;
+    bool ab = a == b, ba = a == b;
+    if (a != b) {
+      int can_ab = 0, can_ba = 0;
+      cudaDeviceCanAccessPeer(&can_ab, a, b);
+      cudaDeviceCanAccessPeer(&can_ba, b, a);
+      if (can_ab) {
+        cudaSetDevice(a);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+        ab = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+        if (e != cudaSuccess) cudaGetLastError();
+      }
+      if (can_ba) {
+        cudaSetDevice(b);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(a, 0);
+        ba = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+        if (e != cudaSuccess) cudaGetLastError();
+      }
     }
+    s->peer_ok[(size_t)k * n_partitions + (k + 1)] = ab;
+    s->peer_ok[(size_t)(k + 1) * n_partitions + k] = ba;
   }
   for (uint32_t k = 0; k < n_partitions; k++) {
     Partition& p = s->parts[k];

@@ -87,8 +87,9 @@ struct UpdateArgs {
   int n_dif;
   int X, Y;
   int z_begin, z_end;      // local planes [z_begin, z_end) are updated
-  void* peer_lo;           // optional: base of the neighbour slab plane that receives plane z_begin (or null)
-  void* peer_hi;           // optional: ... receives plane z_end-1
+  // edge launches of a slab (exactly one plane): the freshly computed plane is also stored into this plane of the
+  // neighbour slab -- its halo plane, on another GPU over NVLink when peer access exists -- by the same kernel
+  void* peer_plane;
   cudaStream_t stream;
 };
 

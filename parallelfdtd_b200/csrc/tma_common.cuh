@@ -115,6 +115,15 @@ __device__ __forceinline__ void lds4(const double* p, V4<double>& o) {
   double2 b = *reinterpret_cast<const double2*>(p + 2);
   o.v[0] = a.x; o.v[1] = a.y; o.v[2] = b.x; o.v[3] = b.y;
 }
+__device__ __forceinline__ void ldg4(const float* p, V4<float>& o) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  o.v[0] = t.x; o.v[1] = t.y; o.v[2] = t.z; o.v[3] = t.w;
+}
+__device__ __forceinline__ void ldg4(const double* p, V4<double>& o) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = b.x; o.v[3] = b.y;
+}
 __device__ __forceinline__ void stg4(float* p, const V4<float>& o) {
   *reinterpret_cast<float4*>(p) = make_float4(o.v[0], o.v[1], o.v[2], o.v[3]);
 }

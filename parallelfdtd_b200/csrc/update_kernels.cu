@@ -91,7 +91,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
     fdtd_update_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                     const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                     T* __restrict__ Pn, T lam2, T a_air, int X, int Y, int z_begin, int z_end, int chunk, int hints,
-                    const DifArgs<T> dif) {
+                    const DifArgs<T> dif, T* __restrict__ peer) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY / RPW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -277,6 +277,20 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
       for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
     }
   }
+  // Edge launch of a slab (one plane): the plane is the neighbour slab's halo for the next step.  Every lane sends the
+  // four voxels it has just written (read back from L2) straight into the neighbour's halo plane -- a peer-mapped
+  // store over NVLink when the neighbour lives on another GPU -- so compute and halo transfer are one launch and the
+  // tiles that finish first travel while the others are still being computed.
+  if (peer != nullptr && n == 1) {
+#pragma unroll
+    for (int k = 0; k < RPW; k++)
+      if (x_ok && (y0 + r0 + k) < Y) {
+        const int64_t row = (int64_t)(y0 + r0 + k) * X + gx;
+        V4<T> v;
+        ldg4(Pn + (int64_t)z_lo * XY + row, v);
+        stg4(peer + row, v);
+      }
+  }
 }
 
 // builds the per-class table with the device arithmetic of update_math.cuh (one thread per class)
@@ -363,7 +377,8 @@ int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupanc
   dim3 grid((a.X + TX - 1) / TX, (a.Y + TY - 1) / TY, (nplanes + chunk - 1) / chunk);
   const UpdConst<T> c = make_const<T>(a);
   kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.cls, (const ClassEntry<T>*)a.class_table, a.n_classes, (T*)a.Pn,
-                                          c.lam2, c.a_air, a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints, make_dif<T>(a));
+                                          c.lam2, c.a_air, a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints, make_dif<T>(a),
+                                          (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }

@@ -183,3 +183,16 @@ def test_run_in_blocks_and_interrupt(capi, gpu):
     r, _ = s.run(50, interrupt=lambda: 1)
     assert not r.any()
     s.close()
+
+
+@pytest.mark.parametrize("name", ["shoebox_48x40x49_ctr_f64_6mat_5parts", "hall_96x128x64_fwd_f32_5mat_oct1"])
+def test_halo_by_peer_stores_equals_halo_by_copies(capi, gpu, name):
+    """Slabs in one process: the edge launches store their plane into the neighbour's halo plane themselves
+    (PFDTD_OPT_PEER_STORES, default) or the planes are copied afterwards -- same responses, and equal to one slab."""
+    case = CASES[name]
+    base, _, _ = fc.run_ours(capi, case, n_parts=1)
+    for n in (2, 3, 5):
+        for peer in (1, 0):
+            for graph in (1, 0):
+                r, _, _ = fc.run_ours(capi, case, n_parts=n, opts=[(capi.OPT_PEER_STORES, peer), (capi.OPT_USE_GRAPH, graph)])
+                assert np.array_equal(r, base), (n, peer, graph)
