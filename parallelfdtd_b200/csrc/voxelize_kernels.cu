@@ -166,13 +166,23 @@ int voxelize_to_device(int device, const float* h_vertices, uint32_t n_vertices,
   const uint32_t vx = (uint32_t)std::ceil(mx[0] / dx) + 3, vy = (uint32_t)std::ceil(mx[1] / dx) + 3, vz = (uint32_t)std::ceil(mx[2] / dx) + 3;
   const size_t n = (size_t)vx * vy * vz;
   if (device >= 0) PF_CUDA(cudaSetDevice(device));
-  float* d_verts = nullptr;
-  uint32_t* d_idx = nullptr;
-  VoxTri* d_tris = nullptr;
-  float* d_cen = nullptr;
-  uint8_t* d_trimat = nullptr;
-  uint8_t *d_in[2] = {nullptr, nullptr}, *d_bid = nullptr, *d_mat = nullptr;
-  int* d_flags = nullptr;
+  struct Scratch {   // freed on every exit path; the two output volumes are released to the caller on success
+    float* verts = nullptr; uint32_t* idx = nullptr; VoxTri* tris = nullptr; float* cen = nullptr; uint8_t* trimat = nullptr;
+    uint8_t* in[2] = {nullptr, nullptr}; uint8_t* bid = nullptr; uint8_t* mat = nullptr; int* flags = nullptr;
+    ~Scratch() {
+      cudaFree(verts); cudaFree(idx); cudaFree(tris); cudaFree(cen); cudaFree(trimat); cudaFree(in[0]); cudaFree(in[1]);
+      cudaFree(bid); cudaFree(mat); cudaFree(flags);
+    }
+  } sc;
+  float*& d_verts = sc.verts;
+  uint32_t*& d_idx = sc.idx;
+  VoxTri*& d_tris = sc.tris;
+  float*& d_cen = sc.cen;
+  uint8_t*& d_trimat = sc.trimat;
+  uint8_t* (&d_in)[2] = sc.in;
+  uint8_t*& d_bid = sc.bid;
+  uint8_t*& d_mat = sc.mat;
+  int*& d_flags = sc.flags;
   PF_CUDA(cudaMalloc(&d_verts, (size_t)n_vertices * 3 * sizeof(float)));
   PF_CUDA(cudaMalloc(&d_idx, (size_t)n_triangles * 3 * sizeof(uint32_t)));
   PF_CUDA(cudaMalloc(&d_tris, (size_t)n_triangles * sizeof(VoxTri)));
@@ -218,9 +228,8 @@ int voxelize_to_device(int device, const float* h_vertices, uint32_t n_vertices,
   nl++;
   PF_CUDA(cudaGetLastError());
   PF_CUDA(cudaDeviceSynchronize());
-  cudaFree(d_verts); cudaFree(d_idx); cudaFree(d_tris); cudaFree(d_cen); cudaFree(d_trimat); cudaFree(d_in[0]); cudaFree(d_in[1]);
-  cudaFree(d_flags);
   *d_bid_out = d_bid; *d_mat_out = d_mat;
+  d_bid = nullptr; d_mat = nullptr;   // now the caller's
   *vx_out = vx; *vy_out = vy; *vz_out = vz;
   if (launches) *launches += nl;
   return PFDTD_OK;

@@ -196,3 +196,33 @@ def test_halo_by_peer_stores_equals_halo_by_copies(capi, gpu, name):
             for graph in (1, 0):
                 r, _, _ = fc.run_ours(capi, case, n_parts=n, opts=[(capi.OPT_PEER_STORES, peer), (capi.OPT_USE_GRAPH, graph)])
                 assert np.array_equal(r, base), (n, peer, graph)
+
+
+def test_step_api_time_reversal(capi, gpu):
+    """launchFDTD3dStep's flip rule (kernels3d.cu:386,462-465): the pointers are flipped only when the direction did
+    not change, so a change of direction runs the lossless scheme backwards -- the field retraces its steps."""
+    dims = (64, 48, 40)
+    from parallelfdtd_b200 import synth
+    bid, mat = synth.shoebox(dims, 1)
+    tab = np.zeros((1, 20), dtype=np.float32)                       # admittance 0: lossless walls
+    s = capi.Solver()
+    s.setup_mesh(bid, mat, (32, 4, 1), capi.SRL_FORWARD, capi.F32, oracle.params(fc.LAM, 0), tab)
+    s.make_partition(2, [0, 0])
+    n_total = 200
+    src = np.zeros((1, n_total), dtype=np.float32)
+    src[0, 1] = 1.0                                                  # impulse at step 1, nothing afterwards
+    s.set_sources([[30, 20, 18]], [capi.SRC_HARD], src)
+    s.set_receivers([[40, 25, 20]])
+    out = np.zeros((1, n_total), np.float32)
+    k, n = 30, 70
+    snap = None
+    for i in range(n):
+        s.step(i, 1, out, n_total)
+        if i == k - 1:
+            snap = s.capture_mesh()                                  # P^k
+    for m in range(n - k + 1):                                       # first reversed call does not flip, then one step back per call
+        s.step(100 + m, -1, out, n_total)                            # step indices with a zero source sample
+    back = s.capture_mesh()
+    s.close()
+    assert np.abs(snap).max() > 0
+    assert fc.rel_l2(back, snap) < 1e-4
