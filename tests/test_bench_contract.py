@@ -1,0 +1,37 @@
+"""CPU: bench.py's JSON contract where it can be exercised without a GPU -- the reference arm on the CPU oracle port
+(--ref-kind port) at config-1 size -- and the product arm's refusal to run without a device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BENCH = os.path.join(ROOT, "bench.py")
+
+
+def test_reference_arm_port_line_has_the_contract_keys():
+    r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--ref-kind", "port", "--workload", "c1", "--steps", "30", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == "Mvox-updates/s" and d["unit"] == "Mvox/s"
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["n_gpus"] == 1 and d["dtype"] == "f32"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Mvox/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--ref-kind", "port", "--workload", "c1", "--gpus", "2", "--steps", "5"],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_product_arm_refuses_to_run_without_a_device(capi):
+    if capi.device_count() > 0:
+        return
+    r = subprocess.run([sys.executable, BENCH, "--workload", "c1", "--steps", "5"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
