@@ -68,6 +68,9 @@ void App::initializeMesh(unsigned int number_of_partitions) {
   if (m_materials.getNumberOfUniqueMaterials() == 0) m_materials.setGlobalMaterial(uniform_surfaces_(), 0.f);
   const uint3 block = make_uint3(32, 4, 1);                     // reference App.cpp:193
   const unsigned int type = (unsigned int)m_parameters.getUpdateType();
+  // frequency-dependent boundaries: the material rows are digital impedance filters of this order (0 = the
+  // reference's scalar admittance per octave)
+  m_mesh.setOption(PFDTD_OPT_DIF_ORDER, (long long)m_materials.getFilterOrder());
   if (vol_bid_.empty()) {
     // triangle mesh -> node volumes on the device (reference App.cpp:181-190 voxelizeGeometry), adopted by setupMesh
     if (m_geometry.getNumberOfTriangles() == 0) { c_log_msg(LOG_ERROR, "App::initializeMesh - no geometry"); throw(-1); }

@@ -82,6 +82,9 @@ class App {
   void setNumSteps(unsigned int num) { m_parameters.setNumSteps(num); }
   void setUpdateType(int i) { m_parameters.setUpdateType((enum UpdateType)i); }
   void setUniformMaterial(float R) { m_materials.setGlobalMaterial(uniform_surfaces_(), reflection2Admitance(R)); }
+  // frequency-dependent boundaries (additions; MaterialHandler::addFilterMaterials / setGlobalFilter)
+  void addSurfaceFilters(const float* coefs, unsigned int n_surfaces, unsigned int order) { m_materials.addFilterMaterials(coefs, n_surfaces, order); }
+  void setUniformFilter(const std::vector<float>& b, const std::vector<float>& a) { m_materials.setGlobalFilter(uniform_surfaces_(), b, a); }
   std::vector<float> getResponse(unsigned int rec);
   std::vector<double> getResponseDouble(unsigned int rec);
   void setDouble(bool set_to) { m_mesh.setDouble(set_to); }

@@ -43,6 +43,13 @@ void addSurfaceMaterials(FDTD::App& a, std::vector<float> coefs, unsigned int n_
   a.m_materials.addMaterials(coefs.data(), n_surfaces, n_coefs);   // reference AppPy.cpp:57-69
 }
 
+// additions: per-surface digital impedance filters, rows [b0 .. bN, a1 .. aN] flattened like addSurfaceMaterials
+void addSurfaceFilters(FDTD::App& a, std::vector<float> coefs, unsigned int n_surfaces, unsigned int order) {
+  if (order < 1 || order > 4) throw std::out_of_range("addSurfaceFilters: filter order must be 1..4");
+  if (coefs.size() < (size_t)n_surfaces * (2 * order + 1)) throw std::out_of_range("addSurfaceFilters: list shorter than surfaces*(2*order+1)");
+  a.addSurfaceFilters(coefs.data(), n_surfaces, order);
+}
+
 void addSourceDataFloat(FDTD::App& a, const std::vector<float>& data, int num_steps, int num_sources) {
   if ((long long)data.size() < (long long)num_steps * num_sources) throw std::out_of_range("addSourceDataFloat: list shorter than steps*sources");
   a.m_parameters.addInputData(std::vector<float>(data.begin(), data.begin() + (size_t)num_steps * num_sources));   // :71-82
@@ -99,6 +106,8 @@ PYBIND11_MODULE(libPyFDTD, m) {
       .def("addSourceDataDouble", &addSourceDataDouble)
       .def("addReceiver", &FDTD::App::addReceiver)
       .def("addSurfaceMaterials", &addSurfaceMaterials)
+      .def("addSurfaceFilters", &addSurfaceFilters, "per-surface digital impedance filters [b0..bN, a1..aN], flattened; order 1..4")
+      .def("setUniformFilter", &FDTD::App::setUniformFilter, "the same digital impedance filter (b: order+1 taps, a: a1..aN) on every surface")
       .def("setSpatialFs", &FDTD::App::setSpatialFs)
       .def("setNumSteps", &FDTD::App::setNumSteps)
       .def("setUpdateType", &FDTD::App::setUpdateType)

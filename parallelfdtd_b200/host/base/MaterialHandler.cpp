@@ -6,7 +6,7 @@
 #include "../global_includes.h"
 
 MaterialHandler::MaterialHandler()
-    : admitance_(true), number_of_coefficients_(MATERIAL_COEF_NUM), number_of_surfaces_(0), number_of_unique_materials_(0) {}
+    : admitance_(true), filter_order_(0), number_of_coefficients_(MATERIAL_COEF_NUM), number_of_surfaces_(0), number_of_unique_materials_(0) {}
 
 void MaterialHandler::addMaterials(float* material_ptr, unsigned int number_of_surfaces, unsigned int number_of_coefficients) {
   // rows shorter than 20 coefficients are zero-extended (reference MaterialHandler.cpp:27-45)
@@ -15,6 +15,34 @@ void MaterialHandler::addMaterials(float* material_ptr, unsigned int number_of_s
     for (unsigned int j = 0; j < number_of_coefficients; j++) row.at(j) = material_ptr[(size_t)i * number_of_coefficients + j];
     addSurfaceMaterial(row);
   }
+}
+
+void MaterialHandler::setFilterOrder(unsigned int order) {
+  if (order > 4) throw std::out_of_range("MaterialHandler::setFilterOrder: filter order > 4");
+  if (order != filter_order_ && number_of_surfaces_ != 0)
+    throw std::logic_error("MaterialHandler::setFilterOrder: surfaces were already added with another filter order");
+  filter_order_ = order;
+  if (order) admitance_ = true;                                  // filter rows are taken as they are
+}
+
+void MaterialHandler::addFilterMaterials(const float* coefs, unsigned int number_of_surfaces, unsigned int order) {
+  if (order == 0) throw std::out_of_range("MaterialHandler::addFilterMaterials: filter order 0 (use addMaterials)");
+  setFilterOrder(order);
+  const unsigned int per_row = 2 * order + 1;
+  std::vector<float> row(MATERIAL_COEF_NUM, 0.f);
+  for (unsigned int i = 0; i < number_of_surfaces; i++) {
+    for (unsigned int j = 0; j < per_row; j++) row[j] = coefs[(size_t)i * per_row + j];
+    addSurfaceMaterial(row);
+  }
+}
+
+void MaterialHandler::setGlobalFilter(unsigned int number_of_surfaces, const std::vector<float>& b, const std::vector<float>& a) {
+  if (b.size() < 2 || a.size() + 1 != b.size()) throw std::out_of_range("MaterialHandler::setGlobalFilter: need order+1 b taps and order a taps");
+  setFilterOrder((unsigned int)a.size());
+  std::vector<float> row(MATERIAL_COEF_NUM, 0.f);
+  for (size_t j = 0; j < b.size(); j++) row[j] = b[j];
+  for (size_t j = 0; j < a.size(); j++) row[b.size() + j] = a[j];
+  for (unsigned int i = 0; i < number_of_surfaces; i++) addSurfaceMaterial(row);
 }
 
 unsigned int MaterialHandler::addSurfaceMaterial(std::vector<float> material_coefficients) {

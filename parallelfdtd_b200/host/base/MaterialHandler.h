@@ -18,6 +18,17 @@ class MaterialHandler {
   void coefsAreAdmittances() { admitance_ = true; }
   void coefsAreReflectances() { admitance_ = false; }
 
+  // Frequency-dependent boundaries (not in the reference, whose `dif_` members are a stub; PFDTD_OPT_DIF_ORDER in
+  // include/pfdtd.h).  With a filter order N in 1..4 each surface row is the digital impedance filter of the surface,
+  // [b0 .. bN, a1 .. aN] (a0 = 1) zero-extended to 20 values, and the unique-material table keeps exactly those
+  // rows (no reflectance conversion, the octave index is not used).  Order 0 = the reference's scalar admittances.
+  void setFilterOrder(unsigned int order);
+  unsigned int getFilterOrder() const { return filter_order_; }
+  // n_surfaces rows of 2*order+1 coefficients each
+  void addFilterMaterials(const float* coefs, unsigned int number_of_surfaces, unsigned int order);
+  // the same filter on every surface: b has order+1 taps, a has order taps (a1..)
+  void setGlobalFilter(unsigned int number_of_surfaces, const std::vector<float>& b, const std::vector<float>& a);
+
   unsigned int getNumberOfCoefficients() { return number_of_coefficients_; }
   unsigned int getNumberOfSurfaces() { return number_of_surfaces_; }
   unsigned int getNumberOfUniqueMaterials() { return number_of_unique_materials_; }
@@ -36,6 +47,7 @@ class MaterialHandler {
  private:
   unsigned int findOrAdd(const std::vector<float>& coefs);
   bool admitance_;
+  unsigned int filter_order_;
   unsigned int number_of_coefficients_;
   unsigned int number_of_surfaces_;
   unsigned int number_of_unique_materials_;

@@ -131,6 +131,23 @@ static void test_material_handler() {
   { MaterialHandler mh; mh.setGlobalMaterial(4, 0.5f);                   // :145-159
     CHECK_EQ(mh.getNumberOfSurfaces(), 4u); CHECK_EQ(mh.getNumberOfUniqueMaterials(), 1u);
     mh.setMaterialIndexAt(2, 7); CHECK_EQ(mh.getMaterialIdxAt(2), 7u); mh.setMaterialIndexAt(9, 1); CHECK_EQ(mh.getMaterialIdxAt(3), 0u); }
+  { MaterialHandler mh;                                                  // filter materials (addition): rows [b0..bN, a1..aN]
+    CHECK_EQ(mh.getFilterOrder(), 0u);
+    const float rows[15] = {0.10f, 0.02f, 0.01f, -0.5f, 0.1f,   0.10f, 0.02f, 0.01f, -0.5f, 0.1f,   0.30f, 0.f, 0.f, -0.2f, 0.f};
+    mh.coefsAreReflectances();                                           // must not convert filter rows
+    mh.addFilterMaterials(rows, 3, 2);
+    CHECK_EQ(mh.getFilterOrder(), 2u); CHECK_EQ(mh.getNumberOfSurfaces(), 3u); CHECK_EQ(mh.getNumberOfUniqueMaterials(), 2u);
+    CHECK_EQ(mh.getMaterialIdxAt(1), 0u); CHECK_EQ(mh.getMaterialIdxAt(2), 1u);
+    float* p = mh.getMaterialCoefficientPtr(); double* pd = mh.getMaterialCoefficientPtrDouble();
+    CHECK_EQ(p[0], 0.10f); CHECK_EQ(p[3], -0.5f); CHECK_EQ(p[4], 0.1f); CHECK_EQ(p[5], 0.f); CHECK_EQ(p[20], 0.30f); CHECK_EQ(p[23], -0.2f);
+    CHECK_EQ(pd[3], (double)-0.5f);
+    CHECK_THROW(mh.setFilterOrder(3), std::logic_error); CHECK_THROW(mh.setFilterOrder(5), std::out_of_range);
+    CHECK_THROW(mh.addFilterMaterials(rows, 1, 0), std::out_of_range); }
+  { MaterialHandler mh; std::vector<float> b(3, 0.1f), a(2, -0.3f);
+    mh.setGlobalFilter(4, b, a);
+    CHECK_EQ(mh.getFilterOrder(), 2u); CHECK_EQ(mh.getNumberOfSurfaces(), 4u); CHECK_EQ(mh.getNumberOfUniqueMaterials(), 1u);
+    CHECK_EQ(mh.getUniqueCoefAt(0, 2), 0.1f); CHECK_EQ(mh.getUniqueCoefAt(0, 4), -0.3f); CHECK_EQ(mh.getUniqueCoefAt(0, 5), 0.f);
+    a.push_back(0.f); CHECK_THROW(mh.setGlobalFilter(1, b, a), std::out_of_range); }
 }
 
 // ---- CudaMeshTest.cpp:182-218 (host only) ------------------------------------------------------------------------

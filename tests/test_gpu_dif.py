@@ -52,3 +52,52 @@ def test_filters_change_the_response_and_reset_clears_state(capi, gpu):
     flat = dict(case, dif_order=0)
     r0, _, _ = fc.run_ours(capi, flat, matidx=0)
     assert not np.array_equal(r, r0)
+
+
+def test_python_module_filter_materials_match_the_c_abi(capi, gpu):
+    """Filter boundaries through the front end (libPyFDTD.App.addSurfaceFilters -> MaterialHandler -> App::initializeMesh
+    -> PFDTD_OPT_DIF_ORDER) give the responses of the same run made directly on the C ABI."""
+    import os
+    import sys
+    from oracle import oracle
+    from parallelfdtd_b200 import build, synth
+    build.build_py_module()
+    sys.path.insert(0, os.path.dirname(build.py_module_path()))
+    import libPyFDTD as pf
+
+    steps, order = 150, 2
+    bid, mat = synth.shoebox((48, 40, 49), 6)
+    tab = synth.filter_material_table([0.99, 0.95, 0.9, 0.8, 0.7, 0.5], order).astype(np.float32)
+    app = pf.App()
+    app.initializeDevices()
+    app.setVoxelVolumes(bid, mat)
+    app.setUpdateType(0)
+    app.setNumSteps(steps)
+    app.setSpatialFs(7000)
+    app.forcePartitionTo(1)
+    app.addSurfaceFilters(tab[:, :2 * order + 1].flatten().tolist(), 6, order)
+    dx = app.getDx()
+    sxyz, rxyz = (20, 18, 22), (30, 25, 12)
+    app.addSource(*[(c - 1) * dx for c in sxyz], 0, 0, 0)           # element = round(pos / dx) + 1
+    app.addReceiver(*[(c - 1) * dx for c in rxyz])
+    app.runSimulation()
+    r_app = np.array(app.getResponse(0), dtype=np.float32)
+    app.close()
+
+    s = capi.Solver()
+    s.set_option(capi.OPT_DIF_ORDER, order)
+    s.setup_mesh(bid, mat, (32, 4, 1), capi.SRL_FORWARD, capi.F32, oracle.params(fc.LAM, 0), tab)
+    s.make_partition(1, [0])
+    s.set_sources([list(sxyz)], [capi.SRC_HARD], oracle.source_samples(0, steps)[None, :])
+    s.set_receivers([list(rxyz)])
+    r, _ = s.run(steps)
+    s.close()
+    s0 = capi.Solver()                                                # the same room without filters differs
+    s0.setup_mesh(bid, mat, (32, 4, 1), capi.SRL_FORWARD, capi.F32, oracle.params(fc.LAM, 0), tab)
+    s0.make_partition(1, [0])
+    s0.set_sources([list(sxyz)], [capi.SRC_HARD], oracle.source_samples(0, steps)[None, :])
+    s0.set_receivers([list(rxyz)])
+    r0, _ = s0.run(steps)
+    s0.close()
+    assert np.abs(r).max() > 0 and not np.array_equal(r0, r)
+    assert np.array_equal(r_app, r[0])

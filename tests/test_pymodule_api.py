@@ -52,3 +52,19 @@ def test_host_side_setters_work_without_a_device(pf, capi):
             app.runSimulation()
     with pytest.raises(RuntimeError):
         app.initializeGeometryFromFile("x.vtk")
+
+
+def test_filter_materials_through_the_module(pf):
+    """additions for the frequency-dependent boundaries: per-surface rows [b0..bN, a1..aN], order 1..4"""
+    app = pf.App()
+    app.addSurfaceFilters([0.1, 0.02, 0.01, -0.5, 0.1] * 3, 3, 2)
+    with pytest.raises(IndexError):
+        app.addSurfaceFilters([0.1, 0.02], 3, 2)            # list shorter than surfaces * (2 order + 1)
+    with pytest.raises(IndexError):
+        app.addSurfaceFilters([0.1] * 11, 1, 5)             # order > 4
+    with pytest.raises(Exception):
+        app.addSurfaceFilters([0.1, 0.02, -0.5], 1, 1)      # another order once surfaces exist
+    other = pf.App()
+    other.setUniformFilter([0.1, 0.02, 0.01], [-0.5, 0.1])
+    with pytest.raises(IndexError):
+        pf.App().setUniformFilter([0.1, 0.02, 0.01], [-0.5])
