@@ -78,6 +78,25 @@ def build_host(force: bool = False) -> str:
     return HOST_LIB
 
 
+MEX_SRC = os.path.join(HOST_DIR, "mex_FDTD.cpp")
+MEX_STUB_DIR = os.path.normpath(os.path.join(HERE, "..", "tests", "cpp", "mex_stub"))
+MEX_TEST_SRC = os.path.normpath(os.path.join(HERE, "..", "tests", "cpp", "mex_tests.cpp"))
+MEX_TEST_BIN = os.path.normpath(os.path.join(HERE, "..", "tests", "cpp", "mex_tests"))
+
+
+def build_mex_tests(force: bool = False) -> str:
+    """The MATLAB gateway (host/mex_FDTD.cpp) compiled against the stand-in MEX API of tests/cpp/mex_stub (MATLAB is
+    not in this image) together with its driver -> tests/cpp/mex_tests.  Inside MATLAB the same source builds with
+    `mex` against the real mex.h."""
+    build_host()
+    deps = [MEX_SRC, MEX_TEST_SRC, os.path.join(MEX_STUB_DIR, "mex.h"), HOST_LIB, os.path.join(HOST_DIR, "App.h")]
+    if force or any(_newer(d, MEX_TEST_BIN) for d in deps):
+        subprocess.check_call([_host_cxx(), "-std=c++17", "-O2", "-Wall", "-Wno-unused-function", "-I", MEX_STUB_DIR, "-I", HOST_DIR,
+                               "-o", MEX_TEST_BIN, MEX_SRC, MEX_TEST_SRC, "-L", HERE, "-l:libpfdtd_host.so", "-l:libpfdtd_b200.so",
+                               "-Wl,-rpath," + HERE])
+    return MEX_TEST_BIN
+
+
 PY_MODULE_SRC = os.path.join(HOST_DIR, "AppPy.cpp")
 
 
@@ -106,3 +125,4 @@ if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose=True))
     print(build_host(force="--force" in sys.argv))
     print(build_py_module(force="--force" in sys.argv))
+    print(build_mex_tests(force="--force" in sys.argv))
