@@ -162,6 +162,15 @@ def pinned_u8(shape):
         return np.empty(shape, dtype=np.uint8), None
 
 
+def receiver_positions(gdims):
+    """Four receivers: one 18 voxels from the source (reached within the warm-up at any domain height, so the
+    finite-and-nonzero check of the responses means something at every N), three spread over the height so that
+    tall multi-slab domains record in several slabs."""
+    cx, cy, cz = gdims[0] // 2, gdims[1] // 2, gdims[2] // 2
+    far = [[cx + 17, cy + 5, min(gdims[2] - 2, 3 + (i * (gdims[2] - 6)) // 3)] for i in (0, 2, 3)]
+    return [[cx + 17, cy + 5, min(gdims[2] - 2, cz + 3)]] + far
+
+
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
     from parallelfdtd_b200 import capi, synth, slabs
@@ -207,7 +216,7 @@ def run_ours(args):
     src_xyz = [[cx, cy, cz]]
     n = np.arange(total, dtype=np.float64)
     src_tab = np.exp(-0.5 * ((n - 40.0) / 6.0) ** 2).astype(npdt)[None, :]      # DATA-type input: a Gaussian pulse
-    rec_xyz = [[cx + 17, cy + 5, min(gdims[2] - 2, 3 + (i * (gdims[2] - 6)) // 3)] for i in range(4)]
+    rec_xyz = receiver_positions(gdims)
     opts = [(capi.OPT_MATIDX_AS_WRITTEN, 0), (capi.OPT_OVERLAP, 0 if args.no_overlap else 1),
             (capi.OPT_KERNEL, {"auto": capi.KERNEL_AUTO, "tma": capi.KERNEL_TMA, "plain": capi.KERNEL_PLAIN}[args.kernel]),
             (capi.OPT_TMA_TILE, args.tile), (capi.OPT_TMA_CHUNK, args.chunk), (capi.OPT_DIF_ORDER, args.dif_order)]
@@ -434,7 +443,7 @@ def run_reference(args):
     bid, mat = synth.shoebox(gdims, n_mat)
     tab = synth.material_table(list(np.linspace(0.99, 0.5, n_mat)) if n_mat > 1 else [0.9])
     cx, cy, cz = gdims[0] // 2, gdims[1] // 2, gdims[2] // 2
-    rec_xyz = [(cx + 17, cy + 5, min(gdims[2] - 2, 3 + (i * (gdims[2] - 6)) // 3)) for i in range(4)]
+    rec_xyz = [tuple(r) for r in receiver_positions(gdims)]
     nn = np.arange(K + W + 64, dtype=np.float64)
     pulse = np.exp(-0.5 * ((nn - 40.0) / 6.0) ** 2)
     if kind == "reference":

@@ -12,16 +12,18 @@
 class GeometryHandler {
  public:
   GeometryHandler() {}
+  // number_of_vertices counts the float COORDINATES (3 per vertex), as in the reference, whose callers pass
+  // mxGetNumberOfElements(vertices) (reference GeometryHandler.cpp:87-108, matlab/mex_FDTD.cpp:89,198)
   void initialize(unsigned int* indices, float* vertices, unsigned int number_of_indices, unsigned int number_of_vertices) {
     indices_.assign(indices, indices + number_of_indices);
-    vertices_.assign(vertices, vertices + (size_t)number_of_vertices * 3);
+    vertices_.assign(vertices, vertices + number_of_vertices);
     for (size_t i = 0; i < indices_.size(); i++)
-      if (indices_[i] >= number_of_vertices) throw std::out_of_range("GeometryHandler::initialize: vertex index out of range");
+      if (indices_[i] >= number_of_vertices / 3) throw std::out_of_range("GeometryHandler::initialize: vertex index out of range");
     update_();
   }
   void initialize(std::vector<unsigned int> indices, std::vector<float> vertices) {
     initialize(indices.empty() ? 0 : &indices[0], vertices.empty() ? 0 : &vertices[0], (unsigned int)indices.size(),
-               (unsigned int)(vertices.size() / 3));
+               (unsigned int)vertices.size());
   }
   unsigned int getNumberOfTriangles() const { return (unsigned int)(indices_.size() / 3); }
   unsigned int getNumberOfVertices() const { return (unsigned int)(vertices_.size() / 3); }

@@ -180,6 +180,11 @@ static void test_geometry_and_voxelizer() {
   GeometryHandler g; g.initialize(idx, v);                               // GeometryHandlerTest.cpp:85-100: 1 m box, area 6
   CHECK_EQ(g.getNumberOfTriangles(), 12u); CHECK(std::fabs(g.getTotalSurfaceArea() - 6.f) < 1e-5f);
   CHECK(g.getBoundingBox() == nv::Vec3f(1.f, 1.f, 1.f));
+  { GeometryHandler gp; gp.initialize(&idx[0], &v[0], (unsigned)idx.size(), (unsigned)v.size());   // pointer form: the last argument counts
+    CHECK_EQ(gp.getNumberOfVertices(), 8u); CHECK_EQ(gp.getNumberOfTriangles(), 12u);                // floats (reference GeometryHandler.cpp:87-108)
+    CHECK(gp.getBoundingBox() == nv::Vec3f(1.f, 1.f, 1.f));
+    std::vector<unsigned> bad(idx); bad[0] = 8; GeometryHandler gb;
+    CHECK_THROW(gb.initialize(&bad[0], &v[0], (unsigned)bad.size(), (unsigned)v.size()), std::out_of_range); }
   const float dx = 0.1f;
   pfdtd_host::VoxelVolumes vol = pfdtd_host::voxelize(g, dx, 0);
   CHECK_EQ(vol.vx, 13u);
@@ -305,7 +310,7 @@ static void test_cuda_mesh_gpu() {
     std::vector<float> resp[2];
     for (int mode = 0; mode < 2; mode++) {
       FDTD::App app; app.m_progress = quiet; app.initializeDevices();
-      app.initializeGeometry(&idx[0], &v[0], (unsigned)idx.size(), (unsigned)v.size() / 3);
+      app.initializeGeometry(&idx[0], &v[0], (unsigned)idx.size(), (unsigned)v.size());   // float count, like the reference's callers
       app.setUniformMaterial(0.9f); app.setSpatialFs(7000); app.setNumSteps(120); app.setUpdateType(0); app.setForcePartitionTo(1);
       app.addSource(0.5f, 0.5f, 0.5f, 0, 0, 0); app.addReceiver(1.5f, 1.0f, 0.7f);
       if (mode == 0) { app.runSimulation(); CHECK(app.getMvoxPerSec() > 0); CHECK(app.getVolume() > 2.5f && app.getVolume() < 4.5f); CHECK(app.getSabine(0) > 0); }
