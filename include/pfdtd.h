@@ -97,6 +97,20 @@ const char* pfdtd_version(void);
 int pfdtd_device_count(int* out_count);
 int pfdtd_device_mem_mb(int device, int* out_total_mb, int* out_free_mb);
 
+/* ---- device memory helpers (src/kernels/cudaUtils.h:59-171: toDevice / valueToDevice / fromDevice / copyHostToDevice /
+ * copyDeviceToHost / destroyMem / getCurrentDevice) -------------------------------------------------------------
+ * The reference's callers (its tests, the voxelizer wrapper) create the `bid` / material volumes with these helpers and
+ * hand them to CudaMesh::setupMesh, which adopts them (pfdtd_setup_mesh_device).  `device` -1 = the calling thread's
+ * current device; otherwise the device is made current, as the reference's helpers do.  Blocking, like the
+ * reference's. */
+int pfdtd_current_device(int* device);
+int pfdtd_device_alloc(int device, size_t bytes, void** d_ptr);
+/* valueToDevice: `count` elements of `elem_size` (1, 2, 4 or 8) bytes set to *value, written on the device */
+int pfdtd_device_fill(int device, void* d_ptr, size_t count, size_t elem_size, const void* value);
+int pfdtd_device_upload(int device, void* d_dst, const void* h_src, size_t bytes);
+int pfdtd_device_download(int device, void* h_dst, const void* d_src, size_t bytes);
+int pfdtd_device_free(int device, void* d_ptr);
+
 /* ---- solver lifetime ----------------------------------------------------- */
 int pfdtd_create(pfdtd_solver** out);
 /* CudaMesh::destroyPartitions (src/kernels/cudaMesh.h:160-182) + receiver buffers */

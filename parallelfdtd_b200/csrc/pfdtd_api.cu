@@ -513,6 +513,25 @@ static int elem_of(pfdtd_solver* s, uint32_t x, uint32_t y, int64_t zl, size_t k
   return PFDTD_OK;
 }
 
+// valueToDevice of the reference fills on the host and copies (cudaUtils.h:84-99); here the value is written on the device
+template <typename W>
+__global__ void fill_words(W* __restrict__ d, W v, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = v;
+}
+
+static int select_device(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    set_error("no CUDA device: libpfdtd_b200 has no CPU fallback");
+    return PFDTD_ERR_NO_DEVICE;
+  }
+  if (device >= 0) {
+    PF_CHECK(device < ndev, PFDTD_ERR_RANGE, "device %d of %d", device, ndev);
+    PF_CUDA(cudaSetDevice(device));
+  }
+  return PFDTD_OK;
+}
+
 }  // namespace pfdtd
 
 // =========================================================================================================
@@ -541,6 +560,65 @@ int pfdtd_device_mem_mb(int device, int* out_total_mb, int* out_free_mb) {
   PF_CUDA(cudaMemGetInfo(&f, &t));
   if (out_total_mb) *out_total_mb = (int)(t >> 20);
   if (out_free_mb) *out_free_mb = (int)(f >> 20);
+  return PFDTD_OK;
+}
+
+int pfdtd_current_device(int* device) {
+  PF_CHECK(device != nullptr, PFDTD_ERR_INVALID, "null out pointer");
+  PF_TRY(select_device(-1));
+  PF_CUDA(cudaGetDevice(device));
+  return PFDTD_OK;
+}
+
+int pfdtd_device_alloc(int device, size_t bytes, void** d_ptr) {
+  PF_CHECK(d_ptr != nullptr, PFDTD_ERR_INVALID, "null out pointer");
+  *d_ptr = nullptr;
+  PF_TRY(select_device(device));
+  PF_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 1));
+  return PFDTD_OK;
+}
+
+int pfdtd_device_fill(int device, void* d_ptr, size_t count, size_t elem_size, const void* value) {
+  PF_CHECK(d_ptr != nullptr && value != nullptr, PFDTD_ERR_INVALID, "null pointer");
+  PF_CHECK(elem_size == 1 || elem_size == 2 || elem_size == 4 || elem_size == 8, PFDTD_ERR_INVALID, "element size %zu", elem_size);
+  PF_TRY(select_device(device));
+  if (count == 0) return PFDTD_OK;
+  const unsigned int blocks = (unsigned int)std::min<size_t>((count + 255) / 256, 148 * 8);
+  if (elem_size == 1) {
+    PF_CUDA(cudaMemset(d_ptr, *(const uint8_t*)value, count));
+  } else if (elem_size == 2) {
+    uint16_t v; memcpy(&v, value, 2);
+    fill_words<uint16_t><<<blocks, 256>>>((uint16_t*)d_ptr, v, count);
+  } else if (elem_size == 4) {
+    uint32_t v; memcpy(&v, value, 4);
+    fill_words<uint32_t><<<blocks, 256>>>((uint32_t*)d_ptr, v, count);
+  } else {
+    uint64_t v; memcpy(&v, value, 8);
+    fill_words<uint64_t><<<blocks, 256>>>((uint64_t*)d_ptr, v, count);
+  }
+  PF_CUDA(cudaGetLastError());
+  PF_CUDA(cudaDeviceSynchronize());
+  return PFDTD_OK;
+}
+
+int pfdtd_device_upload(int device, void* d_dst, const void* h_src, size_t bytes) {
+  PF_CHECK(bytes == 0 || (d_dst != nullptr && h_src != nullptr), PFDTD_ERR_INVALID, "null pointer");
+  PF_TRY(select_device(device));
+  if (bytes) PF_CUDA(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+  return PFDTD_OK;
+}
+
+int pfdtd_device_download(int device, void* h_dst, const void* d_src, size_t bytes) {
+  PF_CHECK(bytes == 0 || (h_dst != nullptr && d_src != nullptr), PFDTD_ERR_INVALID, "null pointer");
+  PF_TRY(select_device(device));
+  if (bytes) PF_CUDA(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+  return PFDTD_OK;
+}
+
+int pfdtd_device_free(int device, void* d_ptr) {
+  if (!d_ptr) return PFDTD_OK;
+  PF_TRY(select_device(device));
+  PF_CUDA(cudaFree(d_ptr));
   return PFDTD_OK;
 }
 

@@ -151,6 +151,15 @@ static void test_material_handler() {
 }
 
 // ---- CudaMeshTest.cpp:182-218 (host only) ------------------------------------------------------------------------
+// without a device the allocation helpers fail like every other device call of the reference: log + throw(-1)
+static void test_device_helpers_without_a_device() {
+  int ndev = 0; pfdtd_device_count(&ndev);
+  if (ndev > 0) return;
+  CHECK_THROW(valueToDevice<unsigned char>(8, (unsigned char)1, 0), int);
+  CHECK_THROW(toDevice<float>(8, 0), int);
+  CHECK_THROW(getCurrentDevice(), int);
+}
+
 static void test_partition_indexing() {
   CudaMesh mesh;
   const int dim_z = 100, num_p = 13, ps = dim_z / num_p;
@@ -253,6 +262,38 @@ static void test_cuda_mesh_gpu() {
     CHECK_EQ(dev, 0); CHECK_EQ(el, 10 * 20 * 32 + 10 * 32 + 10);
     mesh.getElementIdxAndDevice(10, 10, 30, &dev, &el); CHECK_EQ(dev, -1); CHECK_EQ(el, -1);
   }
+  { // the reference's own hand-over (CudaMeshTest.cpp:226-233): device volumes made with valueToDevice, adopted by setupMesh
+    const unsigned n = 20 * 20 * 20;
+    unsigned char* d_pos = valueToDevice<unsigned char>(n, (unsigned char)0, 0);
+    unsigned char* d_mat = valueToDevice<unsigned char>(n, (unsigned char)0, 0);
+    CudaMesh mesh;
+    mesh.setupMesh(d_pos, d_mat, mh.getNumberOfUniqueMaterials(), mh.getMaterialCoefficientPtr(), sp.getParameterPtr(), make_uint3(20, 20, 20),
+                   make_uint3(32, 4, 2), 0);
+    mesh.makePartition(1);
+    CHECK_EQ(mesh.getDimX(), 32u); CHECK_EQ(mesh.getDimY(), 20u); CHECK_EQ(mesh.getDimZ(), 20u);
+    CHECK_EQ(mesh.getNumberOfAirElements(), 0u);
+  }
+  { // cudaUtils.h helpers (reference cudaUtils.h:59-171)
+    CHECK_EQ(getCurrentDevice(), 0);
+    std::vector<float> h(1000); for (size_t i = 0; i < h.size(); i++) h[i] = (float)i * 0.5f;
+    float* d = toDevice<float>(1000, &h[0], 0);
+    float* back = fromDevice<float>(1000, d, 0);
+    CHECK(std::memcmp(back, &h[0], 4000) == 0); std::free(back);
+    CHECK_EQ(getSample<float>(7, d), 3.5f);
+    resetData<float>(1000, d, 0); CHECK_EQ(getSample<float>(7, d), 0.f);
+    h[3] = -2.f; copyHostToDevice<float>(1000, d, &h[0], 0);
+    std::vector<float> h2(1000, 0.f); copyDeviceToHost<float>(1000, &h2[0], d, 0); CHECK(h2 == h);
+    destroyMem(d, 0);
+    double* dd = valueToDevice<double>(333, 1.25, 0); double* hd = fromDevice<double>(333, dd, 0);
+    bool all = true; for (int i = 0; i < 333; i++) all &= hd[i] == 1.25; CHECK(all); std::free(hd); destroyMem(dd);
+    float* df = valueToDevice<float>(777, -3.f, 0); float* hf = fromDevice<float>(777, df, 0);
+    all = true; for (int i = 0; i < 777; i++) all &= hf[i] == -3.f; CHECK(all); std::free(hf); destroyMem(df);
+    unsigned short* ds = valueToDevice<unsigned short>(5, (unsigned short)0xBEEF, 0); unsigned short* hs = fromDevice<unsigned short>(5, ds, 0);
+    CHECK_EQ(hs[4], (unsigned short)0xBEEF); std::free(hs); destroyMem(ds);
+    unsigned char* dz = toDevice<unsigned char>(64, 0); unsigned char* hz = fromDevice<unsigned char>(64, dz, 0);
+    all = true; for (int i = 0; i < 64; i++) all &= hz[i] == 0; CHECK(all); std::free(hz); destroyMem(dz);
+    CHECK_THROW(valueToDevice<float>(4, 1.f, 99), std::out_of_range);     // no such device
+  }
   { // CudaMesh_get_set_multi (:260-303): 50^3, 5 partitions on one device
     std::vector<unsigned char> z((size_t)50 * 50 * 50, 0);
     CudaMesh mesh;
@@ -326,7 +367,7 @@ static void test_cuda_mesh_gpu() {
 
 int main(int argc, char** argv) {
   const std::string what = argc > 1 ? argv[1] : "cpu";
-  if (what == "cpu") { test_simulation_parameters(); test_srcrec(); test_material_handler(); test_partition_indexing(); test_geometry_and_voxelizer(); }
+  if (what == "cpu") { test_simulation_parameters(); test_srcrec(); test_material_handler(); test_device_helpers_without_a_device(); test_partition_indexing(); test_geometry_and_voxelizer(); }
   else if (what == "gpu") { test_cuda_mesh_gpu(); test_voxelizer_gpu(); }
   std::printf("%s: %d checks, %d failures\n", what.c_str(), g_checks, g_fail);
   return g_fail ? 1 : 0;

@@ -54,6 +54,24 @@ def test_no_device_fails_loudly(capi):
     s.close()
 
 
+def test_device_memory_helpers_fail_loudly_without_a_device(capi):
+    """pfdtd_device_alloc / fill / upload / download / free / current_device (reference cudaUtils.h:59-171 helpers)"""
+    import ctypes as C
+    L = capi.lib()
+    if capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    p = C.c_void_p()
+    assert L.pfdtd_device_alloc(C.c_int(0), C.c_size_t(64), C.byref(p)) == 3 and not p.value
+    d = C.c_int(-7)
+    assert L.pfdtd_current_device(C.byref(d)) == 3
+    buf = (C.c_ubyte * 8)()
+    assert L.pfdtd_device_upload(C.c_int(0), C.c_void_p(16), buf, C.c_size_t(8)) == 3
+    assert L.pfdtd_device_download(C.c_int(0), buf, C.c_void_p(16), C.c_size_t(8)) == 3
+    assert L.pfdtd_device_fill(C.c_int(0), C.c_void_p(16), C.c_size_t(8), C.c_size_t(3), buf) == 1     # bad element size first
+    assert L.pfdtd_device_free(C.c_int(0), None) == 0                                                  # freeing nothing is fine
+    assert b"no CPU fallback" in L.pfdtd_last_error() or b"element size" in L.pfdtd_last_error()
+
+
 def test_call_order_errors(capi):
     s = capi.Solver()
     with pytest.raises(capi.PfdtdError):
