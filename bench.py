@@ -340,7 +340,7 @@ def run_ours(args):
             line["variants"] = run_variants(args)
         if world > 1:
             line["halo_ms_last_step"] = halo_ms_last
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -438,7 +438,7 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic"}
     if kind == "reference" and nvox_in >= 2**31:
         # the reference indexes voxels with 32-bit ints (cudaMesh.h:142, kernels3d.cu:505-506)
-        print(json.dumps({"impl": "reference", "unavailable": f"{nvox_in} voxels exceed the reference's 32-bit indexing"}))
+        emit({"impl": "reference", "unavailable": f"{nvox_in} voxels exceed the reference's 32-bit indexing"})
         return
     bid, mat = synth.shoebox(gdims, n_mat)
     tab = synth.material_table(list(np.linspace(0.99, 0.5, n_mat)) if n_mat > 1 else [0.9])
@@ -469,7 +469,7 @@ def run_reference(args):
                          "seconds": wall_e2e,
                          "what": "toDevice(bid,mat) + setupMesh + makePartition + launchFDTD3d incl. per-step source H2D and final response D2H"},
                     gpu_launches=0)
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     # CPU oracle port
     pos, m, _, _ = oracle.setup_mesh(bid, mat, (32, 4, 1), args.update_type, double)
@@ -488,11 +488,34 @@ def run_reference(args):
                 cpu_baseline={"value": value, "unit": "Mvox/s", "cores": threads, "kind": "port",
                               "sample": f"{steps - 1} timed steps of the C++/OpenMP oracle port on the same workload"},
                 e2e={"value": value, "unit": "Mvox/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: everything libraries print there while the job runs (NCCL's
+    version banner, torch warnings) is sent to stderr instead, and the result goes to the original descriptor."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    txt = json.dumps(line) + "\n"
+    if _RESULT_FD is None:
+        sys.stdout.write(txt)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, txt.encode())
 
 
 if __name__ == "__main__":
     a = parse_args()
+    claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

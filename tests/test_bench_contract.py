@@ -13,6 +13,7 @@ def test_reference_arm_port_line_has_the_contract_keys():
     r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--ref-kind", "port", "--workload", "c1", "--steps", "30", "--warmup", "3"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
+    assert len(r.stdout.strip().splitlines()) == 1            # stdout carries the JSON line and nothing else
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["metric"] == "Mvox-updates/s" and d["unit"] == "Mvox/s"
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
