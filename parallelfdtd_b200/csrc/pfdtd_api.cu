@@ -1470,6 +1470,10 @@ int pfdtd_run(pfdtd_solver* s, uint32_t n_steps, void* h_response, pfdtd_interru
 
 int pfdtd_step(pfdtd_solver* s, uint32_t step, int direction, void* h_response, uint32_t n_steps_total) {
   PF_CHECK(s && !s->parts.empty(), PFDTD_ERR_INVALID, "make_partition must be called before step");
+  PF_CHECK(direction == 1 || direction == -1, PFDTD_ERR_INVALID, "direction must be +1 or -1");
+  // the reference writes h_return_ptr[rec * numSteps + step] unchecked (kernels3d.cu:447-455)
+  PF_CHECK(!h_response || s->n_rec == 0 || step < n_steps_total, PFDTD_ERR_RANGE, "step %u beyond the %u-step response buffer", step,
+           n_steps_total);
   PF_TRY(prepare_srcrec(s));
   PF_TRY(ensure_class_tables(s));
   PF_TRY(sync_all(s));
