@@ -1273,13 +1273,16 @@ int pfdtd_reset_pressures(pfdtd_solver* s) {
 }
 
 // ---- sources / receivers ----------------------------------------------------------------------------------
+// height of the whole domain: the local mesh, or the taller domain this process owns a slab of (PFDTD_OPT_GLOBAL_Z_DIM)
+static int64_t global_z_dim(const pfdtd_solver* s) { return s->opt_global_z_dim > 0 ? (int64_t)s->opt_global_z_dim : (int64_t)s->Z; }
+
 int pfdtd_set_sources(pfdtd_solver* s, uint32_t n, const int32_t* xyz, const int32_t* src_types, const void* samples,
                       uint32_t n_steps) {
   PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
   PF_CHECK(n == 0 || (xyz && src_types && samples), PFDTD_ERR_INVALID, "null source arrays");
   for (uint32_t i = 0; i < n; i++)
     PF_CHECK(xyz[3 * i] >= 0 && xyz[3 * i + 1] >= 0 && xyz[3 * i + 2] >= 0 &&
-                 (s->X == 0 || ((uint32_t)xyz[3 * i] < s->X && (uint32_t)xyz[3 * i + 1] < s->Y)),
+                 (s->X == 0 || ((uint32_t)xyz[3 * i] < s->X && (uint32_t)xyz[3 * i + 1] < s->Y && (int64_t)xyz[3 * i + 2] < global_z_dim(s))),
              PFDTD_ERR_RANGE, "source %u at (%d,%d,%d) is outside the mesh", i, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
   s->n_src = n;
   s->src_steps = n_steps;
@@ -1295,7 +1298,7 @@ int pfdtd_set_receivers(pfdtd_solver* s, uint32_t n, const int32_t* xyz) {
   PF_CHECK(n == 0 || xyz, PFDTD_ERR_INVALID, "null receiver array");
   for (uint32_t i = 0; i < n; i++)
     PF_CHECK(xyz[3 * i] >= 0 && xyz[3 * i + 1] >= 0 && xyz[3 * i + 2] >= 0 &&
-                 (s->X == 0 || ((uint32_t)xyz[3 * i] < s->X && (uint32_t)xyz[3 * i + 1] < s->Y)),
+                 (s->X == 0 || ((uint32_t)xyz[3 * i] < s->X && (uint32_t)xyz[3 * i + 1] < s->Y && (int64_t)xyz[3 * i + 2] < global_z_dim(s))),
              PFDTD_ERR_RANGE, "receiver %u at (%d,%d,%d) is outside the mesh", i, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
   s->n_rec = n;
   s->rec_xyz.assign(xyz, xyz + 3 * (size_t)n);
