@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tma-hints", type=int, default=None, help="PFDTD_OPT_TMA_HINTS override (sweeps)")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "reference", "port"],
                     help="reference arm: the reference's own CUDA build (oracle/_ref) or the CPU oracle port")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -220,6 +221,8 @@ def run_ours(args):
     opts = [(capi.OPT_MATIDX_AS_WRITTEN, 0), (capi.OPT_OVERLAP, 0 if args.no_overlap else 1),
             (capi.OPT_KERNEL, {"auto": capi.KERNEL_AUTO, "tma": capi.KERNEL_TMA, "plain": capi.KERNEL_PLAIN}[args.kernel]),
             (capi.OPT_TMA_TILE, args.tile), (capi.OPT_TMA_CHUNK, args.chunk), (capi.OPT_DIF_ORDER, args.dif_order)]
+    if args.tma_hints is not None:
+        opts.append((capi.OPT_TMA_HINTS, args.tma_hints))
 
     def make_solver():
         ss = slabs.SlabSolver(capi, gdims, lambda a, b: (bid, mat), block=(32, 4, 1), element_type=args.update_type, dtype=dt,
