@@ -6,6 +6,8 @@ sm_100 by oracle/Makefile) on the cases of tests/fdtd_cases.parity_cases() and s
 responses, padded dims, node counts, partition index sets and node bytes.  This pins the oracle:
 bit-exact responses (fp32 and fp64), bit-exact node bytes and partition layout.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -58,3 +60,13 @@ def test_constructor_lambda_differs_in_double_only():
     finally:
         fc.LAM = saved
     assert not np.array_equal(r, g["responses"]) and fc.rel_l2(r, g["responses"]) < 1e-11
+
+
+def test_golden_fixtures_are_consistent_with_their_case_definitions():
+    """tools/make_golden.py --check-only: shapes, dtypes, the slab rule and the node checksums of every fixture."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "make_golden.py"), "--check-only"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count(": ok") == len(fc.parity_cases())
