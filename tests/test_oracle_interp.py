@@ -75,3 +75,35 @@ def test_partition_invariance_and_first_arrival(ut):
     # a 27-point stencil reaches a node 10 voxels away along x after 10 updates (impulse at step 1 -> response index 10)
     first = np.flatnonzero(base[3] != 0)[0]
     assert first == 10
+
+
+@pytest.mark.parametrize("ut,a,b", [(3, 1.0 / 6.0, 0.0), (4, 1.0 / 4.0, 1.0 / 16.0)])
+def test_weights_follow_the_published_family_and_land_on_the_right_neighbours(ut, a, b):
+    """Literature anchor (Kowalczyk & van Walstijn, "Room acoustics simulation using 3-D compact explicit FDTD schemes",
+    IEEE TASLP 2011): d1 = lam^2 (1 - 4a + 4b), d2 = lam^2 (a - 2b), d3 = lam^2 b, d4 = 2 (1 - 3 lam^2 + 6 lam^2 a - 4 lam^2 b),
+    IISO (a, b, lam) = (1/6, 0, sqrt(3)/2), IWB = (1/4, 1/16, 1).  And a known answer for WHERE the weights act: one step
+    after a unit impulse in open air the six axial neighbours hold d1, the twelve edge neighbours d2, the eight corner
+    neighbours d3, the voxel itself d4 and everything else 0."""
+    lam = {3: np.sqrt(3.0) / 2.0, 4: 1.0}[ut]
+    assert oracle.interp_lambda(ut) == pytest.approx(lam, abs=1e-15)
+    l2 = lam * lam
+    lit = [l2 * (1 - 4 * a + 4 * b), l2 * (a - 2 * b), l2 * b, 2 * (1 - 3 * l2 + 6 * l2 * a - 4 * l2 * b)]
+    d = oracle.interp_coefficients(ut, l2)
+    assert np.allclose(d, lit, rtol=0, atol=1e-15)
+
+    bid, mat = synth.shoebox((16, 16, 16), 1)
+    pos, m, _, _ = oracle.setup_mesh(bid, mat, (4, 2, 1), 0, True)
+    p8 = oracle.params_interp(lam, 0, d, True)
+    c = 8
+    offs = [(dx, dy, dz) for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1)] + [(2, 0, 0), (0, -2, 0), (2, 1, 0), (1, 1, 2)]
+    rec = [(c + dx, c + dy, c + dz) for dx, dy, dz in offs]
+    src = np.zeros((1, 2))
+    src[0, 0] = 1.0
+    r, _ = oracle.run(pos, m, 3, p8, np.zeros((1, 20)), [(c, c, c)], [0], src, rec, 2, 1, 0)
+    for (dx, dy, dz), v in zip(offs, r[:, 0]):                # response[step 0] = the field after the first update
+        n_off = abs(dx) + abs(dy) + abs(dz)
+        if max(abs(dx), abs(dy), abs(dz)) > 1:
+            want = 0.0
+        else:
+            want = {0: d[3], 1: d[0], 2: d[1], 3: d[2]}[n_off]
+        assert v == want, ((dx, dy, dz), v, want)
