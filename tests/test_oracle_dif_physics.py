@@ -10,7 +10,12 @@ which follows from inserting p_i^n = e^{jwn} (e^{jki} + R e^{-jki}) into the bou
 (1 + b) p0^{n+1} = (2 - lam^2) p0^n + lam^2 p1^n - (1 - b) p0^{n-1}, b = lam Y / 2, and tends to the textbook
 (1 - Y) / (1 + Y) for w -> 0.  What this pins: the sign and the delay conventions of the filter recursion (transposed
 direct form II on u = p^{n+1} - p^{n-1}), the coupling coefficient, and that order 0 is the scalar admittance -- for
-filter orders 0, 1, 2 and 4.  The CUDA kernels are bit-equal to this oracle (tests/test_gpu_dif.py).
+filter orders 0, 1, 2 and 4.  The centred-difference boundary of the SRL scheme (the interior neighbour counted twice,
+b = lam Y) gives, the same way,
+
+    R(w) = (lam sin k - Y(e^{jw}) sin w) / (lam sin k + Y(e^{jw}) sin w)
+
+and is checked for orders 0, 2 and 3.  The CUDA kernels are bit-equal to this oracle (tests/test_gpu_dif.py).
 """
 import numpy as np
 import pytest
@@ -24,7 +29,7 @@ ZS, ZR = 10, 200                 # source plane, receiver plane
 STEPS = 1500                     # incident pulse passes ZR around step 330, the reflection around 1080
 
 
-def _duct(order, b, a):
+def _duct(order, b, a, scheme=0):
     """-> pos, mat node volumes and the [4][20] material table: 0 rigid side walls, 1 / 2 / 3 the end wall's face, edge
     and corner voxels, whose admittance is Y / (number of missing neighbours) so that the cross-section stays uniform
     (the boundary term is proportional to 6 - K, and only one of an edge voxel's missing neighbours is the end wall)."""
@@ -39,7 +44,7 @@ def _duct(order, b, a):
     missing = 1 + (x == 1) + (x == NX) + (y == 1) + (y == NY)
     end = bid[Z - 2] > 0
     mat[Z - 2][end] = np.broadcast_to(missing, end.shape)[end].astype(np.uint8)
-    pos, m, _, _ = oracle.setup_mesh(bid, mat, (32, 4, 1), 0, True)
+    pos, m, _, _ = oracle.setup_mesh(bid, mat, (32, 4, 1), scheme, True)
     tab = np.zeros((4, 20), dtype=np.float64)
     for k in (1, 2, 3):
         tab[k, :order + 1] = np.asarray(b) / k
@@ -47,13 +52,13 @@ def _duct(order, b, a):
     return pos, m, tab
 
 
-def _measured_reflectance(order, b, a):
-    pos, m, tab = _duct(order, b, a)
+def _measured_reflectance(order, b, a, scheme=0):
+    pos, m, tab = _duct(order, b, a, scheme)
     src_xyz = [[x, y, ZS] for y in range(1, NY + 1) for x in range(1, NX + 1)]
     n = np.arange(STEPS, dtype=np.float64)
     pulse = np.exp(-0.5 * ((n - 40.0) / 6.0) ** 2)        # band-limited well below the axial cut-off (w = 1.23 rad / sample)
     prm = oracle.params(LAM, 0, True)
-    r, _ = oracle.run_dif(pos, m, 0, prm, tab, order, src_xyz, [0] * len(src_xyz), np.tile(pulse, (len(src_xyz), 1)),
+    r, _ = oracle.run_dif(pos, m, scheme, prm, tab, order, src_xyz, [0] * len(src_xyz), np.tile(pulse, (len(src_xyz), 1)),
                           [[3, 3, ZR], [1, 1, ZR], [NX, 4, ZR]], STEPS, 1)
     assert np.max(np.abs(r[0] - r[1])) < 1e-12 and np.max(np.abs(r[0] - r[2])) < 1e-12      # the wave stays plane
     split = 700
@@ -67,7 +72,7 @@ def _measured_reflectance(order, b, a):
     return w, np.abs(Fr) / np.maximum(np.abs(Fi), 1e-300), np.abs(Fi) / np.abs(Fi).max()
 
 
-def _closed_form(w, b, a):
+def _closed_form(w, b, a, scheme=0):
     zi = np.exp(-1j * w)
     order = len(b) - 1
     Y = sum(b[i] * zi ** i for i in range(order + 1)) / (1.0 + sum(a[i] * zi ** (i + 1) for i in range(order)))
@@ -75,6 +80,8 @@ def _closed_form(w, b, a):
     D = 1j * LAM * Y * np.sin(w)
     lam2 = LAM * LAM
     with np.errstate(invalid="ignore", divide="ignore"):              # w = 0 is 0 / 0 and is not used
+        if scheme == 2:                                                # centred-difference boundary, see the module docstring
+            return (LAM * np.sin(k) - Y * np.sin(w)) / (LAM * np.sin(k) + Y * np.sin(w)), Y
         return -(lam2 * (np.exp(-1j * k) - 1.0) + D) / (lam2 * (np.exp(1j * k) - 1.0) + D), Y
 
 
@@ -88,11 +95,11 @@ def _filter(order, y0=0.25):
     return y0 * b, a[1:]
 
 
-@pytest.mark.parametrize("order", [0, 1, 2, 4])
-def test_normal_incidence_reflectance_matches_the_closed_form(order):
+@pytest.mark.parametrize("scheme,order", [(0, 0), (0, 1), (0, 2), (0, 4), (2, 0), (2, 2), (2, 3)])
+def test_normal_incidence_reflectance_matches_the_closed_form(scheme, order):
     b, a = _filter(order)
-    w, R_meas, weight = _measured_reflectance(order, b, a)
-    R_exact, Y = _closed_form(w, b, a)
+    w, R_meas, weight = _measured_reflectance(order, b, a, scheme)
+    R_exact, Y = _closed_form(w, b, a, scheme)
     band = (weight > 1e-4) & (w > 0.02)                                  # where the pulse has energy (w < 0.72 rad / sample)
     assert band.sum() > 400
     err = np.max(np.abs(R_meas[band] - np.abs(R_exact[band])))
