@@ -192,8 +192,38 @@ static void test_geometry_and_voxelizer() {
   { GeometryHandler gp; gp.initialize(&idx[0], &v[0], (unsigned)idx.size(), (unsigned)v.size());   // pointer form: the last argument counts
     CHECK_EQ(gp.getNumberOfVertices(), 8u); CHECK_EQ(gp.getNumberOfTriangles(), 12u);                // floats (reference GeometryHandler.cpp:87-108)
     CHECK(gp.getBoundingBox() == nv::Vec3f(1.f, 1.f, 1.f));
-    std::vector<unsigned> bad(idx); bad[0] = 8; GeometryHandler gb;
-    CHECK_THROW(gb.initialize(&bad[0], &v[0], (unsigned)bad.size(), (unsigned)v.size()), std::out_of_range); }
+    std::vector<unsigned> bad(idx); bad[0] = 8; GeometryHandler gb;                                  // index values are checked where used
+    gb.initialize(&bad[0], &v[0], (unsigned)bad.size(), (unsigned)v.size());
+    CHECK_THROW(gb.getSurfaceAreaAt(0), std::out_of_range); CHECK(std::fabs(gb.getSurfaceAreaAt(1) - 0.5f) < 1e-6f); }
+  { // GeometryHandlerTest.cpp:10-84 (constructor / pointer_initialize / getters): 33 floats, 33 indices
+    std::vector<float> vv; std::vector<unsigned> ii;
+    for (unsigned i = 0; i < 33; i++) { vv.push_back((float)(i * 10)); ii.push_back(i); }
+    GeometryHandler a; a.initialize(ii, vv);
+    GeometryHandler b; b.initialize(&ii[0], &vv[0], 33, 33);
+    for (GeometryHandler* gh : {&a, &b}) {
+      CHECK_EQ(gh->getNumberOfIndices(), 33u); CHECK_EQ(gh->getNumberOfTriangles(), 11u); CHECK_EQ(gh->getNumberOfVertices(), 11u);
+      unsigned int* t = gh->getTriangleAt(3); CHECK_EQ(*t, 9u); CHECK_EQ(*(t + 1), 10u);
+      float* f = gh->getVertexAt(3); CHECK_EQ(*f, 90.f);
+      // the bounding-box corner (0, 10, 20) is removed and kept as the geometry offset (GeometryHandler.cpp:63-75)
+      CHECK(gh->getGeometryOffset() == nv::Vec3f(0.f, 10.f, 20.f)); CHECK_EQ(f[1], 90.f); CHECK_EQ(f[2], 90.f);
+      CHECK(gh->getBoundingBox() == nv::Vec3f(300.f, 300.f, 300.f)); CHECK_EQ(gh->getNumberOfLongEdgeNodes(10.f), 30u);
+    }
+    a.setVertexAt(0, 1.f, 2.f, 3.f); CHECK_EQ(a.getVertexAt(0)[2], 3.f);
+    a.setVertexAt(1, 1.f, 0.f, 5.f); a.rotateGeometryAzimuth(90.f);
+    CHECK(std::fabs(a.getVertexAt(1)[0]) < 1e-6f && std::fabs(a.getVertexAt(1)[1] - 1.f) < 1e-6f && a.getVertexAt(1)[2] == 5.f); }
+  { // a box away from the origin voxelises like the same box at the origin
+    std::vector<float> vs(v); for (size_t i = 0; i < vs.size(); i += 3) { vs[i] += 4.f; vs[i + 1] -= 2.5f; vs[i + 2] += 0.25f; }
+    GeometryHandler gs; gs.initialize(idx, vs);
+    CHECK(gs.getGeometryOffset() == nv::Vec3f(4.f, -2.5f, 0.25f)); CHECK(std::fabs(gs.getTotalSurfaceArea() - 6.f) < 1e-5f);
+    pfdtd_host::VoxelVolumes v0 = pfdtd_host::voxelize(g, 0.1f, 0), v1 = pfdtd_host::voxelize(gs, 0.1f, 0);
+    CHECK_EQ(v0.vx, v1.vx); CHECK_EQ(v0.vz, v1.vz); CHECK(v0.bid == v1.bid); }
+  { // GeometryHandler_insertLauyers (:103-147)
+    GeometryHandler gl; gl.setLayerIndices(std::vector<int>(10, 0), "Layer0"); CHECK_EQ(gl.getNumberOfLayers(), 0u);
+    gl.initialize(idx, v);
+    std::vector<int> li(10, 0); li[0] = -10; li[2] = 10; gl.setLayerIndices(li, "Layer0"); CHECK_EQ(gl.getNumberOfLayers(), 0u);
+    std::vector<int> h0, h1; for (int i = 0; i < 6; i++) { h0.push_back(i); h1.push_back(i + 6); }
+    gl.setLayerIndices(h0, "Layer0"); gl.setLayerIndices(h1, "Layer1"); CHECK_EQ(gl.getNumberOfLayers(), 2u);
+    CHECK(gl.getLayerNameAt(3) == ""); CHECK(gl.getLayerNameAt(0) == "Layer0"); CHECK(gl.getLayerNameAt(1) == "Layer1"); }
   const float dx = 0.1f;
   pfdtd_host::VoxelVolumes vol = pfdtd_host::voxelize(g, dx, 0);
   CHECK_EQ(vol.vx, 13u);

@@ -57,8 +57,8 @@ inline VoxelVolumes voxelize(const GeometryHandler& g, float dx, const unsigned 
           const float py = ((float)j - 1.f) * dx + sy * eps, pz = ((float)k - 1.f) * dx + sz * 2 * eps;
           hits.clear();
           for (unsigned int t = 0; t < nt; t++) {
-            nv::Vec3ui tr = g.getTriangleAt(t);
-            nv::Vec3f a = g.getVertexAt(tr.x), b = g.getVertexAt(tr.y), c = g.getVertexAt(tr.z);
+            nv::Vec3ui tr = g.triangle(t);
+            nv::Vec3f a = g.vertex(tr.x), b = g.vertex(tr.y), c = g.vertex(tr.z);
             // barycentric test of (py,pz) in the triangle projected on the yz plane
             const float d = (b.y - a.y) * (c.z - a.z) - (c.y - a.y) * (b.z - a.z);
             if (std::fabs(d) < 1e-20f) continue;
@@ -95,8 +95,8 @@ inline VoxelVolumes voxelize(const GeometryHandler& g, float dx, const unsigned 
   if (tri_material && nt) {
     std::vector<nv::Vec3f> cen(nt);
     for (unsigned int t = 0; t < nt; t++) {
-      nv::Vec3ui tr = g.getTriangleAt(t);
-      cen[t] = (g.getVertexAt(tr.x) + g.getVertexAt(tr.y) + g.getVertexAt(tr.z)) * (1.f / 3.f);
+      nv::Vec3ui tr = g.triangle(t);
+      cen[t] = (g.vertex(tr.x) + g.vertex(tr.y) + g.vertex(tr.z)) * (1.f / 3.f);
     }
     for (unsigned int k = 0; k < v.vz; k++) for (unsigned int j = 0; j < v.vy; j++) for (unsigned int i = 0; i < v.vx; i++) {
       const size_t e = ((size_t)k * v.vy + j) * v.vx + i;
