@@ -120,6 +120,27 @@ class CudaMesh {
   template <typename T> T getSampleAt(unsigned int x, unsigned int y, unsigned int z, unsigned int partition) {
     double v = 0; pfdtd_safe(pfdtd_get_sample_at(solver_, x, y, z, partition, &v), "CudaMesh::getSampleAt"); return (T)v; }
 
+  // position byte of a voxel, from the first partition containing z (reference cudaMesh.h:591-596)
+  unsigned char getPositionSample(unsigned int x, unsigned int y, unsigned int z) {
+    int part = -1, el = -1; getElementIdxAndDevice(x, y, z, &part, &el);
+    if (part < 0) throw std::out_of_range("CudaMesh::getPositionSample: z outside every partition");
+    unsigned char v = 0;
+    pfdtd_safe(pfdtd_device_download((int)getDeviceAt(part), &v, getPositionIdxPtrAt((unsigned int)part) + el, 1), "CudaMesh::getPositionSample");
+    return v;
+  }
+  // device of the LAST partition holding slice z (reference cudaMesh.h:268-278), -1 if none
+  int getDeviceOfElement(unsigned int, unsigned int, unsigned int z) {
+    int ret = -1;
+    const unsigned int n = getNumberOfPartitions();
+    for (unsigned int i = 0; i < n; i++) {
+      unsigned int f, sz, d; part(i, &f, &sz, &d);
+      if (z > f + sz - 1) continue;
+      if (z < f) break;
+      ret = (int)d;
+    }
+    return ret;
+  }
+
   // ---- slices (reference cudaMesh.h:600-646 getSlice / getPositionSlice; malloc'ed, caller frees, orientation 0
   // only as in the reference -- the other orientations go through captureSlice)
   template <typename T> T* getSlice(unsigned int slice, unsigned int orientation) {

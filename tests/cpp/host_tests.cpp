@@ -350,6 +350,9 @@ static void test_cuda_mesh_gpu() {
     mesh.addSample<float>(3.f, 10, 10, 10); CHECK_EQ(mesh.getSample<float>(10, 10, 10), 8.f);
     mesh.setSampleAt<float>(7.f, 5, 5, 23, 0); mesh.setSampleAt<float>(9.f, 5, 5, 1, 1);
     mesh.setSampleAt<float>(0.f, 5, 5, 0, 1); mesh.setSampleAt<float>(0.f, 5, 5, 24, 0);
+    CHECK_EQ(mesh.getDeviceOfElement(1, 1, 10), 0); CHECK_EQ(mesh.getDeviceOfElement(1, 1, 48), 0); CHECK_EQ(mesh.getDeviceOfElement(1, 1, 60), -1);
+    CHECK_EQ((int)mesh.getPositionSample(10, 10, 10), 0);   // an all-solid volume: every position byte is 0
+    CHECK_THROW(mesh.getPositionSample(10, 10, 200), std::out_of_range);
     mesh.switchHalos();                             // slab0[23] -> slab1[0], slab1[1] -> slab0[24]
     CHECK_EQ(mesh.getSampleAt<float>(5, 5, 0, 1), 7.f); CHECK_EQ(mesh.getSampleAt<float>(5, 5, 24, 0), 9.f);
   }
