@@ -122,3 +122,38 @@ def test_synth_slab_generation_is_consistent():
     hi, hm = synth.hall(dims, 5, 13, 30)
     assert np.array_equal(lo, full[:17]) and np.array_equal(hi, full[13:])
     assert np.array_equal(lm, fm[:17]) and np.array_equal(hm, fm[13:])
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/pfdtd.h is a C header (C99, no C++ types) and a C program can link against libpfdtd_b200.so and call the
+    host-only entry points -- the shape of a cgo / JNI / MATLAB loadlibrary binding."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "pfdtd.h")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = tmp_path / "use.c"
+    src.write_text('''
+#include <stdio.h>
+#include "pfdtd.h"
+int main(void) {
+  uint32_t first[5], size[5];
+  if (pfdtd_partition_indexing(100u, 5u, first, size) != PFDTD_OK) return 1;
+  int n = -1;
+  int rc = pfdtd_device_count(&n);
+  pfdtd_solver* s = 0;
+  if (pfdtd_create(&s) != PFDTD_OK) return 2;
+  if (pfdtd_make_partition(s, 1u, 0) == PFDTD_OK) return 3;      /* no mesh yet: must fail with a message */
+  printf("%s|%u %u|%u %u|%d|%s\\n", pfdtd_version(), first[1], size[1], first[4], size[4], rc == PFDTD_OK ? n : 0, pfdtd_last_error());
+  return pfdtd_destroy(s);
+}
+''')
+    libdir = os.path.join(root, "parallelfdtd_b200")
+    exe = tmp_path / "use"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", libdir, "-l:libpfdtd_b200.so",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ver, p1, p4, ndev, err = r.stdout.strip().split("|")
+    assert "pfdtd-b200" in ver and p1 == "19 22" and p4 == "79 21" and "setup_mesh must be called" in err
