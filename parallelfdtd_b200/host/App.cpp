@@ -71,6 +71,23 @@ void App::initializeMesh(unsigned int number_of_partitions) {
   // frequency-dependent boundaries: the material rows are digital impedance filters of this order (0 = the
   // reference's scalar admittance per octave)
   m_mesh.setOption(PFDTD_OPT_DIF_ORDER, (long long)m_materials.getFilterOrder());
+  // capacity check before anything is allocated (reference App.cpp:148-174): estimated voxels x the bytes this build
+  // keeps per voxel (two fields + three node bytes; the reference counts 8 / 18) against the memory of all devices
+  {
+    const float dx = m_parameters.getDx();
+    const nv::Vec3f bb = m_geometry.getBoundingBox();
+    const double est = vol_bid_.empty() ? (double)(bb.x / dx + 3) * (double)(bb.y / dx + 3) * (double)(bb.z / dx + 3)
+                                        : (double)vol_dim_[0] * vol_dim_[1] * vol_dim_[2];
+    const double need_mb = est * (2.0 * (m_mesh.isDouble() ? 8 : 4) + 3.0) / 1e6;
+    double have_mb = 0;
+    for (size_t i = 0; i < device_mem_sizes_.size(); i++) have_mb += device_mem_sizes_[i];
+    log_msg<LOG_INFO>(L"App::initializeMesh - estimated size: %f voxels, dx %f, %f MB of %f MB") % est % dx % need_mb % have_mb;
+    if (!device_mem_sizes_.empty() && need_mb > have_mb) {
+      log_msg<LOG_ERROR>(L"App::initializeMesh - estimated size %f MB exceeds the devices' %f MB, exiting") % need_mb % have_mb;
+      close();
+      throw(-1);
+    }
+  }
   if (vol_bid_.empty()) {
     // triangle mesh -> node volumes on the device (reference App.cpp:181-190 voxelizeGeometry), adopted by setupMesh
     if (m_geometry.getNumberOfTriangles() == 0) { c_log_msg(LOG_ERROR, "App::initializeMesh - no geometry"); throw(-1); }
