@@ -226,3 +226,12 @@ def test_step_api_time_reversal(capi, gpu):
     s.close()
     assert np.abs(snap).max() > 0
     assert fc.rel_l2(back, snap) < 1e-4
+
+
+def test_shared_update_type_runs_the_forward_equations(capi, gpu):
+    """UpdateType SHARED (1): the reference's sliced kernel is numerically broken as written (unmasked position byte,
+    kernels3d.cu:559, SURVEY C-3); its equation is the forward one, so type 1 gives the responses of type 0."""
+    case = {c["name"]: c for c in fc.parity_cases()}["shoebox_48x40x49_fwd_f32_6mat_2parts"]
+    r0, _, _ = fc.run_ours(capi, case)
+    r1, _, info = fc.run_ours(capi, dict(case, update_type=1))
+    assert "forward" in info["kernel"] and np.abs(r0).max() > 0 and np.array_equal(r0, r1)
