@@ -36,3 +36,24 @@ def test_product_arm_refuses_to_run_without_a_device(capi):
         return
     r = subprocess.run([sys.executable, BENCH, "--workload", "c1", "--steps", "5"], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
+
+
+def test_bench_helpers():
+    """host-side pieces of bench.py: receiver placement, the roofline denominator and the committed ncu traffic table"""
+    sys.path.insert(0, ROOT)
+    import bench
+    for dims in [(512, 512, 512), (512, 512, 4096), (64, 64, 64)]:
+        rec = bench.receiver_positions(dims)
+        cx, cy, cz = dims[0] // 2, dims[1] // 2, dims[2] // 2
+        assert len(rec) == 4 and all(0 < x < dims[0] - 1 and 0 < y < dims[1] - 1 and 0 < z < dims[2] - 1 for x, y, z in rec)
+        near = rec[0]
+        assert abs(near[0] - cx) + abs(near[1] - cy) + abs(near[2] - cz) < 30          # reached within the warm-up at any height
+        assert len({r[2] for r in rec}) == 4                                             # spread over the height
+    peak, src = bench.measured_peak()
+    assert 3000 < peak < 9000 and ("measured" in src or "fallback" in src)
+    for dtype, dif in [("f32", 2), ("f64", 2), ("f32", 0), ("f64", 0)]:
+        t = bench.ncu_traffic("c2", dtype, 0, dif)
+        algo = 133693440 * bench.ALGO_BYTES[dtype]
+        assert t is not None and 0.95 * algo < t < 1.06 * algo                          # the kernels move the algorithmic bytes
+    assert bench.ncu_traffic("c2", "f32", 2, 3) is None
+    assert bench.ALGO_BYTES == {"f32": 13, "f64": 25}
