@@ -157,3 +157,10 @@ int main(void) {
     assert r.returncode == 0, r.stdout + r.stderr
     ver, p1, p4, ndev, err = r.stdout.strip().split("|")
     assert "pfdtd-b200" in ver and p1 == "19 22" and p4 == "79 21" and "setup_mesh must be called" in err
+
+
+def test_every_entry_point_is_documented_in_integration_md(capi):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = [s for s in capi.declared_symbols() if s not in txt]
+    assert not missing, missing
