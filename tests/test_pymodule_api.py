@@ -68,3 +68,13 @@ def test_filter_materials_through_the_module(pf):
     other.setUniformFilter([0.1, 0.02, 0.01], [-0.5, 0.1])
     with pytest.raises(IndexError):
         pf.App().setUniformFilter([0.1, 0.02, 0.01], [-0.5])
+
+
+def test_example_workflow_fails_loudly_without_a_device(pf, capi, tmp_path):
+    """examples/test_bench.py (the reference's python/testBench.py workflow) has no CPU path either"""
+    import subprocess
+    if capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "test_bench.py"), "--steps", "10"], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode != 0 and "ParallelFDTD error" in r.stderr
