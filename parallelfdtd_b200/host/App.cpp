@@ -50,6 +50,13 @@ void App::initializeDevices() {
   if (number_of_devices_ < 1) { c_log_msg(LOG_ERROR, "App::initializeDevices - no CUDA device"); throw(-1); }
 }
 
+void App::initializeGeometryFromFile(std::string geometry_fp) {
+  if (!m_file_reader.readVTK(&m_geometry, geometry_fp)) {
+    log_msg<LOG_ERROR>(L"App::initializeGeometryFromFile - invalid file: %s") % geometry_fp;
+    throw(-1);
+  }
+}
+
 void App::initializeGeometry(unsigned int* indices, float* vertices, unsigned int number_of_indices, unsigned int number_of_vertices) {
   m_geometry.initialize(indices, vertices, number_of_indices, number_of_vertices);
   nv::Vec3f bb = m_geometry.getBoundingBox();

@@ -1,6 +1,6 @@
 // App.h -- `FDTD::App`, the facade the MEX gateway, the Python module and main() drive (reference
 // src/App.h:50-396).  Same public methods for everything on or next to the time-stepping path; the
-// OpenGL window / VTK reader / Voxelizer members are not part of this build.
+// OpenGL window / Voxelizer members are not part of this build.
 // Geometry reaches the solver either as voxelizer-style node volumes (setVoxelVolumes, what the
 // reference obtains from the third-party Voxelizer) or, for axis-aligned rooms, through the
 // built-in box voxelizer of initializeMesh.
@@ -11,6 +11,7 @@
 #include "base/MaterialHandler.h"
 #include "base/SimulationParameters.h"
 #include "global_includes.h"
+#include "io/FileReader.h"
 #include "kernels/cudaMesh.h"
 
 typedef bool (*InterruptCallback)(void);
@@ -27,12 +28,15 @@ class App {
   GeometryHandler m_geometry;
   MaterialHandler m_materials;
   CudaMesh m_mesh;
+  FileReader m_file_reader;
   InterruptCallback m_interrupt;
   ProgressCallback m_progress;
 
   void queryDevices();
   void resetDevices();
   void initializeDevices();
+  // VTK POLYDATA in inches (reference App.cpp:133-139, FileReader.cpp:41-101); throws -1 on an unreadable file
+  void initializeGeometryFromFile(std::string geometry_fp);
   void initializeGeometry(unsigned int* indices, float* vertices, unsigned int number_of_indices, unsigned int number_of_vertices);
   void setupDefaultCallbacks();
   void initializeMesh(unsigned int number_of_partitions);

@@ -2,8 +2,8 @@
 // boost::python module (reference src/AppPy.cpp:96-133), so scripts written against it
 // (reference python/testBench.py:110-149) keep running.  pybind11 instead of Boost.Python (Boost is
 // not part of this build); list arguments keep their flattened-list meaning
-// (reference src/AppPy.cpp:29-94).  Methods without a counterpart here (OpenGL viewer, VTK reader)
-// raise RuntimeError instead of silently doing nothing.
+// (reference src/AppPy.cpp:29-94).  The method without a counterpart here (the OpenGL viewer) raises RuntimeError
+// instead of silently doing nothing.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -96,9 +96,7 @@ PYBIND11_MODULE(libPyFDTD, m) {
         return a;
       }))
       .def("initializeDevices", [](FDTD::App& a) { guarded([&] { a.initializeDevices(); }); })
-      .def("initializeGeometryFromFile", [](FDTD::App&, const std::string&) {
-        throw std::runtime_error("initializeGeometryFromFile: the VTK reader is not part of this build; pass the mesh with initializeGeometryPy");
-      })
+      .def("initializeGeometryFromFile", [](FDTD::App& a, const std::string& fp) { guarded([&] { a.initializeGeometryFromFile(fp); }); })
       .def("initializeGeometryPy", &initializeGeometryPy)
       .def("setLayerIndices", [](FDTD::App& a, const std::vector<int>& idx, const std::string& name) { a.m_geometry.setLayerIndices(idx, name); })
       .def("addSource", &FDTD::App::addSource)

@@ -13,6 +13,7 @@
 #include "App.h"
 #include "kernels/kernels3d.h"
 #include "voxelize_ref.h"
+#include <fstream>
 
 static int g_fail = 0, g_checks = 0;
 #define CHECK(c) do { g_checks++; if (!(c)) { g_fail++; std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c); } } while (0)
@@ -158,6 +159,33 @@ static void test_device_helpers_without_a_device() {
   CHECK_THROW(valueToDevice<unsigned char>(8, (unsigned char)1, 0), int);
   CHECK_THROW(toDevice<float>(8, 0), int);
   CHECK_THROW(getCurrentDevice(), int);
+}
+
+static void box_mesh(float lx, float ly, float lz, std::vector<unsigned>& idx, std::vector<float>& v);
+// ---- FileReaderTest.cpp / GeometryHandlerTest.cpp:80-92 (the VTK fixture is not in the reference tree: written here) ------------
+static void test_file_reader() {
+  std::vector<unsigned> idx; std::vector<float> v; box_mesh(1.f, 1.f, 1.f, idx, v);
+  { std::ofstream f("box1m.vtk");
+    f << "# vtk DataFile Version 3.0\nvtk output\nASCII\nDATASET POLYDATA\nPOINTS 8 float\n";
+    for (size_t i = 0; i < v.size(); i += 3) f << v[i] / 0.0254f << " " << v[i + 1] / 0.0254f << " " << v[i + 2] / 0.0254f << "\n";   // inches
+    f << "POLYGONS 12 48\n";
+    for (size_t i = 0; i < idx.size(); i += 3) f << "3 " << idx[i] << " " << idx[i + 1] << " " << idx[i + 2] << "\n"; }
+  FileReader fr; GeometryHandler gh;
+  CHECK(fr.readVTK(&gh, "box1m.vtk", 0.1f));
+  CHECK_EQ(gh.getNumberOfTriangles(), 12u); CHECK_EQ(gh.getNumberOfVertices(), 8u); CHECK_EQ(fr.counter, 24 + 36);
+  CHECK_EQ(gh.getTotalSurfaceArea(), 6.f); CHECK_EQ(gh.getSurfaceAreaAt(0), 0.5f);          // 1 m box: 6 m^2 (GeometryHandlerTest.cpp:88-91)
+  CHECK(gh.getBoundingBox() == nv::Vec3f(1.f, 1.f, 1.f));
+  GeometryHandler none; CHECK(!fr.readVTK(&none, "no_such_file.vtk")); CHECK_EQ(none.getNumberOfTriangles(), 0u);
+  { std::ofstream f("quad.vtk"); f << "DATASET POLYDATA\nPOINTS 4 float\n0 0 0 1 0 0 1 1 0 0 1 0\nPOLYGONS 1 5\n4 0 1 2 3\n"; }
+  CHECK(!fr.readVTK(&none, "quad.vtk"));
+  { std::ofstream f("badidx.vtk"); f << "DATASET POLYDATA\nPOINTS 3 float\n0 0 0 1 0 0 1 1 0\nPOLYGONS 1 4\n3 0 1 7\n"; }
+  CHECK(!fr.readVTK(&none, "badidx.vtk"));
+  { std::ofstream f("ir.txt"); f << "0\n0 -0.333333343\n 0.5\n"; }
+  std::vector<float> ir = fr.readFloat("ir.txt");
+  CHECK_EQ(ir.size(), (size_t)4); CHECK_EQ(ir[2], -0.333333343f); CHECK(fr.readFloat("no_such_file.txt").empty());
+  SimulationParameters sp; sp.readGridIr("ir.txt"); CHECK_EQ(sp.getGridIrDataSample(2), -0.333333343f);
+  FDTD::App app; CHECK_THROW(app.initializeGeometryFromFile("no_such_file.vtk"), int);
+  app.initializeGeometryFromFile("box1m.vtk"); CHECK_EQ(app.m_geometry.getNumberOfTriangles(), 12u);
 }
 
 static void test_partition_indexing() {
@@ -400,7 +428,7 @@ static void test_cuda_mesh_gpu() {
 
 int main(int argc, char** argv) {
   const std::string what = argc > 1 ? argv[1] : "cpu";
-  if (what == "cpu") { test_simulation_parameters(); test_srcrec(); test_material_handler(); test_device_helpers_without_a_device(); test_partition_indexing(); test_geometry_and_voxelizer(); }
+  if (what == "cpu") { test_simulation_parameters(); test_srcrec(); test_material_handler(); test_device_helpers_without_a_device(); test_file_reader(); test_partition_indexing(); test_geometry_and_voxelizer(); }
   else if (what == "gpu") { test_cuda_mesh_gpu(); test_voxelizer_gpu(); }
   std::printf("%s: %d checks, %d failures\n", what.c_str(), g_checks, g_fail);
   return g_fail ? 1 : 0;

@@ -51,7 +51,26 @@ def test_host_side_setters_work_without_a_device(pf, capi):
         with pytest.raises(RuntimeError):
             app.runSimulation()
     with pytest.raises(RuntimeError):
-        app.initializeGeometryFromFile("x.vtk")
+        app.initializeGeometryFromFile("x.vtk")                # unreadable file
+
+
+def test_geometry_from_a_vtk_file(pf, tmp_path):
+    """initializeGeometryFromFile: legacy ASCII VTK POLYDATA in inches (reference FileReader.cpp:41-101)"""
+    inch = 1.0 / 0.0254
+    pts = [(0, 0, 0), (2, 0, 0), (2, 1, 0), (0, 1, 0), (0, 0, 1.5), (2, 0, 1.5), (2, 1, 1.5), (0, 1, 1.5)]
+    quads = [(0, 3, 2, 1), (4, 5, 6, 7), (0, 1, 5, 4), (2, 3, 7, 6), (1, 2, 6, 5), (3, 0, 4, 7)]
+    tris = [t for a, b, c, d in quads for t in ((a, b, c), (a, c, d))]
+    p = tmp_path / "room.vtk"
+    p.write_text("# vtk DataFile Version 3.0\nroom\nASCII\nDATASET POLYDATA\nPOINTS 8 float\n"
+                 + "".join(f"{x * inch} {y * inch} {z * inch}\n" for x, y, z in pts)
+                 + f"POLYGONS {len(tris)} {4 * len(tris)}\n" + "".join(f"3 {a} {b} {c}\n" for a, b, c in tris))
+    app = pf.App()
+    app.initializeGeometryFromFile(str(p))
+    app.setLayerIndices(list(range(len(tris))), "all")          # accepted: the file gave 12 triangles
+    app.setUniformMaterial(0.9)
+    (tmp_path / "quad.vtk").write_text("DATASET POLYDATA\nPOINTS 4 float\n0 0 0 1 0 0 1 1 0 0 1 0\nPOLYGONS 1 5\n4 0 1 2 3\n")
+    with pytest.raises(RuntimeError):
+        pf.App().initializeGeometryFromFile(str(tmp_path / "quad.vtk"))
 
 
 def test_filter_materials_through_the_module(pf):
