@@ -57,3 +57,32 @@ def test_bench_helpers():
         assert t is not None and 0.95 * algo < t < 1.06 * algo                          # the kernels move the algorithmic bytes
     assert bench.ncu_traffic("c2", "f32", 2, 3) is None
     assert bench.ALGO_BYTES == {"f32": 13, "f64": 25}
+
+
+def test_committed_bench_lines_are_well_formed():
+    """profiles/r01_bench_*.json: the lines the measurements in profiles/README.md come from carry every contract key,
+    a consistent roofline fraction and no slowdown reason."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_*.json")))
+    assert len(files) >= 10
+    for f in files:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "e2e", "gpu_launches"):
+            assert k in d, (f, k)
+        if os.path.basename(f) == "r01_bench_f32_dif2_512.json":           # the headline line: default invocation, nothing switched off
+            cb = d["cpu_baseline"]
+            assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+            assert d["roofline"]["traffic"] and len(d["variants"]) >= 6
+        assert d["metric"] == "Mvox-updates/s" and d["unit"] == "Mvox/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+        assert "workload" in d["config"] and "model" not in d["config"]
+        assert d["value"] > 0 and d["steps"] >= 1
+        if d.get("impl") == "reference":
+            assert d["cpu_baseline"]["kind"] in ("reference", "port")
+            continue
+        assert d["warmup"] >= 3 and d["gpu_launches"] > 0
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert d["e2e"] is None or {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+        assert not bad, (f, bad)
