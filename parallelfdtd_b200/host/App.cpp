@@ -126,7 +126,8 @@ void App::initializeMesh(unsigned int number_of_partitions) {
   // as needed (bounded by the device count).  forcePartitionTo keeps its meaning.
   unsigned int n = 1;
   const double bytes = (double)m_mesh.getNumberOfElements64() * (2.0 * (m_mesh.isDouble() ? 8 : 4) + 3.0);
-  if (force_partition_to_ != -1 && force_partition_to_ <= number_of_devices_) n = (unsigned int)force_partition_to_;
+  // a request of 0 partitions (the reference would call makePartition(0)) means "choose", like -1
+  if (force_partition_to_ > 0 && force_partition_to_ <= number_of_devices_) n = (unsigned int)force_partition_to_;
   else {
     const double cap = device_mem_sizes_.empty() ? 150e9 : 0.9 * 1e6 * (double)device_mem_sizes_[0];
     while (n < (unsigned int)number_of_devices_ && n < number_of_partitions * 4 && bytes / n > cap) n++;
