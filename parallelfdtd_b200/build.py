@@ -97,6 +97,27 @@ def build_mex_tests(force: bool = False) -> str:
     return MEX_TEST_BIN
 
 
+MEX_HELPERS = ["mem_check", "device_reset"]
+
+
+def mex_helper_path(name: str) -> str:
+    return os.path.normpath(os.path.join(HERE, "..", "tests", "cpp", f"mex_{name}.so"))
+
+
+def build_mex_helpers(force: bool = False):
+    """matlab/runFDTD.m's two helper MEX functions (host/mem_check.cpp, host/device_reset.cpp) against the stand-in mex.h,
+    as shared objects the tests call through ctypes."""
+    build_lib()
+    out = []
+    for name in MEX_HELPERS:
+        src, dst = os.path.join(HOST_DIR, name + ".cpp"), mex_helper_path(name)
+        if force or _newer(src, dst) or _newer(os.path.join(MEX_STUB_DIR, "mex.h"), dst):
+            subprocess.check_call([_host_cxx(), "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-I", MEX_STUB_DIR, "-o", dst, src,
+                                   "-L", HERE, "-l:libpfdtd_b200.so", "-Wl,-rpath," + HERE])
+        out.append(dst)
+    return out
+
+
 PY_MODULE_SRC = os.path.join(HOST_DIR, "AppPy.cpp")
 
 
@@ -126,3 +147,4 @@ if __name__ == "__main__":
     print(build_host(force="--force" in sys.argv))
     print(build_py_module(force="--force" in sys.argv))
     print(build_mex_tests(force="--force" in sys.argv))
+    print(build_mex_helpers(force="--force" in sys.argv))

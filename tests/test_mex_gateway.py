@@ -32,3 +32,24 @@ def test_mex_gateway_cpu(tmp_path):
 def test_mex_gateway_gpu(tmp_path, gpu):
     r = subprocess.run([_bin(), "gpu"], cwd=tmp_path, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "0 failures" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_runfdtd_helper_mex_functions():
+    """mem_check / device_reset (matlab/runFDTD.m:19,42) through the stand-in MEX API, called via ctypes"""
+    import ctypes as C
+    from parallelfdtd_b200 import build, capi
+
+    class MxArray(C.Structure):
+        _fields_ = [("cls", C.c_int), ("m", C.c_size_t), ("n", C.c_size_t), ("data", C.c_void_p)]
+
+    mem_so, reset_so = build.build_mex_helpers()
+    plhs = (C.POINTER(MxArray) * 1)()
+    L = C.CDLL(mem_so)
+    L.mexFunction(C.c_int(1), plhs, C.c_int(0), None)
+    out = plhs[0].contents
+    ndev = capi.device_count()
+    assert out.cls == 6 and out.n == 1 and out.m == ndev                      # mxDOUBLE_CLASS column, one entry per device
+    if ndev:
+        mem = (C.c_double * ndev).from_address(out.data)
+        assert all(v > 1e9 for v in mem)
+    C.CDLL(reset_so).mexFunction(C.c_int(0), None, C.c_int(0), None)
