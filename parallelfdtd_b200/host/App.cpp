@@ -3,6 +3,7 @@
 // launchFDTD3d[Double], executeStep (:407-436) -> launchFDTD3dStep + captures.
 #include "App.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -121,19 +122,43 @@ void App::initializeMesh(unsigned int number_of_partitions) {
                            m_parameters.getParameterPtr(), dim, block, type);
   }
   num_elements_ = m_mesh.getNumberOfElements();
-  // Partition count.  The reference splits in two above 90e6 (45e6 double) voxels because of Kepler-era memory
-  // (App.cpp:217-233); here one partition is used whenever the mesh fits the device, otherwise as many slabs
-  // as needed (bounded by the device count).  forcePartitionTo keeps its meaning.
+  // Partition count (reference App.cpp:217-233: one partition below 90e6 voxels -- 45e6 in double --, otherwise
+  // `number_of_partitions`, sized for Kepler-era memory).  Same shape with B200 numbers: one partition while a
+  // slab would be smaller than 2^28 voxels (a one-plane halo costs < 0.5 % of a slab that size and the interior
+  // launch hides it), then one more device per 2^28 voxels up to the devices present, and never fewer than the
+  // memory needs.  forcePartitionTo keeps its meaning; 0 (the reference would call makePartition(0)) means "choose".
   unsigned int n = 1;
-  const double bytes = (double)m_mesh.getNumberOfElements64() * (2.0 * (m_mesh.isDouble() ? 8 : 4) + 3.0);
-  // a request of 0 partitions (the reference would call makePartition(0)) means "choose", like -1
+  const double elements = (double)m_mesh.getNumberOfElements64();
+  const double bytes = elements * (2.0 * (m_mesh.isDouble() ? 8 : 4) + 3.0);
   if (force_partition_to_ > 0 && force_partition_to_ <= number_of_devices_) n = (unsigned int)force_partition_to_;
   else {
+    const double element_limit = m_mesh.isDouble() ? 134217728.0 : 268435456.0;
     const double cap = device_mem_sizes_.empty() ? 150e9 : 0.9 * 1e6 * (double)device_mem_sizes_[0];
-    while (n < (unsigned int)number_of_devices_ && n < number_of_partitions * 4 && bytes / n > cap) n++;
+    const unsigned int max_n = (unsigned int)std::max(1, number_of_devices_);
+    while (n < max_n && (elements / n >= 2 * element_limit || bytes / n > cap)) n++;
+    (void)number_of_partitions;
   }
   m_mesh.makePartition(n);
   current_step_ = 0;
+}
+
+void App::runVisualization() {
+  m_mesh.setDouble(false);                                        // reference App.cpp:285-289
+  m_parameters.setNumSteps(m_parameters.getSpatialFs() * 2);
+  force_partition_to_ = 1;
+  initializeMesh(1);
+  const unsigned int steps = m_parameters.getNumSteps();
+  responses_.assign((size_t)steps * m_parameters.getNumReceivers() + 1, 0.f);
+  log_msg<LOG_INFO>(L"App::runVisualization - Volume: %f") % getVolume();
+  log_msg<LOG_INFO>(L"App::runVisualization - TotalAbsorptionArea: %f, octave: %u") % getTotalAborptionArea(0) % m_parameters.getOctave();
+  log_msg<LOG_INFO>(L"App::runVisualization - Sabine RT: %f") % getSabine(0);
+  log_msg<LOG_INFO>(L"App::runVisualization - Eyrting RT: %f") % getEyring(0);
+  log_msg<LOG_WARNING>(L"App::runVisualization - no OpenGL window in this build, stepping headless for %u steps") % steps;
+  for (unsigned int i = 0; i < steps; i++) {
+    executeStep();
+    if (m_interrupt && m_interrupt()) break;
+  }
+  responses_.resize((size_t)steps * m_parameters.getNumReceivers());
 }
 
 void App::runSimulation() {

@@ -44,6 +44,10 @@ class App {
   // voxelizer-style volumes [vz][vy][vx]: `bid` 0..27 and material index per voxel
   void setVoxelVolumes(const unsigned char* bid, const unsigned char* mat, unsigned int vx, unsigned int vy, unsigned int vz);
 
+  // The reference opens its OpenGL viewer here and steps the solver from the window's idle callback (App.cpp:278-306).
+  // This build has no window: same preparation (single precision, one partition, 2 x fs steps), then the steps run
+  // headless through executeStep so the captures and responses a viewer session would produce are still there.
+  void runVisualization();
   void runSimulation();
   void runCapture();
   void close();

@@ -2,8 +2,7 @@
 // boost::python module (reference src/AppPy.cpp:96-133), so scripts written against it
 // (reference python/testBench.py:110-149) keep running.  pybind11 instead of Boost.Python (Boost is
 // not part of this build); list arguments keep their flattened-list meaning
-// (reference src/AppPy.cpp:29-94).  The method without a counterpart here (the OpenGL viewer) raises RuntimeError
-// instead of silently doing nothing.
+// (reference src/AppPy.cpp:29-94).  The method without a counterpart here (the OpenGL viewer) runs its session headless.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -32,6 +31,18 @@ auto guarded(F&& f) -> decltype(f()) {
 bool py_interrupt(void) {
   py::gil_scoped_acquire gil;
   return PyErr_CheckSignals() != 0;
+}
+
+// A run with the GIL released.  An interrupted run returns normally from App (pfdtd_run's INTERRUPTED is not an
+// error there), but the KeyboardInterrupt that PyErr_CheckSignals raised is still pending: hand it to the caller
+// instead of returning with an exception set.
+template <class F>
+void run_released(F&& f) {
+  {
+    py::gil_scoped_release nogil;
+    guarded(f);
+  }
+  if (PyErr_Occurred()) throw py::error_already_set();
 }
 
 void initializeGeometryPy(FDTD::App& a, const std::vector<unsigned int>& indices, const std::vector<float>& vertices) {
@@ -111,9 +122,9 @@ PYBIND11_MODULE(libPyFDTD, m) {
       .def("setUpdateType", &FDTD::App::setUpdateType)
       .def("setUniform", &FDTD::App::setUniformMaterial)
       .def("setUniformMaterial", &FDTD::App::setUniformMaterial)
-      .def("runVisualization", [](FDTD::App&) { throw std::runtime_error("runVisualization: the OpenGL viewer is not part of this build; use runCapture"); })
-      .def("runSimulation", [](FDTD::App& a) { py::gil_scoped_release nogil; guarded([&] { a.runSimulation(); }); })
-      .def("runCapture", [](FDTD::App& a) { py::gil_scoped_release nogil; guarded([&] { a.runCapture(); }); })
+      .def("runVisualization", [](FDTD::App& a) { run_released([&] { a.runVisualization(); }); })   // headless: no OpenGL window here
+      .def("runSimulation", [](FDTD::App& a) { run_released([&] { a.runSimulation(); }); })
+      .def("runCapture", [](FDTD::App& a) { run_released([&] { a.runCapture(); }); })
       .def("getResponse", &FDTD::App::getResponse)
       .def("getResponseDouble", &FDTD::App::getResponseDouble)
       .def("forcePartitionTo", &FDTD::App::setForcePartitionTo)

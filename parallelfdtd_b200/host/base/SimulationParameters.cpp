@@ -21,6 +21,7 @@ SimulationParameters::SimulationParameters()
 void SimulationParameters::readGridIr(std::string ir_fp) {
   std::ifstream in(ir_fp.c_str());
   grid_ir_.clear();
+  ++generation_;
   if (!in) {
     log_msg<LOG_ERROR>(L"SimulationParameters::readGridIr - cannot open %s") % ir_fp;
     return;
@@ -34,6 +35,7 @@ void SimulationParameters::readGridIr(std::string ir_fp) {
 // Interpolated schemes run at their own stability limits.
 void SimulationParameters::setUpdateType(enum UpdateType update_type) {
   update_type_ = update_type;
+  ++generation_;
   switch (update_type) {
     case SRL_FORWARD:
     case SHARED:
@@ -46,8 +48,8 @@ void SimulationParameters::setUpdateType(enum UpdateType update_type) {
 // reference :362-364
 float SimulationParameters::getDx() const { return (float)((double)c_ / ((double)spatial_fs_ * lambda_)); }
 
-void SimulationParameters::addSource(float x, float y, float z) { sources_.push_back(Source(x, y, z)); }
-void SimulationParameters::addSource(Source src) { sources_.push_back(src); }
+void SimulationParameters::addSource(float x, float y, float z) { sources_.push_back(Source(x, y, z)); ++generation_; }
+void SimulationParameters::addSource(Source src) { sources_.push_back(src); ++generation_; }
 void SimulationParameters::addSourceDData(float* d_vector) {
   if (d_source_output_data_.size() < getNumSources()) d_source_output_data_.push_back(d_vector);
 }
@@ -55,21 +57,24 @@ void SimulationParameters::addSourceDData(float* d_vector) {
 void SimulationParameters::removeSource(unsigned int i) {
   if (i >= sources_.size()) throw std::out_of_range("SimulationParameters::removeSource: idx out of range");
   sources_.erase(sources_.begin() + i);
+  ++generation_;
 }
 void SimulationParameters::removeReceiver(unsigned int i) {
   if (i >= receivers_.size()) throw std::out_of_range("SimulationParameters::removeReceiver: idx out of range");
   receivers_.erase(receivers_.begin() + i);
+  ++generation_;
 }
-void SimulationParameters::updateSourceAt(unsigned int i, Source src) { sources_.at(i) = src; }
+void SimulationParameters::updateSourceAt(unsigned int i, Source src) { sources_.at(i) = src; ++generation_; }
 // the reference bounds-checks against the SOURCE list here (:62-66); .at() on the receiver list is what throws
-void SimulationParameters::updateReceiverAt(unsigned int i, Receiver rec) { receivers_.at(i) = rec; }
-void SimulationParameters::resetSourcesAndReceivers() { receivers_.clear(); sources_.clear(); }
+void SimulationParameters::updateReceiverAt(unsigned int i, Receiver rec) { receivers_.at(i) = rec; ++generation_; }
+void SimulationParameters::resetSourcesAndReceivers() { receivers_.clear(); sources_.clear(); ++generation_; }
 
 void SimulationParameters::addInputData(float* data, unsigned int number_of_samples) {
   std::vector<float> v(number_of_samples, 0.f);
   if (data) for (unsigned int i = 0; i < number_of_samples; i++) v[i] = data[i];
   else log_msg<LOG_WARNING>(L"SimulationParameters::addInputData : invalid input data (NULL)");
   source_input_data_.push_back(v);
+  ++generation_;
 }
 
 // reference :160-186: out-of-range data index throws (vector::at), sample index past the end reads 0

@@ -18,15 +18,15 @@ class SimulationParameters {
   ~SimulationParameters() {}
 
   void readGridIr(std::string ir_fp);
-  void setGridIr(const std::vector<float>& ir) { grid_ir_ = ir; }
+  void setGridIr(const std::vector<float>& ir) { grid_ir_ = ir; ++generation_; }
   void setUpdateType(enum UpdateType update_type);
-  void setC(float c) { c_ = c; }
-  void setLambda(double lambda) { lambda_ = lambda; }
-  void setOctave(unsigned int octave) { octave_ = octave; }
-  void setNumSteps(unsigned int num_steps) { num_steps_ = num_steps; }
-  void setSpatialFs(unsigned int spatial_fs) { spatial_fs_ = spatial_fs; }
-  void setBoundingBox(nv::Vec3f bb_min, nv::Vec3f bb_max) { bounding_box_min_ = bb_min; bounding_box_max_ = bb_max; }
-  void setAddPaddingToElementIdx(bool v) { add_padding_to_element_idx_ = v; }
+  void setC(float c) { c_ = c; ++generation_; }
+  void setLambda(double lambda) { lambda_ = lambda; ++generation_; }
+  void setOctave(unsigned int octave) { octave_ = octave; ++generation_; }
+  void setNumSteps(unsigned int num_steps) { num_steps_ = num_steps; ++generation_; }
+  void setSpatialFs(unsigned int spatial_fs) { spatial_fs_ = spatial_fs; ++generation_; }
+  void setBoundingBox(nv::Vec3f bb_min, nv::Vec3f bb_max) { bounding_box_min_ = bb_min; bounding_box_max_ = bb_max; ++generation_; }
+  void setAddPaddingToElementIdx(bool v) { add_padding_to_element_idx_ = v; ++generation_; }
 
   enum UpdateType getUpdateType() const { return update_type_; }
   float getC() const { return c_; }
@@ -39,8 +39,8 @@ class SimulationParameters {
 
   void addSource(float x, float y, float z);
   void addSource(Source src);
-  void addReceiver(float x, float y, float z) { receivers_.push_back(Receiver(x, y, z)); }
-  void addReceiver(Receiver rec) { receivers_.push_back(rec); }
+  void addReceiver(float x, float y, float z) { receivers_.push_back(Receiver(x, y, z)); ++generation_; }
+  void addReceiver(Receiver rec) { receivers_.push_back(rec); ++generation_; }
   void addSourceDData(float* d_vector);
   void removeSource(unsigned int i);
   void removeReceiver(unsigned int i);
@@ -49,8 +49,8 @@ class SimulationParameters {
   void resetSourcesAndReceivers();
 
   void addInputData(float* data, unsigned int number_of_samples);
-  void addInputData(std::vector<float> data) { source_input_data_.push_back(data); }
-  void addInputDataDouble(std::vector<double> data) { source_input_data_double_.push_back(data); }
+  void addInputData(std::vector<float> data) { source_input_data_.push_back(data); ++generation_; }
+  void addInputDataDouble(std::vector<double> data) { source_input_data_double_.push_back(data); ++generation_; }
 
   float getSourceSample(unsigned int source_idx, unsigned int step);
   double getSourceSampleDouble(unsigned int source_idx, unsigned int step);
@@ -78,6 +78,9 @@ class SimulationParameters {
   // reference's O(steps^2) per-step recomputation, with the same summation order per sample.
   void fillSourceTable(std::vector<float>& out, unsigned int num_steps);
   void fillSourceTableDouble(std::vector<double>& out, unsigned int num_steps);
+  // Bumped by every call that can change a source / receiver position, a source sample or the step count: what the
+  // step-by-step launcher (launchFDTD3dStep) compares to know that the tables it uploaded are still the right ones.
+  unsigned long long generation() const { return generation_; }
 
  private:
   float getRegularSourceSample(unsigned int source_idx, unsigned int step);
@@ -102,4 +105,5 @@ class SimulationParameters {
   std::vector<float> parameter_vec_;
   std::vector<double> parameter_vec_double_;
   std::vector<float> grid_ir_;
+  unsigned long long generation_ = 0;
 };

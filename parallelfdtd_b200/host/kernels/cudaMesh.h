@@ -57,9 +57,14 @@ class CudaMesh {
   }
   // reference cudaMesh.h:648-751
   void makePartition(unsigned int number_of_partitions, std::vector<unsigned int> device_list = std::vector<unsigned int>()) {
+    bound_params_ = 0;
     pfdtd_safe(pfdtd_make_partition(solver_, number_of_partitions, device_list.empty() ? 0 : &device_list[0]), "CudaMesh::makePartition");
   }
-  void destroyPartitions() { pfdtd_destroy(solver_); solver_ = 0; pfdtd_safe(pfdtd_create(&solver_), "CudaMesh::destroyPartitions"); }
+  void destroyPartitions() { pfdtd_destroy(solver_); solver_ = 0; bound_params_ = 0; pfdtd_safe(pfdtd_create(&solver_), "CudaMesh::destroyPartitions"); }
+  // Which (SimulationParameters, generation) the source / receiver tables inside the solver were built from
+  // (launchFDTD3dStep rebuilds them when either changes; the solver drops them on makePartition).
+  bool boundTo(const void* params, unsigned long long generation) const { return bound_params_ == params && bound_generation_ == generation; }
+  void setBound(const void* params, unsigned long long generation) { bound_params_ = params; bound_generation_ = generation; }
 
   // ---- getters (reference cudaMesh.h:184-244)
   unsigned int getNumberOfPartitions() { unsigned int n = 0; pfdtd_get_num_partitions(solver_, &n); return n; }
@@ -178,6 +183,8 @@ class CudaMesh {
   void ptrs(unsigned int k, void** p, void** pp, unsigned char** pos, unsigned char** mat) {
     pfdtd_safe(pfdtd_get_device_pointers(solver_, k, p, pp, pos, mat), "CudaMesh::devicePointers"); }
   pfdtd_solver* solver_;
+  const void* bound_params_ = 0;
+  unsigned long long bound_generation_ = 0;
   bool double_;
   uint3 block_;
 };

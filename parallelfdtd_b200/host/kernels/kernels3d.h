@@ -32,14 +32,16 @@ inline void bind_sources_receivers(CudaMesh* d_mesh, SimulationParameters* sp, b
   }
   pfdtd_safe(pfdtd_set_receivers(d_mesh->handle(), nr, nr ? &rxyz[0] : 0), "launchFDTD3d: receivers");
 }
-struct CallbackBridge {   // bool(*)(void) -> int(*)(void) without a capturing lambda
-  static bool (*&interrupt())(void) { static bool (*f)(void) = 0; return f; }
+struct CallbackBridge {   // bool(*)(void) -> int(*)(void) without a capturing lambda; per calling thread (pfdtd_run calls
+                          // back on the thread that called it), so Apps running on different threads do not share it
+  static bool (*&interrupt())(void) { static thread_local bool (*f)(void) = 0; return f; }
   static int call() { return interrupt()() ? 1 : 0; }
 };
 inline float run(CudaMesh* d_mesh, SimulationParameters* sp, void* h_return_ptr, bool dbl, bool (*interruptCallback)(void),
                  void (*progressCallback)(int, int, float)) {
   const unsigned int steps = sp->getNumSteps();
   bind_sources_receivers(d_mesh, sp, dbl, steps);
+  d_mesh->setBound(sp, sp->generation());
   CallbackBridge::interrupt() = interruptCallback;
   float sps = 0.f;
   int rc = pfdtd_run(d_mesh->handle(), steps, h_return_ptr, interruptCallback ? &CallbackBridge::call : 0, progressCallback, &sps);
@@ -60,11 +62,11 @@ inline float launchFDTD3dDouble(CudaMesh* d_mesh, SimulationParameters* sp, doub
 // one step; receivers of this step land in h_return_ptr[rec * numSteps + step] (reference kernels3d.cu:376-482)
 inline void launchFDTD3dStep(CudaMesh* d_mesh, SimulationParameters* sp, float* h_return_ptr, unsigned int step, int step_direction,
                              void (*progressCallback)(int, int, float)) {
-  static CudaMesh* bound_mesh = 0;
-  static unsigned int bound_steps = 0, bound_src = 0, bound_rec = 0;
-  if (bound_mesh != d_mesh || bound_steps != sp->getNumSteps() || bound_src != sp->getNumSources() || bound_rec != sp->getNumReceivers() || step == 0) {
+  // the tables inside the solver are rebuilt whenever the parameters object changed since they were uploaded (any
+  // setter bumps its generation), another parameters object is passed, or the mesh was re-partitioned
+  if (!d_mesh->boundTo(sp, sp->generation())) {
     pfdtd_host::bind_sources_receivers(d_mesh, sp, d_mesh->isDouble(), sp->getNumSteps());
-    bound_mesh = d_mesh; bound_steps = sp->getNumSteps(); bound_src = sp->getNumSources(); bound_rec = sp->getNumReceivers();
+    d_mesh->setBound(sp, sp->generation());
   }
   pfdtd_safe(pfdtd_step(d_mesh->handle(), step, step_direction, h_return_ptr, sp->getNumSteps()), "launchFDTD3dStep");
   if (progressCallback && step % PROGRESS_MOD == 0) progressCallback((int)step, (int)sp->getNumSteps(), 0.f);

@@ -94,6 +94,19 @@ static void test_simulation_parameters() {
 }
 
 // ---- SrcRecTest.cpp ---------------------------------------------------------------------------------------------
+static void test_parameter_generation() {
+  SimulationParameters sp;
+  unsigned long long g = sp.generation();
+  sp.addSource(Source(1.f, 1.f, 1.f)); CHECK(sp.generation() > g); g = sp.generation();
+  sp.updateSourceAt(0, Source(2.f, 1.f, 1.f)); CHECK(sp.generation() > g); g = sp.generation();
+  sp.addReceiver(1.f, 2.f, 3.f); CHECK(sp.generation() > g); g = sp.generation();
+  sp.setNumSteps(7); CHECK(sp.generation() > g); g = sp.generation();
+  sp.setSpatialFs(8000); CHECK(sp.generation() > g); g = sp.generation();
+  sp.addInputData(std::vector<float>(3, 1.f)); CHECK(sp.generation() > g); g = sp.generation();
+  sp.removeSource(0); CHECK(sp.generation() > g); g = sp.generation();
+  (void)sp.getNumSources(); (void)sp.getDx(); CHECK_EQ(sp.generation(), g);
+}
+
 static void test_srcrec() {
   Source s; CHECK_EQ(s.getSourceType(), SRC_HARD); CHECK_EQ(s.getInputType(), IMPULSE); CHECK_EQ(s.getP().x, 0.f);
   Source s2(1.f, 2.f, 3.f, SRC_SOFT, DATA, 4); CHECK_EQ(s2.getSourceType(), SRC_SOFT); CHECK_EQ(s2.getInputType(), DATA);
@@ -424,11 +437,42 @@ static void test_cuda_mesh_gpu() {
     for (size_t i = 0; same && i < resp[0].size(); i++) { mx = std::fmax(mx, std::fabs(resp[0][i])); same &= resp[0][i] == resp[1][i]; }
     CHECK(mx > 0); CHECK(same);
   }
+  { // launchFDTD3dStep re-uploads its source / receiver tables when the parameters change with the COUNTS unchanged
+    // (a moved source, another App / parameters object on the same thread): no stale tables
+    std::vector<unsigned char> bid, mat; shoebox_bid(60, 44, 49, bid, mat);
+    MaterialHandler mh; mh.setGlobalMaterial(1, reflection2Admitance(0.9f));
+    auto run_steps = [&](CudaMesh& mesh, SimulationParameters& p, std::vector<float>& out, unsigned first, unsigned n) {
+      for (unsigned i = first; i < first + n; i++) launchFDTD3dStep(&mesh, &p, &out[0], i, 1, quiet);
+    };
+    auto fresh = [&](float sx, std::vector<float>& out) {
+      SimulationParameters p; p.setSpatialFs(7000); p.setUpdateType(SRL_FORWARD); p.setNumSteps(40);
+      const float dx = p.getDx();
+      p.addSource(Source(sx * dx, 20 * dx, 24 * dx, SRC_HARD, IMPULSE, 0)); p.addReceiver(Receiver(25 * dx, 20 * dx, 24 * dx));
+      CudaMesh mesh;
+      mesh.setupMeshHost(&bid[0], &mat[0], 1, mh.getMaterialCoefficientPtr(), p.getParameterPtr(), make_uint3(60, 44, 49), make_uint3(32, 4, 1), 0);
+      mesh.makePartition(1);
+      out.assign(40, 0.f); run_steps(mesh, p, out, 0, 40);
+    };
+    std::vector<float> near_src, far_src, moved(40, 0.f);
+    fresh(22.f, near_src); fresh(12.f, far_src);
+    CHECK(near_src != far_src);
+    SimulationParameters p; p.setSpatialFs(7000); p.setUpdateType(SRL_FORWARD); p.setNumSteps(40);
+    const float dx = p.getDx();
+    p.addSource(Source(22 * dx, 20 * dx, 24 * dx, SRC_HARD, IMPULSE, 0)); p.addReceiver(Receiver(25 * dx, 20 * dx, 24 * dx));
+    CudaMesh mesh;
+    mesh.setupMeshHost(&bid[0], &mat[0], 1, mh.getMaterialCoefficientPtr(), p.getParameterPtr(), make_uint3(60, 44, 49), make_uint3(32, 4, 1), 0);
+    mesh.makePartition(1);
+    run_steps(mesh, p, moved, 0, 5);
+    p.updateSourceAt(0, Source(12 * dx, 20 * dx, 24 * dx, SRC_HARD, IMPULSE, 0));   // same counts, other position
+    mesh.resetPressures();
+    run_steps(mesh, p, moved, 0, 40);
+    CHECK(moved == far_src);
+  }
 }
 
 int main(int argc, char** argv) {
   const std::string what = argc > 1 ? argv[1] : "cpu";
-  if (what == "cpu") { test_simulation_parameters(); test_srcrec(); test_material_handler(); test_device_helpers_without_a_device(); test_file_reader(); test_partition_indexing(); test_geometry_and_voxelizer(); }
+  if (what == "cpu") { test_simulation_parameters(); test_parameter_generation(); test_srcrec(); test_material_handler(); test_device_helpers_without_a_device(); test_file_reader(); test_partition_indexing(); test_geometry_and_voxelizer(); }
   else if (what == "gpu") { test_cuda_mesh_gpu(); test_voxelizer_gpu(); }
   std::printf("%s: %d checks, %d failures\n", what.c_str(), g_checks, g_fail);
   return g_fail ? 1 : 0;

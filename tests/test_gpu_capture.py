@@ -113,5 +113,10 @@ def test_python_module_runs_like_the_reference_test_bench(capi, gpu):
     rd = np.array([dbl.getResponseDouble(i) for i in range(2)])
     assert fc.rel_l2(r, rd) < 1e-4 and rd.dtype == np.float64
     dbl.close()
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError):                     # no geometry: fails loudly, like every other entry point
         pf.App().runVisualization()
+    vis = make(False, False)                              # headless viewer session: 2 x fs steps through executeStep
+    vis.runVisualization()
+    rv = np.array(vis.getResponse(0))
+    assert rv.shape == (14000,) and np.array_equal(rv[:120], r[0])
+    vis.close()
