@@ -242,6 +242,12 @@ int pfdtd_fetch_responses(pfdtd_solver* s, void* h_response, uint32_t n_steps);
 /* device time of the last pfdtd_enqueue_steps call (CUDA events on the compute stream of
  * partition 0 and, separately, of the update kernels only), valid after pfdtd_sync */
 int pfdtd_last_timing(pfdtd_solver* s, float* total_ms, float* update_kernel_ms, uint32_t* n_update_launches);
+/* the same per-launch event times split by kind: `bulk` = the full-slab or interior launches (the dominant kernel;
+ * bulk_planes = z-planes they updated in total), `edge` = the one-plane launches next to a neighbour slab, which run
+ * on their own stream concurrently with the interior launch.  Needs PFDTD_OPT_TIME_KERNELS.  (The reference has no
+ * counterpart: it times whole steps on the host, kernels3d.cu:61-63,184-202.) */
+int pfdtd_last_timing_detail(pfdtd_solver* s, float* bulk_kernel_ms, uint32_t* n_bulk_launches, uint64_t* bulk_planes,
+                             float* edge_kernel_ms, uint32_t* n_edge_launches);
 
 /* ---- multi-process z-slab decomposition (one process per GPU) --------------- */
 /* The process owns global slices [GLOBAL_Z_FIRST, +vz) (options above) as ONE local partition
@@ -250,6 +256,18 @@ int pfdtd_last_timing(pfdtd_solver* s, float* total_ms, float* update_kernel_ms,
  * (torch.distributed is used for exactly that).  rank/nranks order the slabs bottom to top. */
 int pfdtd_comm_unique_id(uint8_t* out_id128);
 int pfdtd_comm_init(pfdtd_solver* s, const uint8_t* id128, int rank, int nranks);
+/* pfdtd_comm_init also maps the neighbour processes' slabs into this process (CUDA IPC, NVLink peer access): the edge
+ * launches then store their plane straight into the neighbour's halo plane and hand over through a flag word, so
+ * compute and halo transfer are one launch (replaces CudaMesh::switchHalos' copies, cudaMesh.h:432-463).  Interfaces
+ * where the mapping is not possible keep ncclSend/ncclRecv.  pfdtd_comm_release unmaps the neighbours' memory; every
+ * process must call it (followed by a barrier of the caller's) BEFORE any of them destroys its solver.
+ * pfdtd_halo_transport names the transport the stepping loop will use. */
+int pfdtd_comm_release(pfdtd_solver* s);
+int pfdtd_halo_transport(pfdtd_solver* s, char* buf, size_t buflen);
+/* CudaMesh::switchHalos (cudaMesh.h:432-463) alone, `reps` times back to back with nothing else running, timed with
+ * CUDA events on the communication stream: the link time of one exchange when both sides are ready.  Collective:
+ * every process calls it with the same `reps`. */
+int pfdtd_time_halo_exchange(pfdtd_solver* s, uint32_t reps, float* ms_per_exchange);
 /* NVLink halo time (ms) accumulated on the communication stream during the last enqueue */
 int pfdtd_last_halo_ms(pfdtd_solver* s, float* halo_ms);
 

@@ -289,6 +289,27 @@ class Solver:
         _check(lib().pfdtd_last_timing(self._h, C.byref(t), C.byref(k), C.byref(n)))
         return t.value, k.value, n.value
 
+    def last_timing_detail(self):
+        """(bulk_kernel_ms, n_bulk_launches, bulk_planes, edge_kernel_ms, n_edge_launches) of the last timed enqueue"""
+        b, e = C.c_float(), C.c_float()
+        nb, ne, pl = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        _check(lib().pfdtd_last_timing_detail(self._h, C.byref(b), C.byref(nb), C.byref(pl), C.byref(e), C.byref(ne)))
+        return b.value, nb.value, pl.value, e.value, ne.value
+
+    def time_halo_exchange(self, reps=20):
+        ms = C.c_float()
+        _check(lib().pfdtd_time_halo_exchange(self._h, C.c_uint32(reps), C.byref(ms)))
+        return ms.value
+
+    def comm_release(self):
+        if self._h:
+            _check(lib().pfdtd_comm_release(self._h))
+
+    def halo_transport(self):
+        buf = C.create_string_buffer(256)
+        _check(lib().pfdtd_halo_transport(self._h, buf, C.c_size_t(256)))
+        return buf.value.decode()
+
     def last_halo_ms(self):
         h = C.c_float()
         _check(lib().pfdtd_last_halo_ms(self._h, C.byref(h)))

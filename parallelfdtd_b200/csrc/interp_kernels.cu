@@ -59,7 +59,7 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
     fdtd_update_interp_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                            const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                            T* __restrict__ Pn, T d1, T d2, T d3, T d4, int X, int Y, int z_begin, int z_end, int chunk,
-                           const DifArgs<T> dif, T* __restrict__ peer) {
+                           const DifArgs<T> dif, T* __restrict__ peer, int* __restrict__ sig_local, int* __restrict__ sig_remote, int sig_side) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -171,11 +171,14 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
     pc = pp;
   }
   // edge launch of a slab (one plane): send the plane into the neighbour slab's halo plane (update_kernels.cu)
-  if (peer != nullptr && n == 1 && active) {
-    const int64_t row = (int64_t)gy * X + gx;
-    V4<T> v;
-    ldg4(Pn + (int64_t)z_lo * XY + row, v);
-    stg4(peer + row, v);
+  if (peer != nullptr && n == 1) {
+    if (active) {
+      const int64_t row = (int64_t)gy * X + gx;
+      V4<T> v;
+      ldg4(Pn + (int64_t)z_lo * XY + row, v);
+      stg4(peer + row, v);
+    }
+    if (sig_remote != nullptr) halo_publish(sig_local, sig_remote, sig_side, NW * 32);
   }
 }
 
@@ -229,7 +232,8 @@ int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occup
   const UpdConst<T> c = make_const<T>(a);
   kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.cls, (const ClassEntry<T>*)a.class_table, a.n_classes, (T*)a.Pn, c.d[0],
                                           c.d[1], c.d[2], c.d[3], a.X, a.Y, a.z_begin, a.z_end, chunk, make_dif<T>(a),
-                                          (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr);
+                                          (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr, a.sig_local,
+                                          (a.z_end - a.z_begin == 1 && a.peer_plane) ? a.sig_remote : nullptr, a.sig_side);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }

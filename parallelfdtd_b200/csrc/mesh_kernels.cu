@@ -99,6 +99,112 @@ int launch_translate_nodes(uint8_t* d_pos, uint8_t* d_mat, uint64_t n, int centr
   return PFDTD_OK;
 }
 
+// ---- fused padWithZeros + toBilbao/toKowalczyk + calcBoundaries: 16 output bytes per thread -----------------
+// Same results as pad_nodes_kernel (twice) followed by translate_nodes_kernel, in one pass: each thread produces 16
+// consecutive x positions of one output row for BOTH volumes.  The source bytes of a row start at an arbitrary
+// byte offset of the old (unpadded) volume, so they are fetched as five aligned 32-bit words per volume and
+// funnel-shifted into place; bytes outside the copied range (x = 0, x > dx, rows y = 0 / y > dy, planes below
+// z_first_copied or >= dz, reads past the end of the old volume) are masked to zero.  The `bid` -> node byte
+// translation goes through a 256-entry table in shared memory (values above 27 pass through like the reference's
+// kernels leave them).  Traffic: 2 B read + 2 B written per voxel.
+__global__ void __launch_bounds__(256) prepare_nodes_kernel(const uint8_t* __restrict__ old_bid, const uint8_t* __restrict__ old_mat,
+                                                            uint8_t* __restrict__ pos, uint8_t* __restrict__ mat, uint32_t dx, uint32_t dy,
+                                                            uint32_t dz, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t z_first_copied,
+                                                            int centred, unsigned long long* __restrict__ counts) {
+  __shared__ uint8_t lut[256];
+  {
+    const uint32_t k = threadIdx.x;
+    uint32_t out = k;
+    if (centred) { if (k <= 27) out = c_kowalczyk_lut[k]; }
+    else if (k == 0) out = 0;
+    else if (k <= 8) out = 0x83;
+    else if (k <= 20) out = 0x84;
+    else if (k <= 26) out = 0x85;
+    else if (k == 27) out = 0x86;
+    lut[k] = (uint8_t)out;
+  }
+  __syncthreads();
+  const uint32_t air_code = centred ? 0x80u : 0x86u;
+  const uint64_t n_old = (uint64_t)dx * dy * dz;
+  const uint64_t n_old4 = (n_old + 3) & ~(uint64_t)3;          // cudaMalloc'ed: the last partial word is readable
+  const uint32_t cpr = nx / 16;                                 // chunks per row
+  const uint64_t n_chunks = (uint64_t)cpr * ny * nz;
+  const uint32_t* __restrict__ wb = reinterpret_cast<const uint32_t*>(old_bid);
+  const uint32_t* __restrict__ wm = reinterpret_cast<const uint32_t*>(old_mat);
+  unsigned int air = 0, bnd = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += stride) {
+    const uint32_t x0 = (uint32_t)(c % cpr) * 16;
+    const uint64_t r = c / cpr;
+    const uint32_t y = (uint32_t)(r % ny), z = (uint32_t)(r / ny);
+    uint32_t ob[4] = {0, 0, 0, 0}, om[4] = {0, 0, 0, 0};
+    if (y >= 1 && y <= dy && z >= z_first_copied && z < dz && x0 <= dx) {
+      const uint64_t oi0 = (uint64_t)z * dx * dy + (uint64_t)y * dx + x0;
+      const uint64_t w0 = oi0 >> 2;
+      const uint32_t sh = (uint32_t)(oi0 & 3) * 8;
+      uint32_t b[5], m[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        const bool ok = (w0 + j) * 4 < n_old4;
+        b[j] = ok ? __ldg(wb + w0 + j) : 0u;
+        m[j] = ok ? __ldg(wm + w0 + j) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint32_t vb = __funnelshift_r(b[j], b[j + 1], sh), vm = __funnelshift_r(m[j], m[j + 1], sh);
+        uint32_t keep = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const uint32_t x = x0 + 4 * j + q;
+          if (x >= 1 && x <= dx && oi0 + 4 * j + q < n_old) keep |= 0xffu << (8 * q);
+        }
+        vb &= keep; vm &= keep;
+        uint32_t tb = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const uint32_t k = (vb >> (8 * q)) & 0xffu;
+          const uint32_t o = lut[k];
+          tb |= o << (8 * q);
+          if (k == 0) vm &= ~(0xffu << (8 * q));               // solid nodes carry material 0 (cudaMesh.cu:332-336,367-371)
+          air += (o == air_code);
+          bnd += (o != 0 && o != air_code);
+        }
+        ob[j] = tb; om[j] = vm;
+      }
+    }
+    reinterpret_cast<uint4*>(pos)[c] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+    reinterpret_cast<uint4*>(mat)[c] = make_uint4(om[0], om[1], om[2], om[3]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    air += __shfl_down_sync(0xffffffffu, air, o);
+    bnd += __shfl_down_sync(0xffffffffu, bnd, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (air) atomicAdd(counts + 0, (unsigned long long)air);
+    if (bnd) atomicAdd(counts + 1, (unsigned long long)bnd);
+  }
+}
+
+static int stream_blocks(uint64_t items) {
+  const uint64_t want = (items + 255) / 256;
+  return (int)std::max<uint64_t>(1, std::min<uint64_t>(want, 148ull * 16));
+}
+
+int launch_prepare_nodes(const uint8_t* d_old_bid, const uint8_t* d_old_mat, uint8_t* d_pos, uint8_t* d_mat, uint32_t dx, uint32_t dy,
+                         uint32_t dz, uint32_t nx, uint32_t ny, uint32_t nz, int skip_z0, int centred, unsigned long long* d_counts2,
+                         cudaStream_t stream) {
+  const uint64_t n_new = (uint64_t)nx * ny * nz;
+  if (nx % 16 == 0) {
+    prepare_nodes_kernel<<<stream_blocks(n_new / 16), 256, 0, stream>>>(d_old_bid, d_old_mat, d_pos, d_mat, dx, dy, dz, nx, ny, nz,
+                                                                      skip_z0 ? 1u : 0u, centred, d_counts2);
+    PF_CUDA(cudaGetLastError());
+    return PFDTD_OK;
+  }
+  PF_TRY(launch_pad_with_zeros(d_old_bid, d_pos, dx, dy, dz, nx, ny, nz, skip_z0, stream));
+  PF_TRY(launch_pad_with_zeros(d_old_mat, d_mat, dx, dy, dz, nx, ny, nz, skip_z0, stream));
+  return launch_translate_nodes(d_pos, d_mat, n_new, centred, d_counts2, stream);
+}
+
 // ---- node classes ---------------------------------------------------------------------------------
 // key = pos | mat << 8 | K12 << 16 | K8 << 20.  K12 / K8 = number of non-solid voxels among the 12 edge- and
 // 8 corner-neighbours; only the interpolated (27-point) schemes need them, the 7-point schemes use 0.
@@ -175,6 +281,102 @@ __global__ void assign_classes_kernel(const uint8_t* __restrict__ pos, const uin
       }
     }
     cls[i] = c;
+  }
+}
+
+// ---- the same two passes, 16 voxels per thread (X % 16 == 0) ---------------------------------------------------
+// A thread reads its 16 position and material bytes with one 128-bit load each.  Chunks that are all solid or
+// all open air -- nearly all of a room -- are settled from those two words.  For the interpolated schemes the key of
+// an inside voxel also needs its edge / corner neighbour counts: when the nine 18-byte rows around the chunk are all
+// inside, every voxel of the chunk has the full counts (one test instead of 20 byte loads per voxel); otherwise the
+// per-voxel path of node_key is taken.  Runs of equal keys (a row lying along a wall) touch the hash table once.
+__device__ __forceinline__ bool chunk_neighbourhood_all_inside(const uint8_t* __restrict__ pos, uint64_t i0, uint32_t X, uint32_t Y, uint32_t Z) {
+  const int x0 = (int)(i0 % X), y = (int)((i0 / X) % Y), z = (int)(i0 / ((uint64_t)X * Y));
+  if (x0 < 1 || x0 + 16 >= (int)X || y < 1 || y + 1 >= (int)Y || z < 1 || z + 1 >= (int)Z) return false;
+  uint32_t all = 0x80808080u;
+#pragma unroll
+  for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+      const uint64_t r = ((uint64_t)(z + dz) * Y + (y + dy)) * X + x0;
+      const uint4 w = *reinterpret_cast<const uint4*>(pos + r);
+      all &= w.x & w.y & w.z & w.w;
+      all &= (uint32_t)pos[r - 1] * 0x01010101u;
+      all &= (uint32_t)pos[r + 16] * 0x01010101u;
+    }
+  return (all & 0x80808080u) == 0x80808080u;
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint4& w, int i) {
+  const uint32_t v = i < 4 ? w.x : (i < 8 ? w.y : (i < 12 ? w.z : w.w));
+  return (v >> (8 * (i & 3))) & 0xffu;
+}
+
+__device__ __forceinline__ void class_set_insert(uint32_t* __restrict__ table, uint32_t cap, uint32_t* __restrict__ count, uint32_t key) {
+  uint32_t slot = key_hash(key) % cap;
+  for (uint32_t probe = 0; probe < cap; probe++) {
+    const uint32_t cur = table[slot];
+    if (cur == key) return;
+    if (cur == 0xffffffffu) {
+      const uint32_t prev = atomicCAS(&table[slot], 0xffffffffu, key);
+      if (prev == 0xffffffffu) { atomicAdd(count, 1u); return; }
+      if (prev == key) return;
+    }
+    slot = (slot + 1) % cap;
+  }
+}
+
+template <bool ASSIGN>
+__global__ void __launch_bounds__(256) classes16_kernel(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ mat, uint64_t n,
+                                                        uint32_t air_key, uint32_t air_code, int interp, uint32_t X, uint32_t Y, uint32_t Z,
+                                                        uint32_t* __restrict__ table, const uint8_t* __restrict__ ids, uint32_t cap,
+                                                        uint32_t* __restrict__ count, uint8_t* __restrict__ cls) {
+  const uint64_t n_chunks = n / 16;
+  const uint32_t air4 = air_code * 0x01010101u;
+  const uint32_t full = (12u << 16) | (8u << 20);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += stride) {
+    const uint4 pw = reinterpret_cast<const uint4*>(pos)[c];
+    uint32_t out[4] = {0, 0, 0, 0};
+    const bool all_solid = (pw.x | pw.y | pw.z | pw.w) == 0u;
+    const bool all_air = pw.x == air4 && pw.y == air4 && pw.z == air4 && pw.w == air4;
+    bool settled = all_solid;
+    bool nb_full = false;
+    if (!all_solid && interp) nb_full = chunk_neighbourhood_all_inside(pos, c * 16, X, Y, Z);
+    if (all_air && (!interp || nb_full)) {
+      settled = true;
+      out[0] = out[1] = out[2] = out[3] = 0x01010101u;           // class 1
+    }
+    if (!settled) {
+      const uint4 mw = reinterpret_cast<const uint4*>(mat)[c];
+      uint32_t last_key = 0xffffffffu, last_id = 0;
+#pragma unroll 1
+      for (int i = 0; i < 16; i++) {
+        const uint32_t p = byte_of(pw, i);
+        if (p == 0u) continue;
+        uint32_t key;
+        if (!interp) key = (p == air_code) ? p : (p | (byte_of(mw, i) << 8));
+        else if (nb_full) key = ((p == air_code) ? p : (p | (byte_of(mw, i) << 8))) | full;
+        else key = node_key(pos, mat, c * 16 + i, p, air_code, interp, X, Y, Z);
+        uint32_t id = 1;
+        if (key != air_key) {
+          if (key == last_key) id = last_id;
+          else if (ASSIGN) {
+            uint32_t slot = key_hash(key) % cap;
+            id = 0;
+            for (uint32_t probe = 0; probe < cap; probe++) {
+              if (table[slot] == key) { id = ids[slot]; break; }
+              slot = (slot + 1) % cap;
+            }
+          } else {
+            class_set_insert(table, cap, count, key);
+          }
+          last_key = key; last_id = id;
+        }
+        if (ASSIGN) out[i >> 2] |= id << (8 * (i & 3));
+      }
+    }
+    if (ASSIGN) reinterpret_cast<uint4*>(cls)[c] = make_uint4(out[0], out[1], out[2], out[3]);
   }
 }
 
@@ -284,7 +486,11 @@ static int class_blocks(uint64_t n) {
 
 int launch_mark_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_key, uint32_t air_code, int interp,
                         uint32_t X, uint32_t Y, uint32_t Z, uint32_t* d_table, uint32_t cap, uint32_t* d_count, cudaStream_t stream) {
-  mark_classes_kernel<<<class_blocks(n), 256, 0, stream>>>(d_pos, d_mat, n, air_key, air_code, interp, X, Y, Z, d_table, cap, d_count);
+  if (X % 16 == 0)
+    classes16_kernel<false><<<stream_blocks(n / 16), 256, 0, stream>>>(d_pos, d_mat, n, air_key, air_code, interp, X, Y, Z, d_table, nullptr, cap,
+                                                                       d_count, nullptr);
+  else
+    mark_classes_kernel<<<class_blocks(n), 256, 0, stream>>>(d_pos, d_mat, n, air_key, air_code, interp, X, Y, Z, d_table, cap, d_count);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }
@@ -292,7 +498,11 @@ int launch_mark_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, 
 int launch_assign_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_key, uint32_t air_code, int interp,
                           uint32_t X, uint32_t Y, uint32_t Z, const uint32_t* d_table, const uint8_t* d_ids, uint32_t cap,
                           uint8_t* d_cls, cudaStream_t stream) {
-  assign_classes_kernel<<<class_blocks(n), 256, 0, stream>>>(d_pos, d_mat, n, air_key, air_code, interp, X, Y, Z, d_table, d_ids, cap, d_cls);
+  if (X % 16 == 0)
+    classes16_kernel<true><<<stream_blocks(n / 16), 256, 0, stream>>>(d_pos, d_mat, n, air_key, air_code, interp, X, Y, Z,
+                                                                      const_cast<uint32_t*>(d_table), d_ids, cap, nullptr, d_cls);
+  else
+    assign_classes_kernel<<<class_blocks(n), 256, 0, stream>>>(d_pos, d_mat, n, air_key, air_code, interp, X, Y, Z, d_table, d_ids, cap, d_cls);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }

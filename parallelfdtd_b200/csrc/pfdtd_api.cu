@@ -105,7 +105,9 @@ struct Partition {
   void* d_src_samples = nullptr;        // [n_src_total][src_steps]
   void* d_rec_out = nullptr;            // [n_rec_total][rec_cap]
   std::vector<int32_t> rec_slots;       // host copy of owned receiver slots
+  uint32_t rec_cap_alloc = 0;           // steps d_rec_out has room for
   std::vector<cudaEvent_t> kev;         // kernel timing events (pairs)
+  std::vector<int> kev_planes;          // planes updated by the launch each pair brackets
 };
 
 }  // namespace pfdtd
@@ -143,17 +145,29 @@ struct pfdtd_solver {
   std::vector<int32_t> src_xyz, src_type, rec_xyz;
   std::vector<unsigned char> src_samples;   // [n_src][src_steps] of dtype
   uint32_t n_src = 0, n_rec = 0, src_steps = 0, rec_cap = 0;
-  bool srcrec_dirty = true;
+  bool srcrec_dirty = true;              // receiver (and source) tables must be rebuilt: recorded samples are dropped
+  bool src_dirty = false;                // only the source tables changed: the recorded samples stay
+  int dif_order_built = 0;               // filter order the partitions were built for (state layout, row-segment entries)
   // comm
   void* comm = nullptr;
   int rank = 0, nranks = 1;
   cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;
-  float last_total_ms = 0, last_kernel_ms = 0, last_halo_ms = 0;
-  uint32_t last_kernel_launches = 0;
+  float last_total_ms = 0, last_kernel_ms = 0, last_halo_ms = 0, last_edge_ms = 0;
+  uint32_t last_kernel_launches = 0, last_edge_launches = 0;
+  uint64_t last_bulk_planes = 0;
   uint64_t launch_count = 0;
   std::vector<char> halo_sent_up, halo_sent_down;   // per step: interfaces served by the edge launches' peer stores
   std::vector<char> peer_ok;                        // [np*np]: partition a's device can address partition b's memory
   int64_t opt_peer_stores = 1;
+  // neighbour PROCESSES whose slab memory is mapped here (CUDA IPC): their halo planes are written by this process's
+  // edge launches, the hand-over goes through flag words (tma_common.cuh).  link[0] = lower neighbour, link[1] = upper.
+  struct PeerLink {
+    bool ok = false;            // both sides mapped each other and can split their step into edge + interior launches
+    void* nb_P[2] = {nullptr, nullptr};
+    int* nb_flags = nullptr;
+    int64_t nb_size = 0;        // planes in the neighbour's slab
+  } link[2];
+  int* d_halo_flags = nullptr;  // this process's flag block (own 2 MiB allocation: exported whole)
   // graph
   cudaGraphExec_t graph_exec = nullptr;
   uint32_t graph_steps = 0;
@@ -177,7 +191,18 @@ static void partition_indexing(uint32_t dim, uint32_t n, std::vector<int64_t>& f
   }
 }
 
+// mappings of the neighbour processes' slabs and this process's flag block (pfdtd_comm_init)
+static void close_links(pfdtd_solver* s) {
+  for (auto& l : s->link) {
+    for (void*& q : l.nb_P) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    if (l.nb_flags) { cudaIpcCloseMemHandle(l.nb_flags); l.nb_flags = nullptr; }
+    l.ok = false;
+  }
+  if (s->d_halo_flags) { cudaFree(s->d_halo_flags); s->d_halo_flags = nullptr; }
+}
+
 static int free_partitions(pfdtd_solver* s) {
+  close_links(s);
   if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
   for (auto& p : s->parts) {
     cudaSetDevice(p.device);
@@ -202,64 +227,97 @@ static bool has_lower_ext(const pfdtd_solver* s) { return s->comm && s->rank > 0
 static bool has_upper_ext(const pfdtd_solver* s) { return s->comm && s->rank < s->nranks - 1; }
 
 // ---- per-partition source / receiver tables ----------------------------------------------------------
+// Three independent reasons to touch them:
+//   srcrec_dirty  receivers (or the slab layout / communicator) changed: everything is rebuilt, recorded samples dropped
+//   src_dirty     only the sources changed: source tables rebuilt, the receiver buffer with its samples stays
+//   rec_cap grew  (pfdtd_reserve_steps, or enqueue_steps past the reserved length): the receiver buffer is re-allocated
+//                 and the samples recorded so far are carried over row by row
+static int upload_new(void** d, const void* h, size_t bytes) {
+  *d = nullptr;
+  if (bytes == 0) return PFDTD_OK;
+  PF_CUDA(cudaMalloc(d, bytes));
+  PF_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+  return PFDTD_OK;
+}
+
 static int prepare_srcrec(pfdtd_solver* s) {
-  if (!s->srcrec_dirty) return PFDTD_OK;
   PF_CHECK(!s->parts.empty(), PFDTD_ERR_INVALID, "make_partition must be called first");
   const int64_t XY = (int64_t)s->X * s->Y;
   const int64_t zoff = s->opt_global_z_first;
   if (s->rec_cap < s->src_steps) s->rec_cap = s->src_steps;
   if (s->rec_cap == 0) s->rec_cap = 1;
+  bool changed = false;
   for (size_t k = 0; k < s->parts.size(); k++) {
     Partition& p = s->parts[k];
+    const bool all = s->srcrec_dirty;
+    const bool grow = !all && s->n_rec && p.rec_cap_alloc < s->rec_cap;
+    if (!all && !s->src_dirty && !grow) continue;
+    changed = true;
     PF_CUDA(cudaSetDevice(p.device));
-    for (void* q : {(void*)p.d_src_elem, (void*)p.d_src_type, (void*)p.d_src_slot, (void*)p.d_rec_elem, (void*)p.d_rec_slot,
-                    p.d_src_samples, p.d_rec_out})
-      cudaFree(q);
-    p.d_src_elem = nullptr; p.d_src_type = nullptr; p.d_src_slot = nullptr; p.d_rec_elem = nullptr; p.d_rec_slot = nullptr;
-    p.d_src_samples = nullptr; p.d_rec_out = nullptr;
-    std::vector<int64_t> se, re;
-    std::vector<int32_t> st, ss, rs;
-    // sources: every partition that holds the slice, halo copies included (cudaMesh.h:321-338)
-    for (uint32_t i = 0; i < s->n_src; i++) {
-      int64_t z = (int64_t)s->src_xyz[3 * i + 2] - zoff;
-      if (z < p.first || z > p.first + p.size - 1) continue;
-      se.push_back((z - p.first) * XY + (int64_t)s->src_xyz[3 * i + 1] * s->X + s->src_xyz[3 * i]);
-      st.push_back(s->src_type[i]);
-      ss.push_back((int32_t)i);
+    if (p.s_main) PF_CUDA(cudaStreamSynchronize(p.s_main));
+    if (p.s_edge) PF_CUDA(cudaStreamSynchronize(p.s_edge));
+    if (all || s->src_dirty) {
+      for (void* q : {(void*)p.d_src_elem, (void*)p.d_src_type, (void*)p.d_src_slot, p.d_src_samples}) cudaFree(q);
+      p.d_src_elem = nullptr; p.d_src_type = nullptr; p.d_src_slot = nullptr; p.d_src_samples = nullptr;
+      std::vector<int64_t> se;
+      std::vector<int32_t> st, ss;
+      // sources: every partition that holds the slice, halo copies included (cudaMesh.h:321-338)
+      for (uint32_t i = 0; i < s->n_src; i++) {
+        int64_t z = (int64_t)s->src_xyz[3 * i + 2] - zoff;
+        if (z < p.first || z > p.first + p.size - 1) continue;
+        se.push_back((z - p.first) * XY + (int64_t)s->src_xyz[3 * i + 1] * s->X + s->src_xyz[3 * i]);
+        st.push_back(s->src_type[i]);
+        ss.push_back((int32_t)i);
+      }
+      p.n_src = (int)se.size();
+      PF_TRY(upload_new((void**)&p.d_src_elem, se.data(), se.size() * 8));
+      PF_TRY(upload_new((void**)&p.d_src_type, st.data(), st.size() * 4));
+      PF_TRY(upload_new((void**)&p.d_src_slot, ss.data(), ss.size() * 4));
+      if (p.n_src) PF_TRY(upload_new(&p.d_src_samples, s->src_samples.data(), s->src_samples.size()));
     }
-    // receivers: first partition containing the slice (cudaMesh.h:251-266); across processes the
-    // lower process owns the two shared slices
-    for (uint32_t i = 0; i < s->n_rec; i++) {
-      int64_t z = (int64_t)s->rec_xyz[3 * i + 2] - zoff;
-      if (z < p.first || z > p.first + p.size - 1) continue;
-      if (k > 0 && z <= s->parts[k - 1].first + s->parts[k - 1].size - 1) continue;
-      if (k == 0 && zoff > 0 && z <= 1) continue;
-      re.push_back((z - p.first) * XY + (int64_t)s->rec_xyz[3 * i + 1] * s->X + s->rec_xyz[3 * i]);
-      rs.push_back((int32_t)i);
-    }
-    p.n_src = (int)se.size();
-    p.n_rec = (int)re.size();
-    p.rec_slots = rs;
-    auto up = [&](void** d, const void* h, size_t bytes) -> int {
-      if (bytes == 0) return PFDTD_OK;
-      PF_CUDA(cudaMalloc(d, bytes));
-      PF_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
-      return PFDTD_OK;
-    };
-    PF_TRY(up((void**)&p.d_src_elem, se.data(), se.size() * 8));
-    PF_TRY(up((void**)&p.d_src_type, st.data(), st.size() * 4));
-    PF_TRY(up((void**)&p.d_src_slot, ss.data(), ss.size() * 4));
-    PF_TRY(up((void**)&p.d_rec_elem, re.data(), re.size() * 8));
-    PF_TRY(up((void**)&p.d_rec_slot, rs.data(), rs.size() * 4));
-    if (p.n_src) PF_TRY(up(&p.d_src_samples, s->src_samples.data(), s->src_samples.size()));
-    if (s->n_rec) {
-      size_t bytes = (size_t)s->n_rec * s->rec_cap * esize(s);
-      PF_CUDA(cudaMalloc(&p.d_rec_out, bytes));
-      PF_CUDA(cudaMemset(p.d_rec_out, 0, bytes));
+    if (all) {
+      for (void* q : {(void*)p.d_rec_elem, (void*)p.d_rec_slot, p.d_rec_out}) cudaFree(q);
+      p.d_rec_elem = nullptr; p.d_rec_slot = nullptr; p.d_rec_out = nullptr;
+      std::vector<int64_t> re;
+      std::vector<int32_t> rs;
+      // receivers: first partition containing the slice (cudaMesh.h:251-266); across processes the
+      // lower process owns the two shared slices
+      for (uint32_t i = 0; i < s->n_rec; i++) {
+        int64_t z = (int64_t)s->rec_xyz[3 * i + 2] - zoff;
+        if (z < p.first || z > p.first + p.size - 1) continue;
+        if (k > 0 && z <= s->parts[k - 1].first + s->parts[k - 1].size - 1) continue;
+        if (k == 0 && zoff > 0 && z <= 1) continue;
+        re.push_back((z - p.first) * XY + (int64_t)s->rec_xyz[3 * i + 1] * s->X + s->rec_xyz[3 * i]);
+        rs.push_back((int32_t)i);
+      }
+      p.n_rec = (int)re.size();
+      p.rec_slots = rs;
+      PF_TRY(upload_new((void**)&p.d_rec_elem, re.data(), re.size() * 8));
+      PF_TRY(upload_new((void**)&p.d_rec_slot, rs.data(), rs.size() * 4));
+      p.rec_cap_alloc = 0;
+      if (s->n_rec) {
+        const size_t bytes = (size_t)s->n_rec * s->rec_cap * esize(s);
+        PF_CUDA(cudaMalloc(&p.d_rec_out, bytes));
+        PF_CUDA(cudaMemset(p.d_rec_out, 0, bytes));
+        p.rec_cap_alloc = s->rec_cap;
+      }
+    } else if (grow) {
+      void* bigger = nullptr;
+      const size_t es = esize(s);
+      const size_t bytes = (size_t)s->n_rec * s->rec_cap * es;
+      PF_CUDA(cudaMalloc(&bigger, bytes));
+      PF_CUDA(cudaMemset(bigger, 0, bytes));
+      if (p.d_rec_out && p.rec_cap_alloc)
+        PF_CUDA(cudaMemcpy2D(bigger, (size_t)s->rec_cap * es, p.d_rec_out, (size_t)p.rec_cap_alloc * es, (size_t)p.rec_cap_alloc * es,
+                             s->n_rec, cudaMemcpyDeviceToDevice));
+      cudaFree(p.d_rec_out);
+      p.d_rec_out = bigger;
+      p.rec_cap_alloc = s->rec_cap;
     }
   }
   s->srcrec_dirty = false;
-  if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+  s->src_dirty = false;
+  if (changed && s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }   // the graph holds the old pointers
   return PFDTD_OK;
 }
 
@@ -274,6 +332,7 @@ static UpdateArgs make_update_args(pfdtd_solver* s, Partition& p, int z_begin, i
   a.n_classes = (int)s->class_keys.size();
   a.tma_hints = (int)s->opt_tma_hints;
   a.peer_plane = nullptr;
+  a.sig_local = nullptr; a.sig_remote = nullptr; a.sig_side = 0;
   a.dif_order = p.dif_rowbase ? (int)s->opt_dif_order : 0;
   a.dif_state = p.dif_state;
   a.dif_rowbase = p.dif_rowbase;
@@ -314,16 +373,20 @@ static int ensure_class_tables(pfdtd_solver* s) {
 }
 
 static int launch_update(pfdtd_solver* s, Partition& p, int z_begin, int z_end, const TmaConfig& cfg, cudaStream_t st,
-                         bool timed, void* peer_plane = nullptr) {
+                         bool timed, void* peer_plane = nullptr, int* sig_remote = nullptr, int sig_side = 0) {
   if (z_end <= z_begin) return PFDTD_OK;
   UpdateArgs a = make_update_args(s, p, z_begin, z_end, st);
   a.peer_plane = peer_plane;
+  a.sig_local = s->d_halo_flags;
+  a.sig_remote = sig_remote;
+  a.sig_side = sig_side;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed) {
     PF_CUDA(cudaEventCreate(&e0));
     PF_CUDA(cudaEventCreate(&e1));
     p.kev.push_back(e0);
     p.kev.push_back(e1);
+    p.kev_planes.push_back(z_end - z_begin);
     PF_CUDA(cudaEventRecord(e0, st));
   }
   if (s->scheme == SCH_INTERP) {
@@ -336,12 +399,21 @@ static int launch_update(pfdtd_solver* s, Partition& p, int z_begin, int z_end, 
   return PFDTD_OK;
 }
 
+// peer-mapped halo hand-over with the lower / upper neighbour PROCESS is in use for the stepping loop
+static bool ipc_side(const pfdtd_solver* s, int side) {
+  if (!s->comm || s->parts.size() != 1 || !s->opt_peer_stores || !s->opt_overlap || !s->link[side].ok) return false;
+  return side == 0 ? s->rank > 0 : s->rank < s->nranks - 1;
+}
+
 static int launch_srcrec_for(pfdtd_solver* s, Partition& p, cudaStream_t st, int record, int inject, int advance) {
-  if (p.n_src == 0 && p.n_rec == 0 && !advance) return PFDTD_OK;
+  const bool wait_lo = ipc_side(s, 0), wait_hi = ipc_side(s, 1);
+  if (p.n_src == 0 && p.n_rec == 0 && !advance && !wait_lo && !wait_hi) return PFDTD_OK;
   SrcRecArgs a{};
+  a.halo_flags = (wait_lo || wait_hi) ? s->d_halo_flags : nullptr;
+  a.wait_lo = wait_lo; a.wait_hi = wait_hi;
   a.dtype = s->dtype;
   a.P = p.P[s->cur];
-  a.n_rec = p.n_rec; a.rec_elem = p.d_rec_elem; a.rec_slot = p.d_rec_slot; a.rec_out = p.d_rec_out; a.rec_stride = s->rec_cap;
+  a.n_rec = p.n_rec; a.rec_elem = p.d_rec_elem; a.rec_slot = p.d_rec_slot; a.rec_out = p.d_rec_out; a.rec_stride = p.rec_cap_alloc;
   a.n_src = p.n_src; a.src_elem = p.d_src_elem; a.src_type = p.d_src_type; a.src_slot = p.d_src_slot;
   a.src_samples = p.d_src_samples; a.src_stride = s->src_steps;
   a.d_step = p.d_step;
@@ -375,32 +447,23 @@ static int enqueue_halo_local_down(pfdtd_solver* s, size_t k, int b) {  // parti
   PF_CUDA(cudaMemcpyPeerAsync(dst2, lo.device, src2, hi.device, plane, hi.s_edge));
   return PFDTD_OK;
 }
-static int enqueue_halo_external(pfdtd_solver* s, int b) {
+static int enqueue_halo_external(pfdtd_solver* s, int b, bool want_lo = true, bool want_hi = true) {
   if (!s->comm) return PFDTD_OK;
   const size_t plane = (size_t)s->X * s->Y * esize(s);
-  const bool lo_ext = has_lower_ext(s), hi_ext = has_upper_ext(s);
+  const bool lo_ext = has_lower_ext(s) && want_lo, hi_ext = has_upper_ext(s) && want_hi;
   if (!lo_ext && !hi_ext) return PFDTD_OK;
-  Partition& pb = s->parts.front();
-  Partition& pt = s->parts.back();
-  // bottom and top partitions may differ; each side's traffic goes on its own edge stream
+  Partition& p = s->parts.front();        // pfdtd_comm_init: exactly one local partition
+  PF_CUDA(cudaSetDevice(p.device));
+  PF_NCCL(g_nccl.GroupStart());
   if (lo_ext) {
-    PF_CUDA(cudaSetDevice(pb.device));
-    PF_NCCL(g_nccl.GroupStart());
-    PF_NCCL(g_nccl.Send((char*)pb.P[b] + plane, plane, 1 /*ncclUint8*/, s->rank - 1, s->comm, pb.s_edge));
-    PF_NCCL(g_nccl.Recv((char*)pb.P[b], plane, 1, s->rank - 1, s->comm, pb.s_edge));
-    if (hi_ext && &pb == &pt) {
-      PF_NCCL(g_nccl.Send((char*)pt.P[b] + (size_t)(pt.size - 2) * plane, plane, 1, s->rank + 1, s->comm, pt.s_edge));
-      PF_NCCL(g_nccl.Recv((char*)pt.P[b] + (size_t)(pt.size - 1) * plane, plane, 1, s->rank + 1, s->comm, pt.s_edge));
-    }
-    PF_NCCL(g_nccl.GroupEnd());
+    PF_NCCL(g_nccl.Send((char*)p.P[b] + plane, plane, 1 /*ncclUint8*/, s->rank - 1, s->comm, p.s_edge));
+    PF_NCCL(g_nccl.Recv((char*)p.P[b], plane, 1, s->rank - 1, s->comm, p.s_edge));
   }
-  if (hi_ext && !(lo_ext && &pb == &pt)) {
-    PF_CUDA(cudaSetDevice(pt.device));
-    PF_NCCL(g_nccl.GroupStart());
-    PF_NCCL(g_nccl.Send((char*)pt.P[b] + (size_t)(pt.size - 2) * plane, plane, 1, s->rank + 1, s->comm, pt.s_edge));
-    PF_NCCL(g_nccl.Recv((char*)pt.P[b] + (size_t)(pt.size - 1) * plane, plane, 1, s->rank + 1, s->comm, pt.s_edge));
-    PF_NCCL(g_nccl.GroupEnd());
+  if (hi_ext) {
+    PF_NCCL(g_nccl.Send((char*)p.P[b] + (size_t)(p.size - 2) * plane, plane, 1, s->rank + 1, s->comm, p.s_edge));
+    PF_NCCL(g_nccl.Recv((char*)p.P[b] + (size_t)(p.size - 1) * plane, plane, 1, s->rank + 1, s->comm, p.s_edge));
   }
+  PF_NCCL(g_nccl.GroupEnd());
   return PFDTD_OK;
 }
 
@@ -427,6 +490,7 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
   const size_t plane_bytes = (size_t)s->X * s->Y * esize(s);
   s->halo_sent_up.assign(np, 0);      // interface k|k+1: partition k's top plane already stored into k+1's plane 0
   s->halo_sent_down.assign(np, 0);    //                  partition k+1's plane 1 already stored into k's last plane
+  bool ext_sent_lo = false, ext_sent_hi = false;   // process boundaries served by the edge launches (CUDA IPC mapping)
   // phase 1: sources/receivers + edge planes on the edge stream
   for (size_t k = 0; k < np; k++) {
     Partition& p = s->parts[k];
@@ -460,8 +524,20 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
         peer_hi = s->parts[k + 1].P[1 - c];
         s->halo_sent_up[k] = 1;
       }
-      if (lo_nb) { PF_TRY(launch_update(s, p, zb, zb + 1, p.cfg_edge, p.s_edge, timed, peer_lo)); ib = zb + 1; }
-      if (hi_nb) { PF_TRY(launch_update(s, p, ze - 1, ze, p.cfg_edge, p.s_edge, timed, peer_hi)); ie = ze - 1; }
+      // neighbour PROCESSES whose slab is mapped here: same stores, plus the flag hand-over instead of a stream event
+      int *sig_lo = nullptr, *sig_hi = nullptr;
+      if (p.use_tma && k == 0 && ipc_side(s, 0)) {
+        peer_lo = (char*)s->link[0].nb_P[1 - c] + (size_t)(s->link[0].nb_size - 1) * plane_bytes;
+        sig_lo = s->link[0].nb_flags + 1 /* HALO_FROM_HI: this process is its upper neighbour */;
+        ext_sent_lo = true;
+      }
+      if (p.use_tma && k + 1 == np && ipc_side(s, 1)) {
+        peer_hi = s->link[1].nb_P[1 - c];
+        sig_hi = s->link[1].nb_flags + 0 /* HALO_FROM_LO */;
+        ext_sent_hi = true;
+      }
+      if (lo_nb) { PF_TRY(launch_update(s, p, zb, zb + 1, p.cfg_edge, p.s_edge, timed, peer_lo, sig_lo, 0)); ib = zb + 1; }
+      if (hi_nb) { PF_TRY(launch_update(s, p, ze - 1, ze, p.cfg_edge, p.s_edge, timed, peer_hi, sig_hi, 1)); ie = ze - 1; }
       // interior on the main stream, concurrently with the halo traffic below
       PF_CUDA(cudaStreamWaitEvent(p.s_main, p.ev_src, 0));
       PF_TRY(launch_update(s, p, ib, ie, p.cfg_int, p.s_main, timed));
@@ -477,7 +553,7 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
     if (!s->halo_sent_up[k]) PF_TRY(enqueue_halo_local_up(s, k, 1 - c));
     if (!s->halo_sent_down[k]) PF_TRY(enqueue_halo_local_down(s, k, 1 - c));
   }
-  PF_TRY(enqueue_halo_external(s, 1 - c));
+  PF_TRY(enqueue_halo_external(s, 1 - c, !ext_sent_lo, !ext_sent_hi));
   if (time_halo && s->ev_h1) { PF_CUDA(cudaSetDevice(s->parts[0].device)); PF_CUDA(cudaEventRecord(s->ev_h1, s->parts[0].s_edge)); }
   for (size_t k = 0; k < np; k++) {
     Partition& p = s->parts[k];
@@ -517,6 +593,79 @@ static int elem_of(pfdtd_solver* s, uint32_t x, uint32_t y, int64_t zl, size_t k
 template <typename W>
 __global__ void fill_words(W* __restrict__ d, W v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = v;
+}
+
+// ---- CUDA-IPC links to the neighbour processes ------------------------------------------------------------------
+// Every process exports its two field buffers and its flag block, the neighbours map them (NVLink peer access), and
+// both sides confirm.  The handles travel over the NCCL communicator that exists anyway.  An interface uses the
+// mapping only when BOTH sides mapped each other and both can split their step into edge + interior launches with
+// the TMA kernels; otherwise that interface keeps ncclSend/ncclRecv.
+struct LinkHello {
+  cudaIpcMemHandle_t p0, p1, flags;
+  int64_t size;
+  int32_t can_peer, pad;
+};
+
+static int exchange_links(pfdtd_solver* s) {
+  close_links(s);
+  if (s->nranks < 2 || getenv("PFDTD_NO_IPC")) return PFDTD_OK;
+  Partition& p = s->parts[0];
+  PF_CUDA(cudaSetDevice(p.device));
+  PF_CUDA(cudaMalloc(&s->d_halo_flags, 2u << 20));
+  PF_CUDA(cudaMemset(s->d_halo_flags, 0, 2u << 20));
+  LinkHello mine{};
+  bool exportable = cudaIpcGetMemHandle(&mine.p0, p.P[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.p1, p.P[1]) == cudaSuccess &&
+                    cudaIpcGetMemHandle(&mine.flags, s->d_halo_flags) == cudaSuccess;
+  if (!exportable) cudaGetLastError();
+  mine.size = p.size;
+  mine.can_peer = (exportable && p.use_tma && (int)p.size - 2 >= 4) ? 1 : 0;
+  LinkHello* d_hello = nullptr;     // [0] mine, [1] from the lower neighbour, [2] from the upper one
+  int* d_ack = nullptr;             // [0] mine towards lower, [1] mine towards upper, [2] from lower, [3] from upper
+  PF_CUDA(cudaMalloc(&d_hello, 3 * sizeof(LinkHello)));
+  PF_CUDA(cudaMalloc(&d_ack, 4 * sizeof(int)));
+  PF_CUDA(cudaMemset(d_hello, 0, 3 * sizeof(LinkHello)));
+  PF_CUDA(cudaMemset(d_ack, 0, 4 * sizeof(int)));
+  PF_CUDA(cudaMemcpy(d_hello, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  const bool lo = has_lower_ext(s), hi = has_upper_ext(s);
+  auto cleanup = [&]() { cudaFree(d_hello); cudaFree(d_ack); };
+  auto round = [&](const void* send_lo, const void* send_hi, void* recv_lo, void* recv_hi, size_t bytes) -> int {
+    PF_NCCL(g_nccl.GroupStart());
+    if (lo) { PF_NCCL(g_nccl.Send(send_lo, bytes, 1, s->rank - 1, s->comm, p.s_edge)); PF_NCCL(g_nccl.Recv(recv_lo, bytes, 1, s->rank - 1, s->comm, p.s_edge)); }
+    if (hi) { PF_NCCL(g_nccl.Send(send_hi, bytes, 1, s->rank + 1, s->comm, p.s_edge)); PF_NCCL(g_nccl.Recv(recv_hi, bytes, 1, s->rank + 1, s->comm, p.s_edge)); }
+    PF_NCCL(g_nccl.GroupEnd());
+    PF_CUDA(cudaStreamSynchronize(p.s_edge));
+    return PFDTD_OK;
+  };
+  int rc = round(d_hello, d_hello, d_hello + 1, d_hello + 2, sizeof(LinkHello));
+  if (rc != PFDTD_OK) { cleanup(); return rc; }
+  LinkHello got[3];
+  PF_CUDA(cudaMemcpy(got, d_hello, sizeof(got), cudaMemcpyDeviceToHost));
+  int ack[4] = {0, 0, 0, 0};
+  for (int side = 0; side < 2; side++) {
+    if (!(side == 0 ? lo : hi)) continue;
+    const LinkHello& nb = got[1 + side];
+    auto& l = s->link[side];
+    bool mapped = mine.can_peer && nb.can_peer;
+    if (mapped) {
+      mapped = cudaIpcOpenMemHandle(&l.nb_P[0], nb.p0, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+               cudaIpcOpenMemHandle(&l.nb_P[1], nb.p1, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+               cudaIpcOpenMemHandle((void**)&l.nb_flags, nb.flags, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      if (!mapped) {
+        cudaGetLastError();
+        for (void*& q : l.nb_P) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+        if (l.nb_flags) { cudaIpcCloseMemHandle(l.nb_flags); l.nb_flags = nullptr; }
+      }
+    }
+    l.nb_size = nb.size;
+    ack[side] = mapped ? 1 : 0;
+  }
+  PF_CUDA(cudaMemcpy(d_ack, ack, 2 * sizeof(int), cudaMemcpyHostToDevice));
+  rc = round(d_ack + 0, d_ack + 1, d_ack + 2, d_ack + 3, sizeof(int));
+  if (rc != PFDTD_OK) { cleanup(); return rc; }
+  PF_CUDA(cudaMemcpy(ack, d_ack, sizeof(ack), cudaMemcpyDeviceToHost));
+  for (int side = 0; side < 2; side++) s->link[side].ok = (side == 0 ? lo : hi) && ack[side] && ack[2 + side];
+  cleanup();
+  return PFDTD_OK;
 }
 
 static int select_device(int device) {
@@ -633,6 +782,7 @@ int pfdtd_create(pfdtd_solver** out) {
 
 int pfdtd_destroy(pfdtd_solver* s) {
   if (!s) return PFDTD_OK;
+  if (!s->parts.empty()) sync_all(s);
   free_partitions(s);
   if (s->d_pos0) { cudaSetDevice(s->stage_device); cudaFree(s->d_pos0); cudaFree(s->d_mat0); cudaFree(s->d_cls0); }
   // s->comm is owned by the process-wide communicator cache (pfdtd_comm_init)
@@ -666,6 +816,10 @@ int pfdtd_set_option(pfdtd_solver* s, int option, int64_t value) {
   PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
   int64_t* slot = option_slot(s, option);
   PF_CHECK(slot, PFDTD_ERR_INVALID, "unknown option %d", option);
+  // the filter states and row-segment entries of the partitions are laid out for one order
+  PF_CHECK(!(option == PFDTD_OPT_DIF_ORDER && !s->parts.empty() && value != s->dif_order_built), PFDTD_ERR_INVALID,
+           "PFDTD_OPT_DIF_ORDER cannot change (%d -> %lld) while partitions exist: set it before pfdtd_make_partition",
+           s->dif_order_built, (long long)value);
   *slot = value;
   s->tables_dirty = true;
   if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
@@ -711,20 +865,30 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
   auto padded = [](uint32_t d, uint32_t b) { return d % b ? d + (b - d % b) : d; };
   const uint32_t nx = padded(vx, block_x), ny = padded(vy, pby), nz = padded(vz, block_z);
   const uint64_t n_new = (uint64_t)nx * ny * nz;
+  // everything allocated below is released on every early return; the input volumes are adopted either way
+  // (the reference frees them inside padWithZeros, cudaMesh.cu:290-291)
+  struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* q : ptrs) cudaFree(q); }
+    void keep(void* q) { ptrs.erase(std::remove(ptrs.begin(), ptrs.end(), q), ptrs.end()); }
+  } scratch;
+  scratch.ptrs.push_back(d_bid);
+  scratch.ptrs.push_back(d_mat);
   uint8_t *np = nullptr, *nm = nullptr;
   unsigned long long* d_counts = nullptr;
   PF_CUDA(cudaMalloc(&np, n_new));
+  scratch.ptrs.push_back(np);
   PF_CUDA(cudaMalloc(&nm, n_new));
+  scratch.ptrs.push_back(nm);
   PF_CUDA(cudaMalloc(&d_counts, 2 * sizeof(unsigned long long)));
-  PF_CUDA(cudaMemset(d_counts, 0, 2 * sizeof(unsigned long long)));
+  scratch.ptrs.push_back(d_counts);
+  PF_CUDA(cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), 0));
   const int skip_z0 = (s->opt_global_z_first == 0);   // only the global z=0 plane is dropped by the reference's copy
-  PF_TRY(launch_pad_with_zeros(d_bid, np, vx, vy, vz, nx, ny, nz, skip_z0, 0));
-  PF_TRY(launch_pad_with_zeros(d_mat, nm, vx, vy, vz, nx, ny, nz, skip_z0, 0));
-  PF_TRY(launch_translate_nodes(np, nm, n_new, s->scheme == SCH_CENTRED, d_counts, 0));
-  s->launch_count += 3;
+  PF_TRY(launch_prepare_nodes(d_bid, d_mat, np, nm, vx, vy, vz, nx, ny, nz, skip_z0, s->scheme == SCH_CENTRED, d_counts, 0));
+  s->launch_count += (nx % 16 == 0) ? 1 : 3;
   unsigned long long h_counts[2] = {0, 0};
   PF_CUDA(cudaMemcpy(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost));
-  PF_CUDA(cudaFree(d_counts));
+  scratch.keep(d_bid); scratch.keep(d_mat);
   PF_CUDA(cudaFree(d_bid));   // adopted, like the reference (cudaMesh.cu:290-291)
   PF_CUDA(cudaFree(d_mat));
   // node classes: distinct node keys (position byte, material byte [, K12, K8]) -> one class byte per voxel
@@ -737,8 +901,11 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
     uint32_t* d_count = nullptr;
     uint8_t* d_ids = nullptr;
     PF_CUDA(cudaMalloc(&d_table, cap * sizeof(uint32_t)));
+    scratch.ptrs.push_back(d_table);
     PF_CUDA(cudaMalloc(&d_count, sizeof(uint32_t)));
+    scratch.ptrs.push_back(d_count);
     PF_CUDA(cudaMalloc(&d_ids, cap));
+    scratch.ptrs.push_back(d_ids);
     PF_CUDA(cudaMemset(d_table, 0xff, cap * sizeof(uint32_t)));
     PF_CUDA(cudaMemset(d_count, 0, sizeof(uint32_t)));
     PF_TRY(launch_mark_classes(np, nm, n_new, air_key, air_code, interp, nx, ny, nz, d_table, cap, d_count, 0));
@@ -768,6 +935,7 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
           ids[slot] = (uint8_t)(2 + (std::find(found.begin(), found.end(), table[slot]) - found.begin()));
       PF_CUDA(cudaMemcpy(d_ids, ids.data(), cap, cudaMemcpyHostToDevice));
       PF_CUDA(cudaMalloc(&s->d_cls0, n_new));
+      scratch.ptrs.push_back(s->d_cls0);
       PF_TRY(launch_assign_classes(np, nm, n_new, air_key, air_code, interp, nx, ny, nz, d_table, d_ids, cap, s->d_cls0, 0));
       PF_CUDA(cudaDeviceSynchronize());
       s->launch_count += 2;
@@ -775,10 +943,8 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
       s->class_keys.resize(2);
       s->dif_lo = 2; s->n_lossy = 0;
     }
-    PF_CUDA(cudaFree(d_table));
-    PF_CUDA(cudaFree(d_count));
-    PF_CUDA(cudaFree(d_ids));
   }
+  scratch.keep(np); scratch.keep(nm); scratch.keep(s->d_cls0);   // what the solver keeps; the rest goes with `scratch`
   s->d_pos0 = np; s->d_mat0 = nm;
   s->stage_device = device;
   s->X = nx; s->Y = ny; s->Z = nz;
@@ -1011,6 +1177,7 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
     s->d_pos0 = s->d_mat0 = s->d_cls0 = nullptr;
   }
   s->tables_dirty = true;
+  s->dif_order_built = (int)s->opt_dif_order;
   s->mesh_ready = false;   // staging consumed; setup_mesh again before re-partitioning
   s->cur = 0;
   s->srcrec_dirty = true;
@@ -1289,7 +1456,7 @@ int pfdtd_set_sources(pfdtd_solver* s, uint32_t n, const int32_t* xyz, const int
   s->src_xyz.assign(xyz, xyz + 3 * (size_t)n);
   s->src_type.assign(src_types, src_types + n);
   s->src_samples.assign((const unsigned char*)samples, (const unsigned char*)samples + (size_t)n * n_steps * esize(s));
-  s->srcrec_dirty = true;
+  s->src_dirty = true;
   return PFDTD_OK;
 }
 
@@ -1308,7 +1475,7 @@ int pfdtd_set_receivers(pfdtd_solver* s, uint32_t n, const int32_t* xyz) {
 
 int pfdtd_reserve_steps(pfdtd_solver* s, uint32_t n_steps) {
   PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
-  if (n_steps > s->rec_cap) { s->rec_cap = n_steps; s->srcrec_dirty = true; }
+  if (n_steps > s->rec_cap) s->rec_cap = n_steps;   // prepare_srcrec grows the buffers and keeps what they hold
   return PFDTD_OK;
 }
 
@@ -1323,6 +1490,7 @@ int pfdtd_enqueue_steps(pfdtd_solver* s, uint32_t first_step, uint32_t n_steps) 
   for (auto& p : s->parts) {
     for (cudaEvent_t e : p.kev) cudaEventDestroy(e);
     p.kev.clear();
+    p.kev_planes.clear();
   }
   if (s->comm && !s->ev_h0) {
     PF_CUDA(cudaSetDevice(s->parts[0].device));
@@ -1382,24 +1550,44 @@ int pfdtd_enqueue_steps(pfdtd_solver* s, uint32_t first_step, uint32_t n_steps) 
 int pfdtd_sync(pfdtd_solver* s) {
   PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
   PF_TRY(sync_all(s));
-  float total = 0, kern = 0;
-  uint32_t nk = 0;
+  if (s->d_halo_flags) {   // a halo wait that timed out (srcrec_kernels.cu halo_wait): a neighbour process never delivered
+    int err = 0;
+    PF_CUDA(cudaSetDevice(s->parts[0].device));
+    PF_CUDA(cudaMemcpy(&err, s->d_halo_flags + 6 /* HALO_ERR */, sizeof(int), cudaMemcpyDeviceToHost));
+    PF_CHECK(err == 0, PFDTD_ERR_COMM, "halo hand-over timed out: a neighbour process did not deliver its plane (results are invalid)");
+  }
+  // Update launches are timed one by one on their own streams.  A slab with neighbours runs three per step: the two
+  // one-plane edge launches (edge stream) and the interior launch (main stream), which overlap -- so the sum of all
+  // three is not a time anything waited for.  Reported: the bulk launches (everything that is not a one-plane edge
+  // launch: the dominant kernel, and what a roofline is computed from) and the edge launches separately.
+  float total = 0, bulk = 0, edge = 0;
+  uint32_t n_bulk = 0, n_edge = 0;
+  uint64_t bulk_planes = 0;
   for (auto& p : s->parts) {
     PF_CUDA(cudaSetDevice(p.device));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, p.ev_t0, p.ev_t1) == cudaSuccess) total = std::max(total, ms);
     else cudaGetLastError();
-    float ksum = 0;
+    float bsum = 0, esum = 0;
+    uint32_t nb = 0, ne = 0;
+    uint64_t planes = 0;
+    const bool has_edges = s->parts.size() > 1 || s->comm;
     for (size_t i = 0; i + 1 < p.kev.size(); i += 2) {
       float k = 0;
-      if (cudaEventElapsedTime(&k, p.kev[i], p.kev[i + 1]) == cudaSuccess) { ksum += k; nk++; }
-      else cudaGetLastError();
+      if (cudaEventElapsedTime(&k, p.kev[i], p.kev[i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+      const int pl = i / 2 < p.kev_planes.size() ? p.kev_planes[i / 2] : 0;
+      if (has_edges && pl == 1) { esum += k; ne++; }
+      else { bsum += k; nb++; planes += (uint64_t)pl; }
     }
-    kern = std::max(kern, ksum);
+    if (bsum >= bulk) { bulk = bsum; n_bulk = nb; bulk_planes = planes; }
+    if (esum >= edge) { edge = esum; n_edge = ne; }
   }
   s->last_total_ms = total;
-  s->last_kernel_ms = kern;
-  s->last_kernel_launches = nk;
+  s->last_kernel_ms = bulk;
+  s->last_kernel_launches = n_bulk;
+  s->last_edge_ms = edge;
+  s->last_edge_launches = n_edge;
+  s->last_bulk_planes = bulk_planes;
   if (s->ev_h0) {
     float h = 0;
     cudaSetDevice(s->parts[0].device);
@@ -1417,6 +1605,50 @@ int pfdtd_last_timing(pfdtd_solver* s, float* total_ms, float* update_kernel_ms,
   return PFDTD_OK;
 }
 
+int pfdtd_last_timing_detail(pfdtd_solver* s, float* bulk_kernel_ms, uint32_t* n_bulk_launches, uint64_t* bulk_planes, float* edge_kernel_ms,
+                             uint32_t* n_edge_launches) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  if (bulk_kernel_ms) *bulk_kernel_ms = s->last_kernel_ms;
+  if (n_bulk_launches) *n_bulk_launches = s->last_kernel_launches;
+  if (bulk_planes) *bulk_planes = s->last_bulk_planes;
+  if (edge_kernel_ms) *edge_kernel_ms = s->last_edge_ms;
+  if (n_edge_launches) *n_edge_launches = s->last_edge_launches;
+  return PFDTD_OK;
+}
+
+// The halo exchange alone (CudaMesh::switchHalos, cudaMesh.h:432-463), `reps` times back to back on the edge stream(s)
+// with nothing else running, timed with CUDA events on that stream: what one exchange of two planes per interface
+// costs on the link when both sides are ready.  Collective across processes (every rank must call it with the same
+// `reps`, after a barrier).  The fields are exchanged onto themselves: results do not change.
+int pfdtd_time_halo_exchange(pfdtd_solver* s, uint32_t reps, float* ms_per_exchange) {
+  PF_CHECK(s && ms_per_exchange && !s->parts.empty(), PFDTD_ERR_INVALID, "bad argument");
+  PF_CHECK(reps >= 1, PFDTD_ERR_INVALID, "reps must be >= 1");
+  *ms_per_exchange = 0.f;
+  if (s->parts.size() == 1 && !s->comm) return PFDTD_OK;
+  PF_TRY(sync_all(s));
+  Partition& p0 = s->parts[0];
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  PF_CUDA(cudaSetDevice(p0.device));
+  PF_CUDA(cudaEventCreate(&e0));
+  PF_CUDA(cudaEventCreate(&e1));
+  int rc = PFDTD_OK;
+  for (uint32_t r = 0; r <= reps && rc == PFDTD_OK; r++) {      // exchange 0 is a warm-up (connection set-up)
+    if (r == 1) { cudaSetDevice(p0.device); cudaEventRecord(e0, p0.s_edge); }
+    for (size_t k = 0; k + 1 < s->parts.size() && rc == PFDTD_OK; k++) {
+      rc = enqueue_halo_local_up(s, k, s->cur);
+      if (rc == PFDTD_OK) rc = enqueue_halo_local_down(s, k, s->cur);
+    }
+    if (rc == PFDTD_OK) rc = enqueue_halo_external(s, s->cur);
+    if (r == 0 && rc == PFDTD_OK) rc = sync_all(s);
+  }
+  if (rc == PFDTD_OK) { cudaSetDevice(p0.device); cudaEventRecord(e1, p0.s_edge); rc = sync_all(s); }
+  float ms = 0;
+  if (rc == PFDTD_OK && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *ms_per_exchange = ms / (float)reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
 int pfdtd_last_halo_ms(pfdtd_solver* s, float* halo_ms) {
   PF_CHECK(s && halo_ms, PFDTD_ERR_INVALID, "null argument");
   *halo_ms = s->last_halo_ms;
@@ -1431,11 +1663,12 @@ int pfdtd_fetch_responses(pfdtd_solver* s, void* h_response, uint32_t n_steps) {
   const size_t es = esize(s);
   if (s->n_rec) memset(h_response, 0, (size_t)s->n_rec * n_steps * es);
   for (auto& p : s->parts) {
-    if (!p.d_rec_out) continue;
+    if (!p.d_rec_out || p.rec_slots.empty()) continue;
     PF_CUDA(cudaSetDevice(p.device));
+    const uint32_t have = std::min(n_steps, p.rec_cap_alloc);   // steps reserved after the last enqueue hold nothing yet
     for (int32_t slot : p.rec_slots)
-      PF_CUDA(cudaMemcpy((char*)h_response + (size_t)slot * n_steps * es, (char*)p.d_rec_out + (size_t)slot * s->rec_cap * es,
-                         (size_t)n_steps * es, cudaMemcpyDeviceToHost));
+      PF_CUDA(cudaMemcpy((char*)h_response + (size_t)slot * n_steps * es, (char*)p.d_rec_out + (size_t)slot * p.rec_cap_alloc * es,
+                         (size_t)have * es, cudaMemcpyDeviceToHost));
   }
   return PFDTD_OK;
 }
@@ -1520,6 +1753,9 @@ int pfdtd_comm_init(pfdtd_solver* s, const uint8_t* id128, int rank, int nranks)
   PF_CHECK(s && id128, PFDTD_ERR_INVALID, "null argument");
   PF_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, PFDTD_ERR_INVALID, "bad rank %d of %d", rank, nranks);
   PF_CHECK(!s->parts.empty(), PFDTD_ERR_INVALID, "make_partition must be called before comm_init");
+  // one communicator on one device: the process owns exactly one slab (one process per GPU)
+  PF_CHECK(s->parts.size() == 1, PFDTD_ERR_INVALID, "pfdtd_comm_init needs exactly one local partition (this solver has %zu)",
+           s->parts.size());
   PF_TRY(nccl_load());
   NcclId id;
   memcpy(id.bytes, id128, 128);
@@ -1547,6 +1783,33 @@ int pfdtd_comm_init(pfdtd_solver* s, const uint8_t* id128, int rank, int nranks)
   s->nranks = nranks;
   s->srcrec_dirty = true;
   if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+  return exchange_links(s);
+}
+
+int pfdtd_comm_release(pfdtd_solver* s) {
+  PF_CHECK(s, PFDTD_ERR_INVALID, "null solver");
+  if (!s->parts.empty()) PF_TRY(sync_all(s));
+  for (auto& l : s->link) {
+    for (void*& q : l.nb_P) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    if (l.nb_flags) { cudaIpcCloseMemHandle(l.nb_flags); l.nb_flags = nullptr; }
+    l.ok = false;
+  }
+  return PFDTD_OK;
+}
+
+int pfdtd_halo_transport(pfdtd_solver* s, char* buf, size_t buflen) {
+  PF_CHECK(s && buf && buflen > 0, PFDTD_ERR_INVALID, "bad argument");
+  if (s->parts.size() > 1) {
+    bool all = s->opt_peer_stores != 0;
+    for (size_t k = 0; all && k + 1 < s->parts.size(); k++) all = can_store_to(s, k, k + 1) && can_store_to(s, k + 1, k);
+    snprintf(buf, buflen, "%s", all ? "in-process: peer-mapped stores from the edge launches" : "in-process: cudaMemcpyPeerAsync");
+  } else if (!s->comm || s->nranks == 1) {
+    snprintf(buf, buflen, "none");
+  } else {
+    const bool lo = s->rank == 0 || ipc_side(s, 0), hi = s->rank == s->nranks - 1 || ipc_side(s, 1);
+    snprintf(buf, buflen, "%s", (lo && hi) ? "peer-mapped stores from the edge launches (CUDA IPC over NVLink), flag hand-over"
+                                           : ((ipc_side(s, 0) || ipc_side(s, 1)) ? "mixed: peer-mapped stores / NCCL send-recv" : "NCCL send-recv"));
+  }
   return PFDTD_OK;
 }
 

@@ -46,6 +46,10 @@ int launch_pad_with_zeros(const uint8_t* d_old, uint8_t* d_new, uint32_t dx, uin
                           uint32_t nx, uint32_t ny, uint32_t nz, int skip_z0, cudaStream_t stream);
 int launch_translate_nodes(uint8_t* d_pos, uint8_t* d_mat, uint64_t n, int centred, unsigned long long* d_counts2,
                            cudaStream_t stream);
+// padWithZeros of both volumes + translation + counts in one pass (16 bytes per thread when nx % 16 == 0)
+int launch_prepare_nodes(const uint8_t* d_old_bid, const uint8_t* d_old_mat, uint8_t* d_pos, uint8_t* d_mat, uint32_t dx, uint32_t dy,
+                         uint32_t dz, uint32_t nx, uint32_t ny, uint32_t nz, int skip_z0, int centred, unsigned long long* d_counts2,
+                         cudaStream_t stream);
 // node classes: collect the distinct node keys (pos | mat << 8 | K12 << 16 | K8 << 20) in an open-addressing
 // table (d_table: cap slots preset to 0xffffffff), then write the class byte volume through it
 int launch_mark_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n, uint32_t air_key, uint32_t air_code, int interp,
@@ -90,6 +94,10 @@ struct UpdateArgs {
   // edge launches of a slab (exactly one plane): the freshly computed plane is also stored into this plane of the
   // neighbour slab -- its halo plane, on another GPU over NVLink when peer access exists -- by the same kernel
   void* peer_plane;
+  // ... and, when that neighbour lives in another process, the flag words of the hand-over (tma_common.cuh halo_publish)
+  int* sig_local;          // this process's flag block
+  int* sig_remote;         // the neighbour's flag word this launch publishes to (null: neighbour is in this process)
+  int sig_side;            // 0: towards the lower neighbour, 1: towards the upper one
   cudaStream_t stream;
 };
 
@@ -138,6 +146,9 @@ struct SrcRecArgs {
   int n_src; const int64_t* src_elem; const int32_t* src_type; const int32_t* src_slot; const void* src_samples; int64_t src_stride;
   int* d_step;                   // device step counter n: record slot n-1 (if n>0 && do_record), inject sample n (if do_inject)
   int do_record, do_inject, soft_accumulate, advance;
+  // wait, before anything else, until the neighbour processes have delivered the halo planes of the previous step
+  const int* halo_flags;         // this process's flag block (tma_common.cuh) or null
+  int wait_lo, wait_hi;
   cudaStream_t stream;
 };
 int launch_srcrec(const SrcRecArgs& a);

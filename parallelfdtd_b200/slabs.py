@@ -4,8 +4,9 @@ The reference splits the domain into z-slabs with one-slice halos inside ONE pro
 (CudaMesh::getPartitionIndexing / makePartition / switchHalos, reference
 src/kernels/cudaMesh.h:280-307, 648-751, 432-463).  Here every rank owns exactly the slab the
 reference would give partition `rank` of `world` partitions -- same first slice, same size, same
-halo planes -- and the per-step exchange of one plane each way runs over NVLink (NCCL
-point-to-point inside libpfdtd_b200.so, overlapped with the interior update).  torch.distributed
+halo planes -- and the per-step exchange of one plane each way runs over NVLink: the edge launch of a
+slab stores its plane straight into the neighbour process's halo plane through a CUDA-IPC mapping (NCCL
+point-to-point where that mapping is not available), overlapped with the interior update.  torch.distributed
 is used only to hand the 128-byte NCCL id to every rank, for barriers, and to merge the
 receiver responses (each receiver is recorded by the first slab that contains its slice,
 cudaMesh.h:251-266).
@@ -127,6 +128,7 @@ class SlabSolver:
         s.setup_mesh(bid, mat, block, element_type, dtype, params, materials)
         s.make_partition(1, [device])
         self.solver = s
+        self._connected = False
         self._rec_z: List[int] = []
 
     def connect(self, uid: bytes | None = None) -> bytes | None:
@@ -140,6 +142,7 @@ class SlabSolver:
             uid = self.capi.comm_unique_id() if self.rank == 0 else None
             uid = broadcast_bytes(uid, 128, 0)
         self.solver.comm_init(uid, self.rank, self.world)
+        self._connected = True
         dist.barrier()
         return uid
 
@@ -158,4 +161,10 @@ class SlabSolver:
         return merge_responses(local, self._rec_z, self.plan, self.rank)
 
     def close(self):
+        """Collective when world > 1: every rank first unmaps its neighbours' slabs (CUDA IPC), and only after all have
+        done so does any rank free its own (include/pfdtd.h, pfdtd_comm_release)."""
+        if self.world > 1 and self._connected:
+            import torch.distributed as dist
+            self.solver.comm_release()
+            dist.barrier()
         self.solver.close()

@@ -54,12 +54,19 @@ WORKER = textwrap.dedent('''
         double = case["double"]
         Z, Y, X = case["bid"].shape
         prm = oracle.params(fc.LAM, case["octave"], double)
-        for overlap in (1, 0):
+        # halo transports: peer-mapped stores from the edge launches (CUDA IPC, the default), NCCL send/recv, no overlap
+        for overlap, peer in ((1, 1), (1, 0), (0, 1)):
             ss = slabs.SlabSolver(capi, (X, Y, Z), lambda a, b: (case["bid"][a:b], case["mat"][a:b]), block=case["block"],
                                   element_type=case["update_type"], dtype=capi.F64 if double else capi.F32, params=prm,
                                   materials=case["materials"], rank=rank, world=world, device=lr,
-                                  options=[(capi.OPT_OVERLAP, overlap)])
+                                  options=[(capi.OPT_OVERLAP, overlap), (capi.OPT_PEER_STORES, peer)])
             ss.connect()
+            transport = ss.solver.halo_transport()
+            thin = min(ss.plan.size(r) for r in range(world)) - 2 < 4          # a slab too thin to split keeps NCCL on its interfaces
+            if overlap and peer and not thin and os.environ.get("PFDTD_EXPECT_IPC", "1") == "1":
+                assert "peer-mapped" in transport, transport
+            if not (overlap and peer):
+                assert "peer-mapped" not in transport, transport
             src = np.asarray(case["sources"], dtype=np.int32).reshape(-1, 6)
             ss.set_sources(src[:, :3], src[:, 3], fc.source_table(case)[:, :steps])
             ss.set_receivers(case["receivers"])
@@ -77,7 +84,7 @@ WORKER = textwrap.dedent('''
             if rank == 0:
                 ref, _, _ = fc.run_oracle(case, n_parts=1)
                 assert np.abs(ref).max() > 0
-                assert np.array_equal(merged, ref[:, :steps]), (name, overlap, float(np.abs(merged - ref[:, :steps]).max()))
+                assert np.array_equal(merged, ref[:, :steps]), (name, overlap, peer, transport, float(np.abs(merged - ref[:, :steps]).max()))
             dist.barrier()
     dist.destroy_process_group()
     print("MP_OK", rank)
