@@ -63,8 +63,8 @@ UNPINNED = [(0, False, 2), (0, True, 2), (2, False, 2), (3, False, 0), (3, False
 @pytest.mark.parametrize("update_type,double,order", UNPINNED)
 def test_config2_full_size_filter_and_interpolated_variants_against_the_cpu_oracle(capi, gpu, update_type, double, order):
     steps = 100
-    src = [(40, 36, 44, 0, 3, 0)]
-    rec = [(5, 40, 40), (40, 2, 44), (60, 60, 1), (1, 1, 1), (90, 80, 70), (2, 30, 2)]     # faces, an edge, a corner, open air
+    src = [(24, 20, 28, 0, 3, 0)]                                                            # 100 steps reach ~57 voxels
+    rec = [(5, 20, 28), (24, 2, 30), (30, 26, 1), (1, 1, 1), (50, 40, 45), (2, 14, 2)]       # faces, a corner, open air, an edge
     case = fc.make_case(f"c2_512_ut{update_type}_dif{order}", DIMS, update_type, double, steps, 6, 1, src, rec, input_data=[_pulse(steps, 12.0, 3.0)])
     if order:
         case["dif_order"] = order
