@@ -57,7 +57,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        _lib = load_library()
+        _lib = load_library(os.environ.get("PFDTD_LIB_PATH", LIB_PATH))   # override: A/B builds of the same ABI (tools/)
     return _lib
 
 

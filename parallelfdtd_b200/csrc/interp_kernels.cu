@@ -54,12 +54,13 @@ __device__ __forceinline__ void load_plane(const T* __restrict__ pt, int r, int 
 }  // namespace
 
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: TY consumer warps (one tile row each) + 1 producer warp
-template <typename T, bool HAS_D3, int TY, int NST, int DIF>
+template <typename T, bool HAS_D3, int TY, int NST, int DIF, bool WIDE>
 __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (TY == 7 ? (NST >= 6 ? 80 : 64) : (TY == 8 ? 72 : 56)) : (TY == 7 ? 128 : 96))
     fdtd_update_interp_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                            const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
-                           T* __restrict__ Pn, T d1, T d2, T d3, T d4, int X, int Y, int z_begin, int z_end, int chunk,
-                           const DifArgs<T> dif, T* __restrict__ peer, int* __restrict__ sig_local, int* __restrict__ sig_remote, int sig_side) {
+                           T* __restrict__ Pn, T d1, T d2, T d3, T d4, int X, int Y, int z_begin, int z_end, int chunk, int hints,
+                           const DifArgs<T> dif, const WideArgs<T> wide, T* __restrict__ peer, int* __restrict__ sig_local,
+                           int* __restrict__ sig_remote, int sig_side) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -67,12 +68,15 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
   __shared__ __align__(8) uint64_t bar_empty[NST];
   __shared__ ClassEntry<T> s_table[256];
   __shared__ DifEntry<T> s_dif[DIF ? 64 : 1];
+  __shared__ DifStash<T> s_stash[(DIF && PFDTD_DIF_STASH == 1) ? NW * 32 : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  int cby, cbz;
+  cta_tile(hints & 4, cby, cbz);
   const int x0 = blockIdx.x * TX;
-  const int y0 = blockIdx.y * TY;
-  const int z_lo = z_begin + blockIdx.z * chunk;
+  const int y0 = cby * TY;
+  const int z_lo = z_begin + cbz * chunk;
   const int z_hi = min(z_lo + chunk, z_end);
   const int n = z_hi - z_lo;
   if (n <= 0) return;
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
   // filter boundaries: entries and prefetched states of this warp's row (update_math.cuh DifRow), started before the
   // first wait on the pipeline so that the entry -> state round trips overlap the first planes' TMA loads
   constexpr int DMO = DIF ? DIF : 1;
-  DifRow<T, DMO> drow;
+  DifRow<T, DMO, WIDE> drow;
   if (DIF) drow.start(dif, z_lo, z_hi, gy, Y, lane);
   Plane3<T> pm, pc, pp;                      // planes z-1, z, z+1
   {
@@ -152,13 +156,14 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
       } else {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const ClassEntry<T> ce = s_table[(pw >> (8 * q)) & 0xffu];
+          const ClassEntry<T> ce = class_entry<T, WIDE>(s_table, wide, (pw >> (8 * q)) & 0xffu, (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx + q);
           res.v[q] = voxel_interp<T, HAS_D3>(ce.c0, ce.c1, ce.c2, pc.c[q], pc.a4[q], pc.g4[q], pm.c[q], pm.a4[q], pm.g4[q], pp.c[q],
                                              pp.a4[q], pp.g4[q], old.v[q], d1, d2, d3);
         }
       }
     }
-    if (DIF) drow.apply(j, res.v, old.v, pw, active, lane, dif, s_dif);
+    if (DIF) drow.apply(j, res.v, old.v, pw, active, lane, dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0),
+                        (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx);
     if (active) stg4(Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx, res);
     // the store above consumed everything read from stage s2 (and, at j == 0, from the two prologue stages)
     __syncwarp();
@@ -166,7 +171,7 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
       mbar_arrive(&bar_empty[s2]);
       if (j == 0) { mbar_arrive(&bar_empty[0]); mbar_arrive(&bar_empty[1 % NST]); }
     }
-    if (DIF) drow.next(dif, j, n, z_lo, z_hi, gy, Y, lane);
+    if (DIF) drow.next(dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0), Pn + (int64_t)gy * X + x0, XY, j, n, z_lo, z_hi, gy, Y, lane);
     pm = pc;
     pc = pp;
   }
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
 template <typename T, bool HAS_D3>
 __global__ void __launch_bounds__(128) fdtd_update_interp_plain(const uint8_t* __restrict__ cls, const ClassEntry<T>* __restrict__ table,
                                                                 const T* __restrict__ P, T* __restrict__ Pn, T d1, T d2, T d3, int X,
-                                                                int Y, int z_begin) {
+                                                                int Y, int z_begin, const WideArgs<T> wide) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int z = z_begin + blockIdx.z;
@@ -205,15 +210,15 @@ __global__ void __launch_bounds__(128) fdtd_update_interp_plain(const uint8_t* _
     g4[k] = interp_g4<T>(at(x - 1, y - 1, zz), at(x + 1, y - 1, zz), at(x - 1, y + 1, zz), at(x + 1, y + 1, zz));
   }
   const int64_t cur = (int64_t)z * XY + (int64_t)y * X + x;
-  const ClassEntry<T> ce = table[cls[cur]];
+  const ClassEntry<T> ce = (wide.mat != nullptr ? class_entry<T, true>(table, wide, cls[cur], cur) : table[cls[cur]]);
   Pn[cur] = voxel_interp<T, HAS_D3>(ce.c0, ce.c1, ce.c2, c[1], a4[1], g4[1], c[0], a4[0], g4[0], c[2], a4[2], g4[2], Pn[cur], d1, d2, d3);
 }
 
 namespace {
 
-template <typename T, bool HAS_D3, int TY, int NST, int DIF>
+template <typename T, bool HAS_D3, int TY, int NST, int DIF, bool WIDE = false>
 int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupancy_out) {
-  auto kern = fdtd_update_interp_tma<T, HAS_D3, TY, NST, DIF>;
+  auto kern = fdtd_update_interp_tma<T, HAS_D3, TY, NST, DIF, WIDE>;
   const int smem = NST * TileGeom<T, TY>::STAGE_BYTES;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -231,7 +236,7 @@ int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occup
   dim3 grid((a.X + TX - 1) / TX, (a.Y + TY - 1) / TY, (nplanes + chunk - 1) / chunk);
   const UpdConst<T> c = make_const<T>(a);
   kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.cls, (const ClassEntry<T>*)a.class_table, a.n_classes, (T*)a.Pn, c.d[0],
-                                          c.d[1], c.d[2], c.d[3], a.X, a.Y, a.z_begin, a.z_end, chunk, make_dif<T>(a),
+                                          c.d[1], c.d[2], c.d[3], a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints, make_dif<T>(a), make_wide<T>(a),
                                           (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr, a.sig_local,
                                           (a.z_end - a.z_begin == 1 && a.peer_plane) ? a.sig_remote : nullptr, a.sig_side);
   PF_CUDA(cudaGetLastError());
@@ -241,8 +246,20 @@ int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occup
 template <typename T, bool HAS_D3>
 int dispatch_interp(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
   // tile variants shared with the 7-point kernel: only the one-row-per-warp shapes apply here
-  if (a.dif_order > 0) {   // filter boundaries: one kernel per order on the 128x7 shape; fp32 six stages, fp64 five
-    constexpr int DTY = 7, DNST = sizeof(T) == 4 ? 6 : 5;   // fp32: 80 registers, three CTAs per SM
+  // filter boundaries: one kernel per order on the 128x7 shape; fp32 six stages, fp64 five; wide meshes run on it too
+  constexpr int DTY = 7, DNST = sizeof(T) == 4 ? 6 : 5;   // fp32: 80 registers, three CTAs per SM
+  if (a.wide) {
+    switch (a.dif_order) {
+      case 0: return launch_interp_t<T, HAS_D3, DTY, DNST, 0, true>(a, m, chunk, occ);
+      case 1: return launch_interp_t<T, HAS_D3, DTY, DNST, 1, true>(a, m, chunk, occ);
+      case 2: return launch_interp_t<T, HAS_D3, DTY, DNST, 2, true>(a, m, chunk, occ);
+      case 3: return launch_interp_t<T, HAS_D3, DTY, DNST, 3, true>(a, m, chunk, occ);
+      case 4: return launch_interp_t<T, HAS_D3, DTY, DNST, 4, true>(a, m, chunk, occ);
+    }
+    set_error("filter order %d is not supported", a.dif_order);
+    return PFDTD_ERR_INVALID;
+  }
+  if (a.dif_order > 0) {
     switch (a.dif_order) {
       case 1: return launch_interp_t<T, HAS_D3, DTY, DNST, 1>(a, m, chunk, occ);
       case 2: return launch_interp_t<T, HAS_D3, DTY, DNST, 2>(a, m, chunk, occ);
@@ -280,12 +297,12 @@ int launch_update_interp_plain(const UpdateArgs& a) {
   const bool d3 = a.dcoef[2] != 0.0;
   if (a.dtype == PFDTD_F32) {
     const UpdConst<float> c = make_const<float>(a);
-    if (d3) fdtd_update_interp_plain<float, true><<<grid, block, 0, a.stream>>>(a.cls, (const ClassEntry<float>*)a.class_table, (const float*)a.P, (float*)a.Pn, c.d[0], c.d[1], c.d[2], a.X, a.Y, a.z_begin);
-    else fdtd_update_interp_plain<float, false><<<grid, block, 0, a.stream>>>(a.cls, (const ClassEntry<float>*)a.class_table, (const float*)a.P, (float*)a.Pn, c.d[0], c.d[1], c.d[2], a.X, a.Y, a.z_begin);
+    if (d3) fdtd_update_interp_plain<float, true><<<grid, block, 0, a.stream>>>(a.cls, (const ClassEntry<float>*)a.class_table, (const float*)a.P, (float*)a.Pn, c.d[0], c.d[1], c.d[2], a.X, a.Y, a.z_begin, make_wide<float>(a));
+    else fdtd_update_interp_plain<float, false><<<grid, block, 0, a.stream>>>(a.cls, (const ClassEntry<float>*)a.class_table, (const float*)a.P, (float*)a.Pn, c.d[0], c.d[1], c.d[2], a.X, a.Y, a.z_begin, make_wide<float>(a));
   } else {
     const UpdConst<double> c = make_const<double>(a);
-    if (d3) fdtd_update_interp_plain<double, true><<<grid, block, 0, a.stream>>>(a.cls, (const ClassEntry<double>*)a.class_table, (const double*)a.P, (double*)a.Pn, c.d[0], c.d[1], c.d[2], a.X, a.Y, a.z_begin);
-    else fdtd_update_interp_plain<double, false><<<grid, block, 0, a.stream>>>(a.cls, (const ClassEntry<double>*)a.class_table, (const double*)a.P, (double*)a.Pn, c.d[0], c.d[1], c.d[2], a.X, a.Y, a.z_begin);
+    if (d3) fdtd_update_interp_plain<double, true><<<grid, block, 0, a.stream>>>(a.cls, (const ClassEntry<double>*)a.class_table, (const double*)a.P, (double*)a.Pn, c.d[0], c.d[1], c.d[2], a.X, a.Y, a.z_begin, make_wide<double>(a));
+    else fdtd_update_interp_plain<double, false><<<grid, block, 0, a.stream>>>(a.cls, (const ClassEntry<double>*)a.class_table, (const double*)a.P, (double*)a.Pn, c.d[0], c.d[1], c.d[2], a.X, a.Y, a.z_begin, make_wide<double>(a));
   }
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;

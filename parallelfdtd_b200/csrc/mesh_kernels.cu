@@ -206,13 +206,13 @@ int launch_prepare_nodes(const uint8_t* d_old_bid, const uint8_t* d_old_mat, uin
 }
 
 // ---- node classes ---------------------------------------------------------------------------------
-// key = pos | mat << 8 | K12 << 16 | K8 << 20.  K12 / K8 = number of non-solid voxels among the 12 edge- and
+// key = pos | mat << 8 | K12 << 16 | K8 << 20 (mat == nullptr: without the material -- the position classes of wide meshes).  K12 / K8 = number of non-solid voxels among the 12 edge- and
 // 8 corner-neighbours; only the interpolated (27-point) schemes need them, the 7-point schemes use 0.
 // Nodes whose admittance term vanishes (forward byte with K = 6 / centred byte without direction flags)
 // are normalised to material 0; solid nodes already carry material 0.
 __device__ __forceinline__ uint32_t node_key(const uint8_t* __restrict__ pos, const uint8_t* __restrict__ mat, uint64_t i, uint32_t p,
                                              uint32_t air_code, int interp, uint32_t X, uint32_t Y, uint32_t Z) {
-  uint32_t key = (p == air_code) ? p : (p | ((uint32_t)mat[i] << 8));
+  uint32_t key = (p == air_code || mat == nullptr) ? p : (p | ((uint32_t)mat[i] << 8));   // mat == nullptr: position classes only
   if (interp) {
     const int x = (int)(i % X), y = (int)((i / X) % Y), z = (int)(i / ((uint64_t)X * Y));
     uint32_t k12 = 0, k8 = 0;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256) classes16_kernel(const uint8_t* __restric
       out[0] = out[1] = out[2] = out[3] = 0x01010101u;           // class 1
     }
     if (!settled) {
-      const uint4 mw = reinterpret_cast<const uint4*>(mat)[c];
+      const uint4 mw = mat != nullptr ? reinterpret_cast<const uint4*>(mat)[c] : make_uint4(0u, 0u, 0u, 0u);
       uint32_t last_key = 0xffffffffu, last_id = 0;
 #pragma unroll 1
       for (int i = 0; i < 16; i++) {

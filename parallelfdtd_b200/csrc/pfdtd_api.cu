@@ -88,6 +88,10 @@ struct Partition {
   void* dif_state = nullptr;            // [dif_nb][P]
   uint32_t* dif_rowbase = nullptr;      // [size][Y][ceil(X/128)]
   void* dif_table = nullptr;            // DifEntry<T>[n_lossy]
+  // wide meshes: entries per (lossy position class, material), keys = position key | material << 8
+  uint32_t* d_wide_keys = nullptr;      // [n_lossy][n_unique]
+  void* wide_class_table = nullptr;     // ClassEntry<T>[n_lossy][n_unique]
+  void* wide_dif_table = nullptr;       // DifEntry<T>[n_lossy][n_unique]
   uint32_t dif_nb = 0;
   bool owns_nodes = true;
   void* P[2] = {nullptr, nullptr};
@@ -96,7 +100,7 @@ struct Partition {
   cudaEvent_t ev_src = nullptr, ev_int = nullptr, ev_edge = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   bool use_tma = false;
   TmaMaps maps[2];                      // maps[c]: current field = P[c], overwritten field = P[1-c]
-  TmaConfig cfg_full{0, 1}, cfg_int{0, 1}, cfg_edge{0, 1};
+  TmaConfig cfg_full{0, 1, 0}, cfg_int{0, 1, 0}, cfg_edge{0, 1, 0};
   int* d_step = nullptr;                // [0] step counter, [1] first recordable step
   // sources / receivers that live in this partition
   int n_src = 0, n_rec = 0;
@@ -137,6 +141,7 @@ struct pfdtd_solver {
   double dcoef[4] = {0, 0, 0, 0};        // interpolated schemes: d1..d4
   bool dcoef_user = false;
   bool tables_dirty = true;
+  bool wide = false;                      // class byte = position class only; lossy voxels look their material up (WideArgs)
   uint32_t dif_lo = 2, n_lossy = 0;       // class ids >= dif_lo are lossy boundary classes
   std::vector<Partition> parts;
   int cur = 0;                           // index of the current field in Partition::P
@@ -211,6 +216,7 @@ static int free_partitions(pfdtd_solver* s) {
     if (p.owns_nodes) { cudaFree(p.pos); cudaFree(p.mat); cudaFree(p.cls); }
     cudaFree(p.class_table); cudaFree(p.d_class_keys);
     cudaFree(p.dif_state); cudaFree(p.dif_rowbase); cudaFree(p.dif_table);
+    cudaFree(p.d_wide_keys); cudaFree(p.wide_class_table); cudaFree(p.wide_dif_table);
     cudaFree(p.P[0]); cudaFree(p.P[1]); cudaFree(p.materials); cudaFree(p.d_step);
     cudaFree(p.d_src_elem); cudaFree(p.d_src_type); cudaFree(p.d_src_slot); cudaFree(p.d_rec_elem); cudaFree(p.d_rec_slot);
     cudaFree(p.d_src_samples); cudaFree(p.d_rec_out);
@@ -329,6 +335,9 @@ static UpdateArgs make_update_args(pfdtd_solver* s, Partition& p, int z_begin, i
   a.mat = p.mat;
   a.cls = p.cls;
   a.class_table = p.class_table;
+  a.wide = s->wide;
+  a.wide_class_table = p.wide_class_table;
+  a.wide_dif_table = p.wide_dif_table;
   a.n_classes = (int)s->class_keys.size();
   a.tma_hints = (int)s->opt_tma_hints;
   a.peer_plane = nullptr;
@@ -365,6 +374,11 @@ static int ensure_class_tables(pfdtd_solver* s) {
     a.dif_order = (int)s->opt_dif_order;     // class entries take b0 as the scalar admittance when filters are on
     PF_TRY(build_class_table(a, p.d_class_keys, (int)s->class_keys.size(), p.class_table));
     if (p.dif_table) PF_TRY(build_dif_table(a, p.d_class_keys + s->dif_lo, (int)s->n_lossy, p.dif_table));
+    if (p.wide_class_table) {   // the same builders over the (class, material) key list
+      const int nw = (int)(s->n_lossy * s->n_unique);
+      PF_TRY(build_class_table(a, p.d_wide_keys, nw, p.wide_class_table));
+      if (p.wide_dif_table) PF_TRY(build_dif_table(a, p.d_wide_keys, nw, p.wide_dif_table));
+    }
     PF_CUDA(cudaStreamSynchronize(p.s_main));
     s->launch_count++;
   }
@@ -896,7 +910,7 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
     const uint32_t air_code = s->scheme == SCH_CENTRED ? 0x80u : 0x86u;
     const int interp = s->scheme == SCH_INTERP;
     const uint32_t air_key = interp ? (air_code | (12u << 16) | (8u << 20)) : air_code;
-    const uint32_t cap = 4096;
+    const uint32_t cap = 65536;
     uint32_t* d_table = nullptr;
     uint32_t* d_count = nullptr;
     uint8_t* d_ids = nullptr;
@@ -906,29 +920,35 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
     scratch.ptrs.push_back(d_count);
     PF_CUDA(cudaMalloc(&d_ids, cap));
     scratch.ptrs.push_back(d_ids);
-    PF_CUDA(cudaMemset(d_table, 0xff, cap * sizeof(uint32_t)));
-    PF_CUDA(cudaMemset(d_count, 0, sizeof(uint32_t)));
-    PF_TRY(launch_mark_classes(np, nm, n_new, air_key, air_code, interp, nx, ny, nz, d_table, cap, d_count, 0));
-    std::vector<uint32_t> table(cap);
-    uint32_t count = 0;
-    PF_CUDA(cudaMemcpy(table.data(), d_table, cap * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    PF_CUDA(cudaMemcpy(&count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    s->class_keys.clear();
-    s->class_keys.push_back(0);          // class 0: solid
-    s->class_keys.push_back(air_key);    // class 1: air
-    std::vector<uint32_t> found;
-    for (uint32_t k : table) if (k != 0xffffffffu) found.push_back(k);
-    // lossless classes first, lossy boundary classes (K < 6 / a direction flag set) last: "is a filter boundary"
-    // becomes one unsigned compare on the class byte
+    // Narrow first: one class per (position, material) pair.  When that needs more than a byte can name (or more lossy
+    // classes than the kernels' shared filter table holds), classes are formed from the position part alone and the
+    // material is looked up per boundary voxel (update_math.cuh WideArgs) -- "wide" mode.
     const bool centred_bytes = s->scheme == SCH_CENTRED;
     auto lossy = [centred_bytes](uint32_t k) { const uint32_t p = k & 0xffu; return centred_bytes ? (p & 7u) != 0u : (p & 0x7fu) < 6u; };
-    std::sort(found.begin(), found.end(), [&](uint32_t a, uint32_t b) { return lossy(a) != lossy(b) ? lossy(b) : a < b; });
-    uint32_t n_lossless = 0;
-    for (uint32_t k : found) { s->class_keys.push_back(k); if (!lossy(k)) n_lossless++; }
-    s->dif_lo = 2 + n_lossless;
-    s->n_lossy = (uint32_t)found.size() - n_lossless;
     s->d_cls0 = nullptr;
-    if (count + 2 <= 256 && count < cap / 2) {
+    s->wide = false;
+    s->class_keys.assign({0u, air_key});                // class 0: solid, class 1: air
+    s->dif_lo = 2; s->n_lossy = 0;
+    for (int attempt = 0; attempt < 2 && s->d_cls0 == nullptr; attempt++) {
+      const uint8_t* key_mat = attempt == 0 ? nm : nullptr;
+      PF_CUDA(cudaMemset(d_table, 0xff, cap * sizeof(uint32_t)));
+      PF_CUDA(cudaMemset(d_count, 0, sizeof(uint32_t)));
+      PF_TRY(launch_mark_classes(np, key_mat, n_new, air_key, air_code, interp, nx, ny, nz, d_table, cap, d_count, 0));
+      s->launch_count++;
+      std::vector<uint32_t> table(cap);
+      uint32_t count = 0;
+      PF_CUDA(cudaMemcpy(table.data(), d_table, cap * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      PF_CUDA(cudaMemcpy(&count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      std::vector<uint32_t> found;
+      for (uint32_t k : table) if (k != 0xffffffffu) found.push_back(k);
+      // lossless classes first, lossy boundary classes (K < 6 / a direction flag set) last: "is a filter boundary"
+      // becomes one unsigned compare on the class byte
+      std::sort(found.begin(), found.end(), [&](uint32_t a, uint32_t b) { return lossy(a) != lossy(b) ? lossy(b) : a < b; });
+      uint32_t n_lossless = 0;
+      for (uint32_t k : found) if (!lossy(k)) n_lossless++;
+      const uint32_t n_lossy = (uint32_t)found.size() - n_lossless;
+      // (the shared filter table only matters when filters are on: PFDTD_OPT_DIF_ORDER is read here, set it before setup_mesh)
+      if (!(count + 2 <= 256 && count < cap / 2 && (n_lossy <= 64 || s->opt_dif_order == 0))) continue;       // does not fit this way
       std::vector<uint8_t> ids(cap, 0);
       for (uint32_t slot = 0; slot < cap; slot++)
         if (table[slot] != 0xffffffffu)
@@ -936,12 +956,13 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
       PF_CUDA(cudaMemcpy(d_ids, ids.data(), cap, cudaMemcpyHostToDevice));
       PF_CUDA(cudaMalloc(&s->d_cls0, n_new));
       scratch.ptrs.push_back(s->d_cls0);
-      PF_TRY(launch_assign_classes(np, nm, n_new, air_key, air_code, interp, nx, ny, nz, d_table, d_ids, cap, s->d_cls0, 0));
+      PF_TRY(launch_assign_classes(np, key_mat, n_new, air_key, air_code, interp, nx, ny, nz, d_table, d_ids, cap, s->d_cls0, 0));
       PF_CUDA(cudaDeviceSynchronize());
-      s->launch_count += 2;
-    } else {
-      s->class_keys.resize(2);
-      s->dif_lo = 2; s->n_lossy = 0;
+      s->launch_count++;
+      for (uint32_t k : found) s->class_keys.push_back(k);
+      s->dif_lo = 2 + n_lossless;
+      s->n_lossy = n_lossy;
+      s->wide = attempt == 1;
     }
   }
   scratch.keep(np); scratch.keep(nm); scratch.keep(s->d_cls0);   // what the solver keeps; the rest goes with `scratch`
@@ -1099,6 +1120,15 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       PF_CUDA(cudaMalloc(&p.class_table, nc * class_entry_bytes(s->dtype)));
       PF_CUDA(cudaMalloc(&p.d_class_keys, nc * sizeof(uint32_t)));
       PF_CUDA(cudaMemcpy(p.d_class_keys, s->class_keys.data(), nc * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      if (s->wide && s->n_lossy) {
+        std::vector<uint32_t> wk((size_t)s->n_lossy * s->n_unique);
+        for (uint32_t i = 0; i < s->n_lossy; i++)
+          for (uint32_t m = 0; m < s->n_unique; m++) wk[(size_t)i * s->n_unique + m] = s->class_keys[s->dif_lo + i] | (m << 8);
+        PF_CUDA(cudaMalloc(&p.d_wide_keys, wk.size() * sizeof(uint32_t)));
+        PF_CUDA(cudaMemcpy(p.d_wide_keys, wk.data(), wk.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        PF_CUDA(cudaMalloc(&p.wide_class_table, wk.size() * class_entry_bytes(s->dtype)));
+        if (s->opt_dif_order > 0) PF_CUDA(cudaMalloc(&p.wide_dif_table, wk.size() * dif_entry_bytes(s->dtype)));
+      }
     }
     for (int b = 0; b < 2; b++) {
       PF_CUDA(cudaMalloc(&p.P[b], nelem * es));
@@ -1130,7 +1160,9 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       PF_CHECK(s->opt_dif_order <= PFDTD_DIF_MAX_ORDER_HOST, PFDTD_ERR_INVALID, "filter order %lld > %d", (long long)s->opt_dif_order,
                PFDTD_DIF_MAX_ORDER_HOST);
       PF_CHECK(p.use_tma, PFDTD_ERR_INVALID, "filter (DIF) boundaries need the TMA kernel (X %% 16 == 0 and <= 256 node classes)");
-      PF_CHECK(s->n_lossy <= 64, PFDTD_ERR_INVALID, "filter (DIF) boundaries support <= 64 lossy node classes, mesh has %u", s->n_lossy);
+      PF_CHECK(s->n_lossy <= 64, PFDTD_ERR_INVALID,
+               "filter (DIF) boundaries: %u lossy node classes do not fit the kernels' table of 64 -- set PFDTD_OPT_DIF_ORDER before "
+               "pfdtd_setup_mesh so that the mesh is classified by position and material separately", s->n_lossy);
       const int segs = ((int)s->X + 127) / 128;
       const size_t n_seg = (size_t)p.size * s->Y * segs;
       // per-segment counts -> entries, on the device (three small kernels); only the total comes back
@@ -1160,11 +1192,11 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
     }
     if (p.use_tma) {
       int64_t want_tile = s->opt_tma_tile;
-      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->opt_dif_order, (int)s->X, (int)s->Y, nplanes, p.device, want_tile, s->opt_tma_chunk,
+      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->opt_dif_order, s->wide, (int)s->X, (int)s->Y, nplanes, p.device, want_tile, s->opt_tma_chunk,
                              &p.cfg_full));
-      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->opt_dif_order, (int)s->X, (int)s->Y, std::max(1, nplanes - 2), p.device,
+      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->opt_dif_order, s->wide, (int)s->X, (int)s->Y, std::max(1, nplanes - 2), p.device,
                              p.cfg_full.tile + 1, s->opt_tma_chunk, &p.cfg_int));
-      p.cfg_edge = TmaConfig{p.cfg_full.tile, 1};
+      p.cfg_edge = TmaConfig{p.cfg_full.tile, 1, p.cfg_full.occupancy};
       for (int c = 0; c < 2; c++)
         PF_TRY(tma_encode_maps(&p.maps[c], s->dtype, p.cfg_full.tile, p.P[c], p.P[1 - c], p.cls, (int)s->X, (int)s->Y, (int)p.size));
     }
@@ -1821,8 +1853,9 @@ int pfdtd_kernel_name(pfdtd_solver* s, char* buf, size_t buflen) {
   const char* sch = s->scheme == SCH_CENTRED ? "centred" : s->scheme == SCH_INTERP ? (s->dcoef[2] != 0 ? "interp27+corners" : "interp27") : "forward";
   const char* fam = s->scheme == SCH_INTERP ? "fdtd_update_interp" : "fdtd_update";
   if (p.use_tma)
-    snprintf(buf, buflen, "%s_tma<%s,%s> tile %s chunk %d", fam, s->dtype == PFDTD_F32 ? "f32" : "f64", sch,
-             tma_tile_name(s->dtype, p.cfg_full.tile), p.cfg_full.chunk);
+    snprintf(buf, buflen, "%s_tma<%s,%s> tile %s chunk %d, %d CTAs/SM%s", fam, s->dtype == PFDTD_F32 ? "f32" : "f64", sch,
+             tma_tile_name(s->dtype, p.cfg_full.tile), p.cfg_full.chunk, p.cfg_full.occupancy,
+             s->wide ? ", position classes x material table" : "");
   else
     snprintf(buf, buflen, "%s_plain<%s,%s>", fam, s->dtype == PFDTD_F32 ? "f32" : "f64", sch);
   return PFDTD_OK;

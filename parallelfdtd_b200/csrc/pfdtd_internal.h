@@ -73,6 +73,10 @@ struct UpdateArgs {
   const uint8_t* cls;      // node class byte volume (TMA kernel)
   const void* class_table; // device ClassEntry<T>[n_classes]
   int n_classes;
+  // wide meshes (update_math.cuh WideArgs): per (lossy position class, material) tables in global memory; null = narrow
+  bool wide;
+  const void* wide_class_table;  // ClassEntry<T>[n_lossy][n_unique]
+  const void* wide_dif_table;    // DifEntry<T>[n_lossy][n_unique]
   int tma_hints;           // bit0: evict_first on once-read operands, bit1: evict_last on P
   const void* P;           // current field (slab base)
   void* Pn;                // past field, overwritten with the next field
@@ -103,7 +107,7 @@ struct UpdateArgs {
 
 enum { KERNEL_AUTO = 0, KERNEL_TMA = 1, KERNEL_PLAIN = 2 };
 
-struct TmaConfig { int tile; int chunk; };
+struct TmaConfig { int tile; int chunk; int occupancy = 0; /* resident CTAs per SM (occupancy API) */ };
 
 bool tma_supported(int X, int Y, int dtype);
 int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void* Pold, const uint8_t* cls, int X, int Y, int nz);
@@ -119,8 +123,8 @@ int launch_count_dif_segments(const uint8_t* d_cls, int X, int Y, int nz, uint32
 // d_col_scratch: n_cols words
 int launch_build_dif_entries(const uint32_t* d_counts, int n_cols, int nz, uint32_t* d_col_scratch, unsigned long long* d_nb,
                              uint32_t* d_entries, cudaStream_t stream);
-int tma_pick_config(int dtype, int scheme, int dif_order, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk,
-                    TmaConfig* out);
+int tma_pick_config(int dtype, int scheme, int dif_order, bool wide, int X, int Y, int nplanes, int device, int64_t opt_tile,
+                    int64_t opt_chunk, TmaConfig* out);
 int launch_update_tma(const UpdateArgs& a, const TmaMaps& maps, const TmaConfig& cfg);
 int launch_update_plain(const UpdateArgs& a);
 // 27-point kernels (interp_kernels.cu); the TMA variant shares TmaMaps / TmaConfig with the 7-point one

@@ -142,10 +142,12 @@ __device__ __forceinline__ void stg4(double* p, const V4<double>& o) {
 enum : int { HALO_FROM_LO = 0, HALO_FROM_HI = 1, HALO_SEQ = 2, HALO_CTR = 4, HALO_ERR = 6, HALO_FLAG_INTS = 8 };
 
 // Called by every consumer thread of an edge launch after its peer stores.  `side`: 0 = towards the lower neighbour.
+// One system-scope fence per CTA (by thread 0, after the CTA barrier: the barrier orders the other threads' stores
+// before it, the fence is cumulative over them) -- a fence per thread costs a link round trip per warp.
 __device__ __forceinline__ void halo_publish(int* __restrict__ local, int* __restrict__ remote_slot, int side, int consumer_threads) {
-  __threadfence_system();                                             // this thread's peer stores, system-wide
   asm volatile("bar.sync 1, %0;" ::"r"(consumer_threads) : "memory");   // consumer warps only: the producer warp has exited
   if (threadIdx.x == 0) {
+    __threadfence_system();                                           // the CTA's peer stores, system-wide
     const unsigned total = gridDim.x * gridDim.y * gridDim.z;
     unsigned prev;
     asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(local + HALO_CTR + side) : "memory");
@@ -157,6 +159,21 @@ __device__ __forceinline__ void halo_publish(int* __restrict__ local, int* __res
       asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote_slot), "r"(seq) : "memory");
     }
   }
+}
+
+// CTA -> (tile row, z chunk).  Natural order, or (hint bit 2) the first and last tile rows of every chunk first: in a
+// room those hold the rows that lie in the y walls, whose warps pay a state round trip per plane -- started first,
+// they finish inside the launch instead of forming its tail.  blockIdx.x (the tile column) is never remapped.
+__device__ __forceinline__ void cta_tile(int heavy_first, int& by, int& bz) {
+  by = blockIdx.y;
+  bz = blockIdx.z;
+  const int gx = gridDim.x, gy = gridDim.y;
+  if (!heavy_first || gy < 3) return;
+  int t = by + gy * bz;                    // launch order within a tile column
+  const int n_heavy = 2 * gridDim.z;
+  if (t < n_heavy) { by = (t & 1) ? gy - 1 : 0; bz = t >> 1; }
+  else { t -= n_heavy; by = 1 + t % (gy - 2); bz = t / (gy - 2); }
+  (void)gx;
 }
 
 constexpr int align128(int x) { return (x + 127) & ~127; }

@@ -34,7 +34,20 @@ inline DifArgs<T> make_dif(const UpdateArgs& a) {
   d.dif_lo = a.dif_lo;
   d.n_dif = a.n_dif;
   d.segs = (a.X + 127) / 128;
+  d.wide_mat = a.wide ? a.mat : nullptr;
+  d.wide_table = (const DifEntry<T>*)a.wide_dif_table;
+  d.n_mat = a.n_coefs / 20;
   return d;
+}
+
+template <typename T>
+inline WideArgs<T> make_wide(const UpdateArgs& a) {
+  WideArgs<T> w;
+  w.mat = a.wide ? a.mat : nullptr;
+  w.table = (const ClassEntry<T>*)a.wide_class_table;
+  w.lo = a.dif_lo;
+  w.n_mat = a.n_coefs / 20;
+  return w;
 }
 
 

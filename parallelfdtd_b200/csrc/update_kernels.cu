@@ -86,12 +86,13 @@ constexpr int tma_max_regs(size_t esize, int scheme, int ty, int rpw, int nst, i
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: (TY/RPW + 1) warps (last warp = TMA producer)
 // DIF = 0: frequency-independent boundaries; 1..4: digital impedance filters of that order
 // (one-row-per-warp 128x8 tile: three resident CTAs per SM in fp32, two in fp64)
-template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF>
+template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF, bool WIDE>
 __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(sizeof(T), SCHEME, TY, RPW, NST, DIF))
     fdtd_update_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                     const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                     T* __restrict__ Pn, T lam2, T a_air, int X, int Y, int z_begin, int z_end, int chunk, int hints,
-                    const DifArgs<T> dif, T* __restrict__ peer, int* __restrict__ sig_local, int* __restrict__ sig_remote, int sig_side) {
+                    const DifArgs<T> dif, const WideArgs<T> wide, T* __restrict__ peer, int* __restrict__ sig_local,
+                    int* __restrict__ sig_remote, int sig_side) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY / RPW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -99,12 +100,15 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
   __shared__ __align__(8) uint64_t bar_empty[NST];
   __shared__ ClassEntry<T> s_table[256];
   __shared__ DifEntry<T> s_dif[DIF ? 64 : 1];
+  __shared__ DifStash<T> s_stash[(DIF && PFDTD_DIF_STASH == 1) ? NW * 32 : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  int cby, cbz;
+  cta_tile(hints & 4, cby, cbz);
   const int x0 = blockIdx.x * TX;
-  const int y0 = blockIdx.y * TY;
-  const int z_lo = z_begin + blockIdx.z * chunk;
+  const int y0 = cby * TY;
+  const int z_lo = z_begin + cbz * chunk;
   const int z_hi = min(z_lo + chunk, z_end);
   const int n = z_hi - z_lo;              // planes this CTA computes
   if (n <= 0) return;
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
   // first wait on the pipeline so that the entry -> state round trips overlap the first planes' TMA loads.
   static_assert(!DIF || RPW == 1, "filter boundaries use the one-row-per-warp tile shapes");
   constexpr int DMO = DIF ? DIF : 1;
-  DifRow<T, DMO> drow;
+  DifRow<T, DMO, WIDE> drow;
   if (DIF) drow.start(dif, z_lo, z_hi, y0 + r0, Y, lane);
 
   V4<T> down[RPW], cur[RPW], up[RPW];
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
           } else {
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-              const ClassEntry<T> ce = s_table[(pw[k] >> (8 * q)) & 0xffu];
+              const ClassEntry<T> ce = class_entry<T, WIDE>(s_table, wide, (pw[k] >> (8 * q)) & 0xffu, (out - Pn) + (int64_t)k * X + q);
               if (SCHEME == SCH_CENTRED) {
                 T xm = (q == 0) ? xm_edge : cc.v[q - 1 < 0 ? 0 : q - 1];
                 T xp = (q == 3) ? xp_edge : cc.v[q + 1 > 3 ? 3 : q + 1];
@@ -262,7 +266,8 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
             }
           }
         }
-        if (DIF) drow.apply(j, res.v, old[k].v, pw[k], active, lane, dif, s_dif);
+        if (DIF) drow.apply(j, res.v, old[k].v, pw[k], active, lane, dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0),
+                            (out - Pn) + (int64_t)k * X);
         if (active) stg4(out + (int64_t)k * X, res);
       }
       out += XY;
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
         mbar_arrive_a(be + 8 * ((u + 1) % NST));
         if (j == 0) mbar_arrive_a(be);   // plane z_lo-1, read in the prologue
       }
-      if (DIF) drow.next(dif, j, n, z_lo, z_hi, y0 + r0, Y, lane);
+      if (DIF) drow.next(dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0), Pn + (int64_t)(y0 + r0) * X + x0, XY, j, n, z_lo, z_hi, y0 + r0, Y, lane);
 #pragma unroll
       for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
     }
@@ -359,9 +364,9 @@ constexpr int kNumTiles = (int)(sizeof(kTiles) / sizeof(kTiles[0]));
 template <typename T, int TY>
 constexpr int stage_bytes() { return TileGeom<T, TY>::STAGE_BYTES; }
 
-template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF = 0>
+template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF = 0, bool WIDE = false>
 int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupancy_out) {
-  auto kern = fdtd_update_tma<T, SCHEME, TY, RPW, NST, DIF>;
+  auto kern = fdtd_update_tma<T, SCHEME, TY, RPW, NST, DIF, WIDE>;
   const int smem = NST * stage_bytes<T, TY>();
   static bool attr_set[64] = {false};   // per device
   int dev = 0;
@@ -379,7 +384,7 @@ int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupanc
   dim3 grid((a.X + TX - 1) / TX, (a.Y + TY - 1) / TY, (nplanes + chunk - 1) / chunk);
   const UpdConst<T> c = make_const<T>(a);
   kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.cls, (const ClassEntry<T>*)a.class_table, a.n_classes, (T*)a.Pn,
-                                          c.lam2, c.a_air, a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints, make_dif<T>(a),
+                                          c.lam2, c.a_air, a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints, make_dif<T>(a), make_wide<T>(a),
                                           (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr, a.sig_local,
                                           (a.z_end - a.z_begin == 1 && a.peer_plane) ? a.sig_remote : nullptr, a.sig_side);
   PF_CUDA(cudaGetLastError());
@@ -388,10 +393,22 @@ int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupanc
 
 template <typename T, int SCHEME>
 int dispatch_tile(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
+  // filter boundaries: one kernel per order on the shape tma_pick_config selects for them -- fp32: 128x8 with six
+  // stages (72 registers, three CTAs per SM); fp64: 128x7 with five (eight warps per CTA leave 128 registers).
+  // Wide meshes (position classes x material table) run on the same shapes, with and without filters.
+  constexpr int DTY = sizeof(T) == 4 ? 8 : 7, DNST = sizeof(T) == 4 ? 6 : 5;
+  if (a.wide) {
+    switch (a.dif_order) {
+      case 0: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 0, true>(a, m, chunk, occ);
+      case 1: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 1, true>(a, m, chunk, occ);
+      case 2: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 2, true>(a, m, chunk, occ);
+      case 3: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 3, true>(a, m, chunk, occ);
+      case 4: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 4, true>(a, m, chunk, occ);
+    }
+    set_error("filter order %d is not supported", a.dif_order);
+    return PFDTD_ERR_INVALID;
+  }
   if (a.dif_order > 0) {
-    // filter boundaries: one kernel per order on the shape tma_pick_config selects for them -- fp32: 128x8 with six
-    // stages (72 registers, three CTAs per SM); fp64: 128x7 with five (eight warps per CTA leave 128 registers)
-    constexpr int DTY = sizeof(T) == 4 ? 8 : 7, DNST = sizeof(T) == 4 ? 6 : 5;
     switch (a.dif_order) {
       case 1: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 1>(a, m, chunk, occ);
       case 2: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 2>(a, m, chunk, occ);
@@ -449,13 +466,13 @@ int tma_encode_maps(TmaMaps* out, int dtype, int tile, const void* P, const void
   return PFDTD_OK;
 }
 
-int tma_pick_config(int dtype, int scheme, int dif_order, int X, int Y, int nplanes, int device, int64_t opt_tile, int64_t opt_chunk,
-                    TmaConfig* out) {
+int tma_pick_config(int dtype, int scheme, int dif_order, bool wide, int X, int Y, int nplanes, int device, int64_t opt_tile,
+                    int64_t opt_chunk, TmaConfig* out) {
   // Defaults (B200, profiles/r01_sweep.md): the 128x7 one-row-per-warp shapes -- eight warps per CTA divide evenly
   // over the four sub-partitions, which leaves 64 (fp32, four CTAs per SM) / 128 (fp64, two) registers per thread
   // and room for a fifth or sixth stage.  The filter kernels have one shape per dtype (dispatch_tile).
   int tile;
-  if (dif_order > 0) tile = dtype == PFDTD_F64 ? 6 : (scheme == SCH_INTERP ? 7 : 3);
+  if (dif_order > 0 || wide) tile = dtype == PFDTD_F64 ? 6 : (scheme == SCH_INTERP ? 7 : 3);
   else if (opt_tile > 0 && opt_tile <= kNumTiles) tile = (int)opt_tile - 1;
   else tile = (dtype == PFDTD_F32 && scheme == SCH_FORWARD) ? 7 : 6;
   if (Y <= 8 && kTiles[tile].ty > 8) tile = 0;
@@ -463,10 +480,11 @@ int tma_pick_config(int dtype, int scheme, int dif_order, int X, int Y, int npla
   probe.dtype = dtype;
   probe.scheme = scheme;
   probe.dif_order = dif_order;
+  probe.wide = wide;
   TmaMaps dummy{};
   int occ = 0;
   if (scheme == SCH_INTERP) {
-    TmaConfig pc{tile, 1};
+    TmaConfig pc{tile, 1, 0};
     PF_TRY(launch_update_interp_tma(probe, dummy, pc, &occ));
   } else {
     PF_TRY(dispatch(probe, dummy, tile, 1, &occ));
@@ -502,6 +520,7 @@ int tma_pick_config(int dtype, int scheme, int dif_order, int X, int Y, int npla
     if (chunk <= 0) chunk = nplanes;
   }
   out->tile = tile;
+  out->occupancy = occ;
   out->chunk = std::max(1, std::min(chunk, std::max(nplanes, 1)));
   return PFDTD_OK;
 }

@@ -132,6 +132,22 @@ struct alignas(16) ClassEntry {
 
 enum : uint32_t { CLS_SOLID = 0, CLS_AIR = 1 };
 
+// Wide meshes: more distinct (position, material) pairs than the 256 a class byte can name (or more lossy ones than the
+// shared filter table holds).  The class byte then names the POSITION class alone; lossless classes (solid, air-like)
+// keep their entry in the shared table, a lossy voxel takes table[(class - lo) * n_mat + material byte] from global
+// memory, the material byte from the slab's material volume -- two dependent loads, in boundary voxels only.
+template <typename T>
+struct WideArgs {
+  const uint8_t* mat;            // null: narrow mode
+  const ClassEntry<T>* table;    // [n_lossy][n_mat]
+  uint32_t lo, n_mat;
+};
+template <typename T, bool WIDE>
+__device__ __forceinline__ ClassEntry<T> class_entry(const ClassEntry<T>* __restrict__ s_table, const WideArgs<T>& w, uint32_t cid, int64_t vox) {
+  if (WIDE) { if (cid >= w.lo) return w.table[(cid - w.lo) * w.n_mat + w.mat[vox]]; }
+  return s_table[cid];
+}
+
 // ---- digital impedance filters (frequency-dependent boundaries; not in the reference) ----
 // Material m has the admittance Y_m(z) = (b0 + b1 z^-1 + .. + bN z^-N) / (1 + a1 z^-1 + .. + aN z^-N) acting on
 // u^n = p^(n+1) - p^(n-1).  With the filter in transposed direct form II (states s_1..s_N per boundary voxel):
@@ -140,6 +156,11 @@ enum : uint32_t { CLS_SOLID = 0, CLS_AIR = 1 };
 // c3 = kappa * sw/(1+beta0), kappa = 0.5*(6-K)*lam (forward / interpolated) or lam*(dir_x+dir_y+dir_z) (centred).
 // Order 0 leaves p_new = val0: exactly the reference's locally-reacting boundary.
 #define PFDTD_DIF_MAX_ORDER 4
+// how single-voxel planes are evaluated (DifRow): 0 = by the voxel's lane at the plane's turn, 1 = stashed in shared
+// memory and evaluated 32 planes at a time, 2 = the same with the stash in the registers of lane (plane & 31)
+#ifndef PFDTD_DIF_STASH
+#define PFDTD_DIF_STASH 1
+#endif
 template <typename T>
 struct DifEntry {
   T c3, b0;
@@ -155,7 +176,21 @@ struct DifArgs {
   uint32_t dif_lo;               // class ids >= dif_lo are lossy boundary classes
   int n_dif;
   int segs;                      // row segments per row = ceil(X / 128)
+  // wide meshes (more node classes than a byte / the shared tables hold): the class byte is the POSITION class only and
+  // the entry of a lossy voxel is table[(class - dif_lo) * n_mat + material byte] in global memory
+  const uint8_t* wide_mat;       // material byte volume of the slab, or null
+  const DifEntry<T>* wide_table; // [n_dif][n_mat]
+  uint32_t n_mat;
 };
+
+// entry of a lossy voxel of class `cid` whose material byte is `m` (only read in wide mode)
+template <typename T, bool WIDE>
+__device__ __forceinline__ const DifEntry<T>& dif_entry(const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif, uint32_t cid, uint32_t m) {
+  if (WIDE) return d.wide_table[(cid - d.dif_lo) * d.n_mat + m];
+  return s_dif[cid - d.dif_lo];
+}
+template <typename T, bool WIDE>
+__device__ __forceinline__ uint32_t dif_mat(const DifArgs<T>& d, int64_t vox) { return WIDE ? (uint32_t)d.wide_mat[vox] : 0u; }
 
 // Row-segment entry (one per plane, row and 128-voxel tile column): x = index of the segment's first filter voxel
 // (its voxels are numbered consecutively in x order), y = flags:
@@ -210,9 +245,9 @@ __device__ __forceinline__ void dif_filter(const DifEntry<T>& e, const T (&s)[OR
 }
 
 // the two less common kinds of row segment (see DifRow): contiguous runs and the general case
-template <typename T, int ORD>
+template <typename T, int ORD, bool WIDE>
 __device__ __noinline__ Quad<T> dif_apply_multi(Quad<T> res_q, const Quad<T> old_q, uint32_t pw, bool active, int lane, uint32_t fl,
-                                                uint32_t base, const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif) {
+                                                uint32_t base, const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif, int64_t vox0) {
   constexpr int P = dif_pad(ORD);
   T (&res)[4] = res_q.v;
   const T (&old)[4] = old_q.v;
@@ -227,7 +262,7 @@ __device__ __noinline__ Quad<T> dif_apply_multi(Quad<T> res_q, const Quad<T> old
 #pragma unroll
       for (int q = 0; q < 4; q++)
         if ((uint32_t)(r0 + q) < cnt) {
-          const DifEntry<T>& e = s_dif[((pw >> (8 * q)) & 0xffu) - d.dif_lo];
+          const DifEntry<T>& e = dif_entry<T, WIDE>(d, s_dif, (pw >> (8 * q)) & 0xffu, dif_mat<T, WIDE>(d, vox0 + q));
           T ns[ORD], p_new;
           dif_filter<T, ORD>(e, s[q], res[q], old[q], p_new, ns);
           dif_st<T, ORD>(sp + q * P, ns);
@@ -254,12 +289,47 @@ __device__ __noinline__ Quad<T> dif_apply_multi(Quad<T> res_q, const Quad<T> old
       T* sp = d.state + ((size_t)base + rank) * P;
       T s[ORD], ns[ORD], p_new;
       dif_ld<T, ORD>(sp, s);
-      const DifEntry<T>& e = s_dif[((pw >> (bit - 7)) & 0xffu) - d.dif_lo];
+      const DifEntry<T>& e = dif_entry<T, WIDE>(d, s_dif, (pw >> (bit - 7)) & 0xffu, dif_mat<T, WIDE>(d, vox0 + q));
       dif_filter<T, ORD>(e, s, sel4<T>(res, q), sel4<T>(old, q), p_new, ns);
       dif_st<T, ORD>(sp, ns);
       put4<T>(res, q, p_new);
     }
   return res_q;
+}
+
+// What the march leaves behind for a single-voxel plane: the frequency-independent result of the voxel, the value
+// it overwrites and its class.  The filter itself runs once per 32 planes, on 32 voxels at a time (DifRow::flush).
+template <typename T, int N> struct DifArr { T v[N]; };
+template <typename T>
+struct alignas(16) DifStash {
+  T val0, p_old;
+  uint32_t cls, pad;
+};
+
+// The deferred filter evaluation of a block's single-voxel planes (DifRow below): lane l holds the entry and the
+// states of plane z_blk + l.  `row` = address of (x = tile origin, the warp's row, plane 0) of the field being
+// written.  Out of line, arguments by value: it runs once per 32 planes and its registers stay out of the march.
+template <typename T, int ORD, bool WIDE>
+__device__ __noinline__ void dif_flush(uint2 ent, DifArr<T, ORD> sv, DifStash<T> mine, const DifArgs<T>& d,
+                                       const DifEntry<T>* __restrict__ s_dif, const DifStash<T>* __restrict__ stash, T* __restrict__ row,
+                                       int64_t XY, int z_blk, int lane) {
+  constexpr int P = dif_pad(ORD);
+  __syncwarp();                                     // the stash entries and the march's stores of these planes
+  if (ent.y & DIF_SINGLE) {
+#if PFDTD_DIF_STASH == 2
+    const DifStash<T> st = mine;
+    (void)stash;
+#else
+    const DifStash<T> st = stash[lane];
+    (void)mine;
+#endif
+    const DifEntry<T>& e = dif_entry<T, WIDE>(d, s_dif, st.cls & 0xffu, st.cls >> 8);
+    T ns[ORD], p_new;
+    dif_filter<T, ORD>(e, sv.v, st.val0, st.p_old, p_new, ns);
+    dif_st<T, ORD>(d.state + (size_t)ent.x * P, ns);
+    row[(int64_t)(z_blk + lane) * XY + (ent.y & 127u)] = p_new;
+  }
+  __syncwarp();
 }
 
 // Filter-boundary bookkeeping of one consumer warp (one tile row, 128 voxels, marching in z).  ORD = the filter
@@ -268,19 +338,26 @@ __device__ __noinline__ Quad<T> dif_apply_multi(Quad<T> res_q, const Quad<T> old
 //   * entries: lane l keeps the entry of plane 32*b + l of the current block of 32 planes (one load per block);
 //     DIF_ANY says whether the block has a filter voxel in this row segment at all -- segments in open air skip
 //     everything with one test per plane.
-//   * single-voxel planes: lane l also loads the states of plane 32*b + l's voxel right away, up to a whole block
-//     ahead (filter voxels are numbered z-fastest within a row segment, so a wall crossing the rows makes this one
-//     coalesced access); the plane's turn hands them to the voxel's lane by shuffle.
+//   * single-voxel planes (a wall crossing the rows: half of all row segments of a shoebox): lane l also loads the
+//     states of plane 32*b + l's voxel right away (filter voxels are numbered z-fastest within a row segment, so this
+//     is one coalesced access).  At the plane's turn the voxel's lane only stashes (val0, p_old, class) in shared
+//     memory -- one predicated store instead of a one-lane-wide filter evaluation per plane.  After the block's last
+//     plane, flush() runs the filter for all 32 planes at once, lane l for plane 32*b + l: full-width arithmetic,
+//     one coalesced state store, and a 4-byte patch of the value the march had stored for the voxel.
 //   * runs (rows lying in a wall): every lane loads the states of its own (up to four) voxels when the plane's turn
 //     comes -- one exposed round trip per plane, in the few warps that own such rows.
 //   * anything else: ranked by ballots, one pass per voxel of the busiest lane.
 // Per voxel (transposed direct form II, see above):
 //     p_new = val0 - c3*s_1 ; u = p_new - p_old ; y = b0*u + s_1 ; s_i <- b_i*u - a_i*y + s_(i+1)
-template <typename T, int ORD>
+template <typename T, int ORD, bool WIDE>
 struct DifRow {
   static constexpr int P = dif_pad(ORD);
   uint2 ent;            // lane l: entry of plane 32*b + l; DIF_ANY is set in every lane's flags when any plane of the block has voxels
   T st_blk[ORD];        // lane l: states of the single filter voxel of plane 32*b + l
+#if PFDTD_DIF_STASH == 2
+  T r_val0, r_old;      // lane l: what the march left behind for plane 32*b + l
+  uint32_t r_cls;
+#endif
 
   __device__ __forceinline__ void load_block(const DifArgs<T>& d, int z_first, int z_end, int gy, int Y, int lane) {
     const int z = z_first + lane;
@@ -295,41 +372,87 @@ struct DifRow {
     if (__ballot_sync(0xffffffffu, (ent.y & DIF_HAS) != 0u)) ent.y |= DIF_ANY;
   }
   __device__ __forceinline__ void start(const DifArgs<T>& d, int z_lo, int z_hi, int gy, int Y, int lane) {
+#if PFDTD_DIF_STASH == 2
+    r_val0 = (T)0; r_old = (T)0; r_cls = 0u;
+#endif
 #pragma unroll
     for (int i = 0; i < ORD; i++) st_blk[i] = (T)0;
     load_block(d, z_lo, z_hi, gy, Y, lane);
   }
-  // end of plane j (of n): the next block of entries is due
-  __device__ __forceinline__ void next(const DifArgs<T>& d, int j, int n, int z_lo, int z_hi, int gy, int Y, int lane) {
+
+  // end of plane j (of n): flush the block that ends here, then fetch the next block of entries
+  __device__ __forceinline__ void next(const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif, const DifStash<T>* __restrict__ stash,
+                                       T* __restrict__ row, int64_t XY, int j, int n, int z_lo, int z_hi, int gy, int Y, int lane) {
+#if PFDTD_DIF_STASH == 0
+    (void)s_dif; (void)stash; (void)row; (void)XY;
     if (((j + 1) & 31) == 0 && j + 1 < n) load_block(d, z_lo + j + 1, z_hi, gy, Y, lane);
+#else
+    if (((j + 1) & 31) == 0 || j + 1 == n) {
+      if (ent.y & DIF_ANY) {
+        DifArr<T, ORD> sv;
+#pragma unroll
+        for (int i = 0; i < ORD; i++) sv.v[i] = st_blk[i];
+#if PFDTD_DIF_STASH == 2
+        DifStash<T> mine;
+        mine.val0 = r_val0; mine.p_old = r_old; mine.cls = r_cls; mine.pad = 0u;
+        dif_flush<T, ORD, WIDE>(ent, sv, mine, d, s_dif, stash, row, XY, z_lo + (j & ~31), lane);
+#else
+        dif_flush<T, ORD, WIDE>(ent, sv, DifStash<T>{}, d, s_dif, stash, row, XY, z_lo + (j & ~31), lane);
+#endif
+      }
+      if (j + 1 < n) load_block(d, z_lo + j + 1, z_hi, gy, Y, lane);
+    }
+#endif
   }
 
   // Warp-convergent, plane j of the chunk.  res = the frequency-independent results of this lane's four voxels
-  // (updated in place), pw = their class bytes.
+  // (updated in place for runs / general segments; single voxels are patched by flush), pw = their class bytes.
   __device__ __forceinline__ void apply(int j, T (&res)[4], const T (&old)[4], uint32_t pw, bool active, int lane, const DifArgs<T>& d,
-                                        const DifEntry<T>* __restrict__ s_dif) {
+                                        const DifEntry<T>* __restrict__ s_dif, DifStash<T>* __restrict__ stash, int64_t vox0) {
     if (!(ent.y & DIF_ANY)) return;   // the same in every lane
     const uint32_t fl = __shfl_sync(0xffffffffu, ent.y, j & 31);
     if (!(fl & DIF_HAS)) return;
-    if (fl & DIF_SINGLE) {   // the states were fetched with the block's entries; hand them to the voxel's lane
+    if (fl & DIF_SINGLE) {
+#if PFDTD_DIF_STASH == 0
       T s[ORD];
 #pragma unroll
       for (int i = 0; i < ORD; i++) s[i] = __shfl_sync(0xffffffffu, st_blk[i], j & 31);
       const uint32_t base = __shfl_sync(0xffffffffu, ent.x, j & 31);
       if ((uint32_t)lane == ((fl & 127u) >> 2)) {
         const int q = (int)(fl & 3u);
-        const DifEntry<T>& e = s_dif[((pw >> (8 * q)) & 0xffu) - d.dif_lo];
+        const DifEntry<T>& e = dif_entry<T, WIDE>(d, s_dif, (pw >> (8 * q)) & 0xffu, dif_mat<T, WIDE>(d, vox0 + q));
         T ns[ORD], p_new;
         dif_filter<T, ORD>(e, s, sel4<T>(res, q), sel4<T>(old, q), p_new, ns);
         dif_st<T, ORD>(d.state + (size_t)base * P, ns);
         put4<T>(res, q, p_new);
       }
+#elif PFDTD_DIF_STASH == 1
+      if ((uint32_t)lane == ((fl & 127u) >> 2)) {
+        const int q = (int)(fl & 3u);
+        DifStash<T> st;
+        st.val0 = sel4<T>(res, q);
+        st.p_old = sel4<T>(old, q);
+        st.cls = ((pw >> (8 * q)) & 0xffu) | (dif_mat<T, WIDE>(d, vox0 + q) << 8);
+        st.pad = 0u;
+        stash[j & 31] = st;
+      }
+#else
+      {   // q and the source lane are warp-uniform: every lane selects, the voxel's lane's values go to lane (j & 31)
+        const int q = (int)(fl & 3u), src = (int)((fl & 127u) >> 2);
+        const T v0 = __shfl_sync(0xffffffffu, sel4<T>(res, q), src);
+        const T po = __shfl_sync(0xffffffffu, sel4<T>(old, q), src);
+        uint32_t c = (pw >> (8 * q)) & 0xffu;
+        if (WIDE && lane == src) c |= dif_mat<T, WIDE>(d, vox0 + q) << 8;
+        c = __shfl_sync(0xffffffffu, c, src);
+        if (lane == (j & 31)) { r_val0 = v0; r_old = po; r_cls = c; }
+      }
+#endif
       return;
     }
     // rows lying in a wall and everything else: out of line, so that their register needs stay out of the march
     const uint32_t base = __shfl_sync(0xffffffffu, ent.x, j & 31);
     Quad<T> r{{res[0], res[1], res[2], res[3]}}, o{{old[0], old[1], old[2], old[3]}};
-    r = dif_apply_multi<T, ORD>(r, o, pw, active, lane, fl, base, d, s_dif);
+    r = dif_apply_multi<T, ORD, WIDE>(r, o, pw, active, lane, fl, base, d, s_dif, vox0);
 #pragma unroll
     for (int q = 0; q < 4; q++) res[q] = r.v[q];
   }

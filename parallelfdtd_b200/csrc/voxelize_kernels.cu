@@ -13,8 +13,10 @@
 //   2. classification: air-neighbour set -> bid code; voxels whose set has no code (thin
 //      features) are turned solid, repeated until nothing changes (the fixed point does not depend on the order:
 //      a subset of a set without a code has no code either).
-//   3. material of a boundary voxel = material of the triangle with the nearest centroid.
+//   3. material of a boundary voxel = material of the NEAREST TRIANGLE (point-to-triangle distance, tri_dist.h; the
+//      first of equally near triangles in mesh order).
 #include "pfdtd_internal.h"
+#include "tri_dist.h"
 
 #include <algorithm>
 #include <cmath>
@@ -117,8 +119,15 @@ __global__ void vox_classify_kernel(const uint8_t* __restrict__ in, uint8_t* __r
   }
 }
 
-__global__ void vox_material_kernel(const uint8_t* __restrict__ bid, const float* __restrict__ cen, const uint8_t* __restrict__ tri_mat, uint32_t nt,
-                                    float dx, uint32_t vx, uint32_t vy, uint32_t vz, uint8_t* __restrict__ mat) {
+struct DevOps {   // one IEEE rounding per operation, never contracted (tri_dist.h)
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+
+__global__ void vox_material_kernel(const uint8_t* __restrict__ bid, const VoxTri* __restrict__ tris, const uint8_t* __restrict__ tri_mat,
+                                    uint32_t nt, float dx, uint32_t vx, uint32_t vy, uint32_t vz, uint8_t* __restrict__ mat) {
   const size_t n = (size_t)vx * vy * vz;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
     const uint8_t b = bid[e];
@@ -129,8 +138,8 @@ __global__ void vox_material_kernel(const uint8_t* __restrict__ bid, const float
       float best = 1e30f;
       uint32_t bt = 0;
       for (uint32_t t = 0; t < nt; t++) {
-        const float ddx = fsub(cen[3 * t], px), ddy = fsub(cen[3 * t + 1], py), ddz = fsub(cen[3 * t + 2], pz);
-        const float dd = fadd(fadd(fmul(ddx, ddx), fmul(ddy, ddy)), fmul(ddz, ddz));
+        const VoxTri r = tris[t];
+        const float dd = pfdtd_geom::point_triangle_dist2<DevOps>(px, py, pz, r.ax, r.ay, r.az, r.bx, r.by, r.bz, r.cx, r.cy, r.cz);
         if (dd < best) { best = dd; bt = t; }
       }
       m = tri_mat[bt];
@@ -224,7 +233,7 @@ int voxelize_to_device(int device, const float* h_vertices, uint32_t n_vertices,
     cur = 1 - cur;
     if (!flags[0]) break;
   }
-  vox_material_kernel<<<blocks, 256>>>(d_bid, d_cen, d_trimat, h_tri_material ? n_triangles : 0u, dx, vx, vy, vz, d_mat);
+  vox_material_kernel<<<blocks, 256>>>(d_bid, d_tris, d_trimat, h_tri_material ? n_triangles : 0u, dx, vx, vy, vz, d_mat);
   nl++;
   PF_CUDA(cudaGetLastError());
   PF_CUDA(cudaDeviceSynchronize());

@@ -276,6 +276,32 @@ static void test_geometry_and_voxelizer() {
 }
 
 // ---- GPU: CudaMeshTest.cpp:220-469 re-expressed ------------------------------------------------------------------
+// Coarse, flat room (10 x 10 x 3 m, two triangles per face, dx = 0.25): every face voxel must carry the material of the
+// face it lies on -- the nearest TRIANGLE, not the nearest centroid (which gives half the floor to the walls).
+static void test_voxelizer_materials_follow_the_nearest_triangle() {
+  std::vector<unsigned> idx; std::vector<float> v; box_mesh(10.f, 10.f, 3.f, idx, v);
+  GeometryHandler g; g.initialize(&idx[0], &v[0], (unsigned)idx.size(), (unsigned)v.size());
+  const unsigned nt = g.getNumberOfTriangles();
+  std::vector<unsigned char> tm(nt);
+  for (unsigned t = 0; t < nt; t++) {         // material = 1 + index of the axis-aligned face the triangle lies in
+    nv::Vec3ui tr = g.triangle(t);
+    const nv::Vec3f a = g.vertex(tr.x), b = g.vertex(tr.y), c = g.vertex(tr.z);
+    unsigned char m = 0;
+    if (a.z == b.z && b.z == c.z) m = a.z == 0.f ? 1 : 2;
+    else if (a.y == b.y && b.y == c.y) m = a.y == 0.f ? 3 : 4;
+    else if (a.x == b.x && b.x == c.x) m = a.x == 0.f ? 6 : 5;
+    tm[t] = m;
+  }
+  pfdtd_host::VoxelVolumes vol = pfdtd_host::voxelize(g, 0.25f, &tm[0]);
+  int face[28] = {0}; face[26] = 1; face[21] = 2; face[22] = 3; face[23] = 4; face[25] = 5; face[24] = 6;
+  long total = 0, wrong = 0;
+  for (size_t e = 0; e < vol.bid.size(); e++) {
+    const int b = vol.bid[e];
+    if (b >= 21 && b <= 26) { total++; if (vol.mat[e] != face[b]) wrong++; }
+  }
+  CHECK(total > 3000); CHECK_EQ(wrong, 0l);
+}
+
 static void shoebox_bid(unsigned vx, unsigned vy, unsigned vz, std::vector<unsigned char>& bid, std::vector<unsigned char>& mat) {
   bid.assign((size_t)vx * vy * vz, 0); mat.assign(bid.size(), 0);
   auto in = [&](int x, int y, int z) { return x >= 1 && y >= 1 && z >= 1 && x < (int)vx - 1 && y < (int)vy - 1 && z < (int)vz - 1; };
@@ -472,7 +498,7 @@ static void test_cuda_mesh_gpu() {
 
 int main(int argc, char** argv) {
   const std::string what = argc > 1 ? argv[1] : "cpu";
-  if (what == "cpu") { test_simulation_parameters(); test_parameter_generation(); test_srcrec(); test_material_handler(); test_device_helpers_without_a_device(); test_file_reader(); test_partition_indexing(); test_geometry_and_voxelizer(); }
+  if (what == "cpu") { test_simulation_parameters(); test_parameter_generation(); test_srcrec(); test_material_handler(); test_device_helpers_without_a_device(); test_file_reader(); test_partition_indexing(); test_geometry_and_voxelizer(); test_voxelizer_materials_follow_the_nearest_triangle(); }
   else if (what == "gpu") { test_cuda_mesh_gpu(); test_voxelizer_gpu(); }
   std::printf("%s: %d checks, %d failures\n", what.c_str(), g_checks, g_fail);
   return g_fail ? 1 : 0;

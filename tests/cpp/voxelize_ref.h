@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <vector>
 #include "base/GeometryHandler.h"
+#include "../../parallelfdtd_b200/csrc/tri_dist.h"
 
 namespace pfdtd_host {
 
@@ -90,21 +91,19 @@ inline VoxelVolumes voxelize(const GeometryHandler& g, float dx, const unsigned 
       if (b == 0) { in[e] = 0; v.bid[e] = 0; changed = true; } else v.bid[e] = b;
     }
   }
-  // material of a boundary voxel = material of the nearest triangle (by centroid distance)
+  // material of a boundary voxel = material of the nearest triangle (point-to-triangle distance, csrc/tri_dist.h with
+  // plain float operators; first of equally near triangles)
   v.mat.assign(n, 0);
   if (tri_material && nt) {
-    std::vector<nv::Vec3f> cen(nt);
-    for (unsigned int t = 0; t < nt; t++) {
-      nv::Vec3ui tr = g.triangle(t);
-      cen[t] = (g.vertex(tr.x) + g.vertex(tr.y) + g.vertex(tr.z)) * (1.f / 3.f);
-    }
     for (unsigned int k = 0; k < v.vz; k++) for (unsigned int j = 0; j < v.vy; j++) for (unsigned int i = 0; i < v.vx; i++) {
       const size_t e = ((size_t)k * v.vy + j) * v.vx + i;
       if (v.bid[e] == 0 || v.bid[e] == 27) continue;
       const nv::Vec3f p(((float)i - 1.f) * dx, ((float)j - 1.f) * dx, ((float)k - 1.f) * dx);
       float best = 1e30f; unsigned int bt = 0;
       for (unsigned int t = 0; t < nt; t++) {
-        nv::Vec3f d = cen[t] - p; const float dd = d.x * d.x + d.y * d.y + d.z * d.z;
+        nv::Vec3ui tr = g.triangle(t);
+        const nv::Vec3f a = g.vertex(tr.x), b = g.vertex(tr.y), c = g.vertex(tr.z);
+        const float dd = pfdtd_geom::point_triangle_dist2<pfdtd_geom::PlainOps>(p.x, p.y, p.z, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
         if (dd < best) { best = dd; bt = t; }
       }
       v.mat[e] = tri_material[bt];

@@ -89,3 +89,21 @@ def test_c5_fp64_iiso_20_materials_10_sources_as_separate_runs(capi, gpu):
         assert (np.abs(r).max(axis=1) > 0).all()
         seen.add(r.tobytes())
     assert len(seen) == 10                                   # ten different responses
+
+
+# More (position, material) pairs than a class byte can name -- or more lossy ones than the kernels' shared filter table
+# holds: the mesh is classified by position alone and boundary voxels look their material up (update_math.cuh WideArgs).
+# The reference has no such ceiling (separate material byte, cudaMesh.h:90-91, kernels3d.cu:639-640).
+@pytest.mark.parametrize("update_type,double,order,n_parts", [(2, False, 2, 1), (3, True, 2, 2), (2, True, 0, 3), (3, False, 0, 1), (4, False, 1, 2)])
+def test_c5_hall_20_materials_beyond_256_node_classes(capi, gpu, update_type, double, order, n_parts):
+    dims = (96, 128, 64)
+    bid, mat = synth.hall(dims, 20)
+    # a material per boundary voxel instead of per surface: every (position, material) pair occurs
+    rng = np.random.default_rng(11)
+    mat = np.where((bid > 0) & (bid < 27), rng.integers(0, 20, size=bid.shape, dtype=np.uint8), 0).astype(np.uint8)
+    c = _case(f"wide_{update_type}_{order}", bid, mat, update_type, double, 150, 20, n_parts, [(40, 20, 20, 0, 0, 0)],
+              [(50, 60, 30), (20, 100, 40), (3, 64, 30)], dif_order=order or None)
+    r, info = _check(capi, c)
+    if update_type == 2:      # 26 position bytes x 20 materials = 384 pairs on this mesh; the interpolated cases go wide when their
+        assert "position classes" in info["kernel"], info["kernel"]      # K12 / K8 combinations or lossy-class count ask for it
+    assert (np.abs(r).max(axis=1) > 0).all()

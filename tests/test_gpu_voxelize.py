@@ -41,11 +41,29 @@ def test_box_room_matches_the_analytic_classification(capi, gpu, dims_m, dx):
     exp = expected_bid(bid.shape, inside)
     assert np.array_equal(bid, exp)
     assert (bid == 27).sum() > 0 and ((bid > 0) & (bid < 27)).sum() > 0
-    # materials: boundary voxels of a face carry that face's material (corners/edges: nearest centroid), others 0
+    # materials: boundary voxels of a face carry that face's material (corners/edges: nearest triangle), others 0
     assert (mat[(bid == 0) | (bid == 27)] == 0).all()
     zc, yc = bid.shape[0] // 2, bid.shape[1] // 2
     assert mat[zc, yc, 2] == tri_mat[10] and mat[zc, yc, np.nonzero(bid[zc, yc])[0][-1]] == tri_mat[8]   # x = 0 / x = L faces
     assert mat[2, yc, bid.shape[2] // 2] == tri_mat[0] and mat[np.nonzero(bid[:, yc, bid.shape[2] // 2])[0][-1], yc, bid.shape[2] // 2] == tri_mat[2]
+
+
+@pytest.mark.parametrize("dims_m,dx", [((10.0, 10.0, 3.0), 0.25), ((6.0, 2.0, 9.0), 0.2)])
+def test_every_face_voxel_of_a_flat_room_carries_its_own_face_material(capi, gpu, dims_m, dx):
+    """Coarse room mesh (two triangles per face), low aspect ratio: a floor voxel next to a wall is nearer to the wall
+    triangles' CENTROIDS than to the floor triangles' -- the material must come from the nearest TRIANGLE.  Every face
+    voxel is checked (bid 21..26 = exactly one missing neighbour), not only the face centres."""
+    v, t = box((0, 0, 0), dims_m)
+    tri_mat = (1 + np.arange(len(t)) // 2).astype(np.uint8)      # faces in box() order: z=0, z=top, y=0, y=max, x=max, x=0
+    bid, mat = capi.voxelize(v, t, dx, tri_mat)
+    face_of_bid = {26: 1, 21: 2, 22: 3, 23: 4, 25: 5, 24: 6}     # missing Down / Up / In (y-1) / Out (y+1) / Right (x+1) / Left (x-1)
+    for b, m in face_of_bid.items():
+        sel = bid == b
+        assert sel.sum() > 0, b
+        assert (mat[sel] == m).all(), (b, m, np.unique(mat[sel], return_counts=True))
+    # edges and corners belong to one of the faces they touch
+    edge = (bid > 0) & (bid < 21)
+    assert edge.sum() > 0 and (mat[edge] >= 1).all() and (mat[edge] <= 6).all()
 
 
 def test_l_shaped_room_and_thin_features(capi, gpu):
