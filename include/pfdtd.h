@@ -83,8 +83,14 @@ enum {
    * materials[m*20 + octave].  Order-0 filters reproduce that path bit for bit.  Set before pfdtd_make_partition. */
   PFDTD_OPT_DIF_ORDER = 13,
   /* slabs in one process: the edge launches store their plane straight into the neighbour slab's halo plane
-   * (peer-mapped stores; default 1).  0 = copy the planes with cudaMemcpyPeerAsync after the edge launches. */
-  PFDTD_OPT_PEER_STORES = 14
+   * (peer-mapped stores; default 1).  0 = copy the planes with cudaMemcpyPeerAsync after the edge launches.
+   * One process per GPU: the same through CUDA-IPC mappings (pfdtd_comm_init); 0 = ncclSend/ncclRecv. */
+  PFDTD_OPT_PEER_STORES = 14,
+  /* single slab: record the receivers and inject the next step's sources inside the update launch (default 1) instead
+   * of a separate launch per step (the reference does both with per-element memcpys, kernels3d.cu:93-104,164-173).
+   * Same results; 0 keeps the separate launch.  Also bit 2 of PFDTD_OPT_TMA_HINTS: CTAs of the first / last tile row
+   * (rows lying in the y walls) are scheduled first. */
+  PFDTD_OPT_FUSE_SRCREC = 15
 };
 
 typedef int (*pfdtd_interrupt_cb)(void);                      /* kernels3d.h: bool (*)(void) */

@@ -21,7 +21,7 @@ SRL_FORWARD, SHARED, SRL, IISO, IWB = 0, 1, 2, 3, 4
 SRC_HARD, SRC_SOFT, SRC_TRANSPARENT = 0, 1, 2
 (OPT_MATIDX_AS_WRITTEN, OPT_SOFT_ACCUMULATE, OPT_KERNEL, OPT_GLOBAL_Z_FIRST, OPT_GLOBAL_Z_DIM,
  OPT_DOUBLE_PAD_AS_WRITTEN, OPT_USE_GRAPH, OPT_OVERLAP, OPT_TMA_CHUNK, OPT_TMA_TILE, OPT_TIME_KERNELS, OPT_TMA_HINTS, OPT_DIF_ORDER,
- OPT_PEER_STORES) = range(1, 15)
+ OPT_PEER_STORES, OPT_FUSE_SRCREC) = range(1, 16)
 KERNEL_AUTO, KERNEL_TMA, KERNEL_PLAIN = 0, 1, 2
 
 INTERRUPT_CB = C.CFUNCTYPE(C.c_int)

@@ -101,7 +101,12 @@ struct Partition {
   bool use_tma = false;
   TmaMaps maps[2];                      // maps[c]: current field = P[c], overwritten field = P[1-c]
   TmaConfig cfg_full{0, 1, 0}, cfg_int{0, 1, 0}, cfg_edge{0, 1, 0};
-  int* d_step = nullptr;                // [0] step counter, [1] first recordable step
+  int* d_step = nullptr;                // [0] step counter, [1] first recordable step, [2] last step of the current enqueue
+  // sources / receivers handled by the update launch itself (single slab; tma_common.cuh fused_srcrec)
+  bool fused = false;
+  void* d_fused = nullptr;              // FusedSrcRec<T>
+  FusedItem* d_fused_items = nullptr;   // sources, then receivers
+  unsigned int* d_fused_done = nullptr;
   // sources / receivers that live in this partition
   int n_src = 0, n_rec = 0;
   int64_t* d_src_elem = nullptr; int32_t* d_src_type = nullptr; int32_t* d_src_slot = nullptr;
@@ -122,7 +127,7 @@ struct pfdtd_solver {
   // options
   int64_t opt_matidx_as_written = 1, opt_soft_accumulate = 0, opt_kernel = KERNEL_AUTO, opt_global_z_first = 0,
           opt_global_z_dim = 0, opt_double_pad = 0, opt_use_graph = 1, opt_overlap = 1, opt_tma_chunk = 0, opt_tma_tile = 0,
-          opt_time_kernels = 0, opt_tma_hints = 0, opt_dif_order = 0;
+          opt_time_kernels = 0, opt_tma_hints = 0, opt_dif_order = 0, opt_fuse_srcrec = 1;
   int dtype = PFDTD_F32;
   int element_type = 0;
   int scheme = SCH_FORWARD;
@@ -152,6 +157,7 @@ struct pfdtd_solver {
   uint32_t n_src = 0, n_rec = 0, src_steps = 0, rec_cap = 0;
   bool srcrec_dirty = true;              // receiver (and source) tables must be rebuilt: recorded samples are dropped
   bool src_dirty = false;                // only the source tables changed: the recorded samples stay
+  bool fuse_dirty = true;                // the fused source / receiver descriptor must be rebuilt (options changed)
   int dif_order_built = 0;               // filter order the partitions were built for (state layout, row-segment entries)
   // comm
   void* comm = nullptr;
@@ -218,6 +224,7 @@ static int free_partitions(pfdtd_solver* s) {
     cudaFree(p.dif_state); cudaFree(p.dif_rowbase); cudaFree(p.dif_table);
     cudaFree(p.d_wide_keys); cudaFree(p.wide_class_table); cudaFree(p.wide_dif_table);
     cudaFree(p.P[0]); cudaFree(p.P[1]); cudaFree(p.materials); cudaFree(p.d_step);
+    cudaFree(p.d_fused); cudaFree(p.d_fused_items); cudaFree(p.d_fused_done);
     cudaFree(p.d_src_elem); cudaFree(p.d_src_type); cudaFree(p.d_src_slot); cudaFree(p.d_rec_elem); cudaFree(p.d_rec_slot);
     cudaFree(p.d_src_samples); cudaFree(p.d_rec_out);
     if (p.s_main) cudaStreamDestroy(p.s_main);
@@ -243,6 +250,45 @@ static int upload_new(void** d, const void* h, size_t bytes) {
   if (bytes == 0) return PFDTD_OK;
   PF_CUDA(cudaMalloc(d, bytes));
   PF_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+  return PFDTD_OK;
+}
+
+// Single slab with the TMA kernel and every source / receiver in an updated plane: the update launch records and injects
+// (tma_common.cuh fused_srcrec).  Anything else keeps the separate launch.
+static int build_fused(pfdtd_solver* s) {
+  for (auto& p : s->parts) {
+    p.fused = false;
+    cudaFree(p.d_fused); cudaFree(p.d_fused_items); cudaFree(p.d_fused_done);
+    p.d_fused = nullptr; p.d_fused_items = nullptr; p.d_fused_done = nullptr;
+  }
+  if (s->parts.size() != 1 || s->comm || !s->opt_fuse_srcrec) return PFDTD_OK;
+  Partition& p = s->parts[0];
+  if (!p.use_tma || s->n_src > 64 || s->n_rec > 4096 || s->n_src + s->n_rec == 0) return PFDTD_OK;
+  const int64_t zoff = s->opt_global_z_first;
+  std::vector<FusedItem> items;
+  for (int pass = 0; pass < 2; pass++) {
+    const uint32_t n = pass == 0 ? s->n_src : s->n_rec;
+    const std::vector<int32_t>& xyz = pass == 0 ? s->src_xyz : s->rec_xyz;
+    for (uint32_t i = 0; i < n; i++) {
+      const int64_t z = (int64_t)xyz[3 * i + 2] - zoff - p.first;
+      if (z < 1 || z > p.size - 2) return PFDTD_OK;             // a plane this slab never updates: separate launch
+      items.push_back(FusedItem{xyz[3 * i], xyz[3 * i + 1], (int)z, (int)i, pass == 0 ? s->src_type[i] : 0});
+    }
+  }
+  PF_CUDA(cudaSetDevice(p.device));
+  PF_CUDA(cudaMalloc(&p.d_fused_items, items.size() * sizeof(FusedItem)));
+  PF_CUDA(cudaMemcpy(p.d_fused_items, items.data(), items.size() * sizeof(FusedItem), cudaMemcpyHostToDevice));
+  PF_CUDA(cudaMalloc(&p.d_fused_done, sizeof(unsigned int)));
+  PF_CUDA(cudaMemset(p.d_fused_done, 0, sizeof(unsigned int)));
+  FusedSrcRec<void> h{};
+  h.n_src = (int)s->n_src; h.n_rec = (int)s->n_rec; h.soft_accumulate = (int)s->opt_soft_accumulate;
+  h.rec_stride = p.rec_cap_alloc; h.src_stride = s->src_steps;
+  h.rec_out = p.d_rec_out; h.src_samples = p.d_src_samples;
+  h.d_step = p.d_step; h.done = p.d_fused_done;
+  h.src = p.d_fused_items; h.rec = p.d_fused_items + s->n_src;
+  PF_CUDA(cudaMalloc(&p.d_fused, sizeof(h)));
+  PF_CUDA(cudaMemcpy(p.d_fused, &h, sizeof(h), cudaMemcpyHostToDevice));
+  p.fused = true;
   return PFDTD_OK;
 }
 
@@ -321,6 +367,8 @@ static int prepare_srcrec(pfdtd_solver* s) {
       p.rec_cap_alloc = s->rec_cap;
     }
   }
+  if (changed || s->fuse_dirty) PF_TRY(build_fused(s));
+  s->fuse_dirty = false;
   s->srcrec_dirty = false;
   s->src_dirty = false;
   if (changed && s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }   // the graph holds the old pointers
@@ -342,6 +390,7 @@ static UpdateArgs make_update_args(pfdtd_solver* s, Partition& p, int z_begin, i
   a.tma_hints = (int)s->opt_tma_hints;
   a.peer_plane = nullptr;
   a.sig_local = nullptr; a.sig_remote = nullptr; a.sig_side = 0;
+  a.fused_srcrec = nullptr;
   a.dif_order = p.dif_rowbase ? (int)s->opt_dif_order : 0;
   a.dif_state = p.dif_state;
   a.dif_rowbase = p.dif_rowbase;
@@ -387,9 +436,10 @@ static int ensure_class_tables(pfdtd_solver* s) {
 }
 
 static int launch_update(pfdtd_solver* s, Partition& p, int z_begin, int z_end, const TmaConfig& cfg, cudaStream_t st,
-                         bool timed, void* peer_plane = nullptr, int* sig_remote = nullptr, int sig_side = 0) {
+                         bool timed, void* peer_plane = nullptr, int* sig_remote = nullptr, int sig_side = 0, bool fused = false) {
   if (z_end <= z_begin) return PFDTD_OK;
   UpdateArgs a = make_update_args(s, p, z_begin, z_end, st);
+  a.fused_srcrec = fused ? p.d_fused : nullptr;
   a.peer_plane = peer_plane;
   a.sig_local = s->d_halo_flags;
   a.sig_remote = sig_remote;
@@ -496,8 +546,9 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
   if (single) {
     Partition& p = s->parts[0];
     PF_CUDA(cudaSetDevice(p.device));
-    PF_TRY(launch_srcrec_for(s, p, p.s_main, 1, 1, 1));
-    PF_TRY(launch_update(s, p, 1, (int)p.size - 1, p.cfg_full, p.s_main, timed));
+    // fused: the update launch records this step's receivers, injects the next step's sources and advances the step
+    if (!p.fused) PF_TRY(launch_srcrec_for(s, p, p.s_main, 1, 1, 1));
+    PF_TRY(launch_update(s, p, 1, (int)p.size - 1, p.cfg_full, p.s_main, timed, nullptr, nullptr, 0, p.fused));
     s->cur = 1 - c;
     return PFDTD_OK;
   }
@@ -578,8 +629,8 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
   return PFDTD_OK;
 }
 
-static int set_step_counters(pfdtd_solver* s, int step, int first_recordable) {
-  int h[2] = {step, first_recordable};
+static int set_step_counters(pfdtd_solver* s, int step, int first_recordable, int last_step) {
+  int h[3] = {step, first_recordable, last_step};
   for (auto& p : s->parts) {
     PF_CUDA(cudaSetDevice(p.device));
     cudaStream_t st = (s->parts.size() == 1 && !s->comm) ? p.s_main : p.s_edge;
@@ -822,6 +873,7 @@ static int64_t* option_slot(pfdtd_solver* s, int option) {
     case PFDTD_OPT_TMA_HINTS: return &s->opt_tma_hints;
     case PFDTD_OPT_DIF_ORDER: return &s->opt_dif_order;
     case PFDTD_OPT_PEER_STORES: return &s->opt_peer_stores;
+    case PFDTD_OPT_FUSE_SRCREC: return &s->opt_fuse_srcrec;
   }
   return nullptr;
 }
@@ -836,6 +888,7 @@ int pfdtd_set_option(pfdtd_solver* s, int option, int64_t value) {
            s->dif_order_built, (long long)value);
   *slot = value;
   s->tables_dirty = true;
+  s->fuse_dirty = true;
   if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
   return PFDTD_OK;
 }
@@ -1136,8 +1189,8 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
     }
     PF_CUDA(cudaMalloc(&p.materials, s->materials_host.size()));
     PF_CUDA(cudaMemcpy(p.materials, s->materials_host.data(), s->materials_host.size(), cudaMemcpyHostToDevice));
-    PF_CUDA(cudaMalloc(&p.d_step, 2 * sizeof(int)));
-    PF_CUDA(cudaMemset(p.d_step, 0, 2 * sizeof(int)));
+    PF_CUDA(cudaMalloc(&p.d_step, 4 * sizeof(int)));
+    PF_CUDA(cudaMemset(p.d_step, 0, 4 * sizeof(int)));
     int lo_pri = 0, hi_pri = 0;
     PF_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
     PF_CUDA(cudaStreamCreateWithPriority(&p.s_main, cudaStreamNonBlocking, lo_pri));
@@ -1529,13 +1582,20 @@ int pfdtd_enqueue_steps(pfdtd_solver* s, uint32_t first_step, uint32_t n_steps) 
     PF_CUDA(cudaEventCreate(&s->ev_h0));
     PF_CUDA(cudaEventCreate(&s->ev_h1));
   }
-  PF_TRY(set_step_counters(s, (int)first_step, (int)first_step));
+  PF_TRY(set_step_counters(s, (int)first_step, (int)first_step, (int)(first_step + n_steps) - 1));
   for (auto& p : s->parts) {
     PF_CUDA(cudaSetDevice(p.device));
     cudaStream_t lead = single ? p.s_main : p.s_edge;
     PF_CUDA(cudaEventRecord(p.ev_t0, lead));
   }
   uint32_t done = 0;
+  const bool fused = single && s->parts[0].fused;
+  if (fused && n_steps > 0) {   // sources of the first step; every later injection is done by the update launches
+    Partition& p = s->parts[0];
+    PF_CUDA(cudaSetDevice(p.device));
+    PF_TRY(launch_srcrec_for(s, p, p.s_main, 0, 1, 0));
+  }
+  const uint64_t per_step = fused ? 1 : 2;   // launches per step of a single slab
   // CUDA-graph replay of two-step blocks (single partition, untimed): the launch-bound regime of small meshes
   if (single && s->opt_use_graph && !timed && n_steps >= 8) {
     Partition& p = s->parts[0];
@@ -1547,7 +1607,7 @@ int pfdtd_enqueue_steps(pfdtd_solver* s, uint32_t first_step, uint32_t n_steps) 
       int rc = enqueue_one_step(s, false, false);
       if (rc == PFDTD_OK) rc = enqueue_one_step(s, false, false);
       cudaError_t ce = cudaStreamEndCapture(p.s_main, &g);
-      s->launch_count -= 4;   // capture recorded, nothing ran
+      s->launch_count -= 2 * per_step;   // capture recorded, nothing ran
       if (rc != PFDTD_OK) { if (g) cudaGraphDestroy(g); return rc; }
       PF_CUDA(ce);
       PF_CUDA(cudaGraphInstantiate(&s->graph_exec, g, 0));
@@ -1555,7 +1615,7 @@ int pfdtd_enqueue_steps(pfdtd_solver* s, uint32_t first_step, uint32_t n_steps) 
     }
     while (n_steps - done >= 2) {
       PF_CUDA(cudaGraphLaunch(s->graph_exec, p.s_main));
-      s->launch_count += 4;
+      s->launch_count += 2 * per_step;
       done += 2;
     }
   }
@@ -1564,7 +1624,7 @@ int pfdtd_enqueue_steps(pfdtd_solver* s, uint32_t first_step, uint32_t n_steps) 
   for (auto& p : s->parts) {
     PF_CUDA(cudaSetDevice(p.device));
     if (single) {
-      PF_TRY(launch_srcrec_for(s, p, p.s_main, 1, 0, 0));
+      if (!fused) PF_TRY(launch_srcrec_for(s, p, p.s_main, 1, 0, 0));   // fused: the last update launch has recorded them
       PF_CUDA(cudaEventRecord(p.ev_t1, p.s_main));
     } else {
       // the last step's interior, and the neighbours' halo copies into this partition's end planes
@@ -1745,7 +1805,7 @@ int pfdtd_step(pfdtd_solver* s, uint32_t step, int direction, void* h_response, 
   PF_TRY(prepare_srcrec(s));
   PF_TRY(ensure_class_tables(s));
   PF_TRY(sync_all(s));
-  PF_TRY(set_step_counters(s, (int)step, 0x7fffffff));
+  PF_TRY(set_step_counters(s, (int)step, 0x7fffffff, (int)step));
   const bool single = (s->parts.size() == 1 && !s->comm);
   for (auto& p : s->parts) {
     PF_CUDA(cudaSetDevice(p.device));

@@ -102,6 +102,8 @@ struct UpdateArgs {
   int* sig_local;          // this process's flag block
   int* sig_remote;         // the neighbour's flag word this launch publishes to (null: neighbour is in this process)
   int sig_side;            // 0: towards the lower neighbour, 1: towards the upper one
+  // single slab: device FusedSrcRec<T> (tma_common.cuh) -- receivers recorded / next sources injected by this launch; or null
+  const void* fused_srcrec;
   cudaStream_t stream;
 };
 
@@ -141,6 +143,20 @@ int launch_capture_slice(int dtype, const void* P, const uint8_t* pos, void* out
 int voxelize_to_device(int device, const float* h_vertices, uint32_t n_vertices, const uint32_t* h_indices, uint32_t n_triangles,
                        const uint8_t* h_tri_material, float dx, uint8_t** d_bid_out, uint8_t** d_mat_out, uint32_t* vx_out, uint32_t* vy_out,
                        uint32_t* vz_out, uint64_t* launches);
+
+// ---- sources / receivers handled inside the update launch (tma_common.cuh fused_srcrec); lives in device memory ----
+struct FusedItem { int x, y, z, slot, type; };   // voxel coordinates local to the slab
+template <typename T>
+struct FusedSrcRec {
+  int n_src, n_rec, soft_accumulate, pad;
+  long long rec_stride, src_stride;
+  T* rec_out;                    // [n_rec_total][rec_stride]
+  const T* src_samples;          // [n_src_total][src_stride]
+  int* d_step;                   // [0] step of the launch, [1] first recordable step, [2] last step of the enqueue
+  unsigned int* done;            // CTA counter
+  const FusedItem* src;
+  const FusedItem* rec;
+};
 
 // ---- source / receiver kernel (srcrec_kernels.cu) -------------------------------------------------
 struct SrcRecArgs {

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include "pfdtd_internal.h"
 
 namespace pfdtd {
 namespace {
@@ -157,6 +158,48 @@ __device__ __forceinline__ void halo_publish(int* __restrict__ local, int* __res
       local[HALO_SEQ + side] = seq;
       __threadfence_system();
       asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote_slot), "r"(seq) : "memory");
+    }
+  }
+}
+
+// ---- sources and receivers inside the update launch (single slab) ---------------------------------------------------
+// The reference's step is source(n) -> update -> receiver(n) (kernels3d.cu:93-104,164-173); receiver(n) and
+// source(n+1) both act on the field the update has just written.  So the CTA that computed a receiver's voxel records
+// it, and the CTA that computed a source's voxel overwrites (or adds to) what it stored with the next step's sample:
+// no second launch per step.  Lists live in device memory (built by the host: voxel coordinates, not linear indices, so
+// that "is it in my tile" is six compares).  d_step: [0] step n of this launch, [1] first recordable step, [2] last
+// step of the enqueue (its sources for n+1 are left to the next enqueue: the field a caller sees is the same as with
+// the separate launch).  The last CTA to finish advances the step.
+template <typename T>
+__device__ __forceinline__ void fused_srcrec(const FusedSrcRec<T>* __restrict__ sr, T* __restrict__ Pn, int X, int64_t XY, int x0, int y0, int ty,
+                                             int z_lo, int z_hi, int warp, int lane, int consumer_threads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(consumer_threads) : "memory");   // every store of this CTA's tile has been issued
+  if (warp != 0) return;
+  const int n = sr->d_step[0];
+  const int n_rec = sr->n_rec, n_src = sr->n_src;
+  if (n >= sr->d_step[1] && (long long)n < sr->rec_stride)
+    for (int i = lane; i < n_rec; i += 32) {
+      const FusedItem it = sr->rec[i];
+      if (it.x >= x0 && it.x < x0 + TX && it.y >= y0 && it.y < y0 + ty && it.z >= z_lo && it.z < z_hi)
+        sr->rec_out[(long long)it.slot * sr->rec_stride + n] = Pn[(int64_t)it.z * XY + (int64_t)it.y * X + it.x];
+    }
+  __syncwarp();
+  if (lane == 0) {
+    if (n < sr->d_step[2] && (long long)(n + 1) < sr->src_stride)
+      for (int i = 0; i < n_src; i++) {      // in source order: a later source at the same voxel wins, like the reference's loop
+        const FusedItem it = sr->src[i];
+        if (it.x >= x0 && it.x < x0 + TX && it.y >= y0 && it.y < y0 + ty && it.z >= z_lo && it.z < z_hi) {
+          T* q = Pn + (int64_t)it.z * XY + (int64_t)it.y * X + it.x;
+          const T v = sr->src_samples[(long long)it.slot * sr->src_stride + n + 1];
+          if (it.type == 0 /* PFDTD_SRC_HARD */ || !sr->soft_accumulate) *q = v;
+          else *q += v;
+        }
+      }
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    __threadfence();
+    if (atomicAdd(sr->done, 1u) == total - 1) {     // every CTA has read d_step[0] and finished: advance
+      *sr->done = 0u;
+      sr->d_step[0] = n + 1;
     }
   }
 }

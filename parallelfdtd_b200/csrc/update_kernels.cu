@@ -92,7 +92,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
                     const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                     T* __restrict__ Pn, T lam2, T a_air, int X, int Y, int z_begin, int z_end, int chunk, int hints,
                     const DifArgs<T> dif, const WideArgs<T> wide, T* __restrict__ peer, int* __restrict__ sig_local,
-                    int* __restrict__ sig_remote, int sig_side) {
+                    int* __restrict__ sig_remote, int sig_side, const FusedSrcRec<T>* __restrict__ fused) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY / RPW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -282,6 +282,8 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
       for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
     }
   }
+  // single slab: receivers of this step and sources of the next one, by the CTA that owns their voxel (tma_common.cuh)
+  if (fused != nullptr) fused_srcrec<T>(fused, Pn, X, XY, x0, y0, TY, z_lo, z_hi, warp, lane, NW * 32);
   // Edge launch of a slab (one plane): the plane is the neighbour slab's halo for the next step.  Every lane sends the
   // four voxels it has just written (read back from L2) straight into the neighbour's halo plane -- a peer-mapped
   // store over NVLink when the neighbour lives on another GPU -- so compute and halo transfer are one launch and the
@@ -386,7 +388,8 @@ int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupanc
   kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.cls, (const ClassEntry<T>*)a.class_table, a.n_classes, (T*)a.Pn,
                                           c.lam2, c.a_air, a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints, make_dif<T>(a), make_wide<T>(a),
                                           (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr, a.sig_local,
-                                          (a.z_end - a.z_begin == 1 && a.peer_plane) ? a.sig_remote : nullptr, a.sig_side);
+                                          (a.z_end - a.z_begin == 1 && a.peer_plane) ? a.sig_remote : nullptr, a.sig_side,
+                                          (const FusedSrcRec<T>*)a.fused_srcrec);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }
