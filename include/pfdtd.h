@@ -86,10 +86,12 @@ enum {
    * (peer-mapped stores; default 1).  0 = copy the planes with cudaMemcpyPeerAsync after the edge launches.
    * One process per GPU: the same through CUDA-IPC mappings (pfdtd_comm_init); 0 = ncclSend/ncclRecv. */
   PFDTD_OPT_PEER_STORES = 14,
-  /* single slab: record the receivers and inject the next step's sources inside the update launch (default 1) instead
-   * of a separate launch per step (the reference does both with per-element memcpys, kernels3d.cu:93-104,164-173).
-   * Same results; 0 keeps the separate launch.  Also bit 2 of PFDTD_OPT_TMA_HINTS: CTAs of the first / last tile row
-   * (rows lying in the y walls) are scheduled first. */
+  /* single slab: record the receivers and inject the next step's sources inside the update launch instead of a
+   * separate launch per step (the reference does both with per-element memcpys, kernels3d.cu:93-104,164-173).
+   * 1 (default): where the step is launch-bound (slabs up to 2^24 voxels, frequency-independent boundaries, at most 16
+   * sources + receivers); 2: for any slab size; 0: always the separate launch.  Same results either way.
+   * (Also bit 2 of PFDTD_OPT_TMA_HINTS: CTAs of the first / last tile row -- rows lying in the y walls -- are
+   * scheduled first.) */
   PFDTD_OPT_FUSE_SRCREC = 15
 };
 

@@ -54,13 +54,14 @@ __device__ __forceinline__ void load_plane(const T* __restrict__ pt, int r, int 
 }  // namespace
 
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: TY consumer warps (one tile row each) + 1 producer warp
-template <typename T, bool HAS_D3, int TY, int NST, int DIF, bool WIDE>
+template <typename T, bool HAS_D3, int TY, int NST, int DIF, bool WIDE, int TAIL>
 __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (TY == 7 ? (NST >= 6 ? 80 : 64) : (TY == 8 ? 72 : 56)) : (TY == 7 ? 128 : 96))
     fdtd_update_interp_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                            const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                            T* __restrict__ Pn, T d1, T d2, T d3, T d4, int X, int Y, int z_begin, int z_end, int chunk, int hints,
                            const DifArgs<T> dif, const WideArgs<T> wide, T* __restrict__ peer, int* __restrict__ sig_local,
-                           int* __restrict__ sig_remote, int sig_side, const FusedSrcRec<T>* __restrict__ fused) {
+                           int* __restrict__ sig_remote, int sig_side, const __grid_constant__ FusedParams fused_p,
+                    const FusedSrcRec<T>* __restrict__ fused) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -156,28 +157,29 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
       } else {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const ClassEntry<T> ce = class_entry<T, WIDE>(s_table, wide, (pw >> (8 * q)) & 0xffu, (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx + q);
+          const ClassEntry<T> ce = class_entry<T, WIDE>(s_table, wide, (pw >> (8 * q)) & 0xffu,
+                                                        WIDE ? (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx + q : 0);
           res.v[q] = voxel_interp<T, HAS_D3>(ce.c0, ce.c1, ce.c2, pc.c[q], pc.a4[q], pc.g4[q], pm.c[q], pm.a4[q], pm.g4[q], pp.c[q],
                                              pp.a4[q], pp.g4[q], old.v[q], d1, d2, d3);
         }
       }
     }
-    if (DIF) drow.apply(j, res.v, old.v, pw, active, lane, dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0),
-                        (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx);
-    if (active) stg4(Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx, res);
+    T* const vox_ptr = Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx;     // this lane's four voxels of plane z
+    if (DIF) drow.apply(j, res.v, old.v, pw, active, lane, dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0), vox_ptr, Pn);
+    if (active) stg4(vox_ptr, res);
     // the store above consumed everything read from stage s2 (and, at j == 0, from the two prologue stages)
     __syncwarp();
     if (lane == 0) {
       mbar_arrive(&bar_empty[s2]);
       if (j == 0) { mbar_arrive(&bar_empty[0]); mbar_arrive(&bar_empty[1 % NST]); }
     }
-    if (DIF) drow.next(dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0), Pn + (int64_t)gy * X + x0, XY, j, n, z_lo, z_hi, gy, Y, lane);
+    if (DIF) drow.next(dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0), vox_ptr + XY - 4 * lane, XY, j, n, z_lo, z_hi, gy, Y, lane);
     pm = pc;
     pc = pp;
   }
-  if (fused != nullptr) fused_srcrec<T>(fused, Pn, X, XY, x0, y0, TY, z_lo, z_hi, warp, lane, NW * 32);
+  if (TAIL == 2) fused_srcrec<T>(fused_p, fused, Pn, X, Y, TY, z_begin, z_end, chunk, hints, NW * 32);
   // edge launch of a slab (one plane): send the plane into the neighbour slab's halo plane (update_kernels.cu)
-  if (peer != nullptr && n == 1) {
+  if (TAIL == 1 && peer != nullptr && n == 1) {
     if (active) {
       const int64_t row = (int64_t)gy * X + gx;
       V4<T> v;
@@ -217,9 +219,9 @@ __global__ void __launch_bounds__(128) fdtd_update_interp_plain(const uint8_t* _
 
 namespace {
 
-template <typename T, bool HAS_D3, int TY, int NST, int DIF, bool WIDE = false>
+template <typename T, bool HAS_D3, int TY, int NST, int DIF, bool WIDE = false, int TAIL = 0>
 int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupancy_out) {
-  auto kern = fdtd_update_interp_tma<T, HAS_D3, TY, NST, DIF, WIDE>;
+  auto kern = fdtd_update_interp_tma<T, HAS_D3, TY, NST, DIF, WIDE, TAIL>;
   const int smem = NST * TileGeom<T, TY>::STAGE_BYTES;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -240,37 +242,38 @@ int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occup
                                           c.d[1], c.d[2], c.d[3], a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints, make_dif<T>(a), make_wide<T>(a),
                                           (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr, a.sig_local,
                                           (a.z_end - a.z_begin == 1 && a.peer_plane) ? a.sig_remote : nullptr, a.sig_side,
-                                          (const FusedSrcRec<T>*)a.fused_srcrec);
+                                          a.fused_params, (const FusedSrcRec<T>*)a.fused_srcrec);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
+}
+
+// filter boundaries, wide meshes and launches with a tail: one kernel per order on the 128x7 shape (fp32 six stages:
+// 80 registers, three CTAs per SM; fp64 five)
+template <typename T, bool HAS_D3, bool WIDE, int TAIL>
+int dispatch_interp_order(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occ) {
+  constexpr int DTY = 7, DNST = sizeof(T) == 4 ? 6 : 5;
+  switch (a.dif_order) {
+    case 0: return launch_interp_t<T, HAS_D3, DTY, DNST, 0, WIDE, TAIL>(a, m, chunk, occ);
+    case 1: return launch_interp_t<T, HAS_D3, DTY, DNST, 1, WIDE, TAIL>(a, m, chunk, occ);
+    case 2: return launch_interp_t<T, HAS_D3, DTY, DNST, 2, WIDE, TAIL>(a, m, chunk, occ);
+    case 3: return launch_interp_t<T, HAS_D3, DTY, DNST, 3, WIDE, TAIL>(a, m, chunk, occ);
+    case 4: return launch_interp_t<T, HAS_D3, DTY, DNST, 4, WIDE, TAIL>(a, m, chunk, occ);
+  }
+  set_error("filter order %d is not supported", a.dif_order);
+  return PFDTD_ERR_INVALID;
 }
 
 template <typename T, bool HAS_D3>
 int dispatch_interp(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
   // tile variants shared with the 7-point kernel: only the one-row-per-warp shapes apply here
-  // filter boundaries: one kernel per order on the 128x7 shape; fp32 six stages, fp64 five; wide meshes run on it too
-  constexpr int DTY = 7, DNST = sizeof(T) == 4 ? 6 : 5;   // fp32: 80 registers, three CTAs per SM
-  if (a.wide) {
-    switch (a.dif_order) {
-      case 0: return launch_interp_t<T, HAS_D3, DTY, DNST, 0, true>(a, m, chunk, occ);
-      case 1: return launch_interp_t<T, HAS_D3, DTY, DNST, 1, true>(a, m, chunk, occ);
-      case 2: return launch_interp_t<T, HAS_D3, DTY, DNST, 2, true>(a, m, chunk, occ);
-      case 3: return launch_interp_t<T, HAS_D3, DTY, DNST, 3, true>(a, m, chunk, occ);
-      case 4: return launch_interp_t<T, HAS_D3, DTY, DNST, 4, true>(a, m, chunk, occ);
-    }
-    set_error("filter order %d is not supported", a.dif_order);
-    return PFDTD_ERR_INVALID;
+  constexpr int DTY = 7, DNST = sizeof(T) == 4 ? 6 : 5;
+  if (a.tail == 1) return a.wide ? dispatch_interp_order<T, HAS_D3, true, 1>(a, m, chunk, occ) : dispatch_interp_order<T, HAS_D3, false, 1>(a, m, chunk, occ);
+  if (a.tail == 2) {
+    PF_CHECK(a.dif_order == 0 && !a.wide, PFDTD_ERR_INVALID, "fused sources / receivers are built for the frequency-independent kernels");
+    return launch_interp_t<T, HAS_D3, DTY, DNST, 0, false, 2>(a, m, chunk, occ);
   }
-  if (a.dif_order > 0) {
-    switch (a.dif_order) {
-      case 1: return launch_interp_t<T, HAS_D3, DTY, DNST, 1>(a, m, chunk, occ);
-      case 2: return launch_interp_t<T, HAS_D3, DTY, DNST, 2>(a, m, chunk, occ);
-      case 3: return launch_interp_t<T, HAS_D3, DTY, DNST, 3>(a, m, chunk, occ);
-      case 4: return launch_interp_t<T, HAS_D3, DTY, DNST, 4>(a, m, chunk, occ);
-    }
-    set_error("filter order %d is not supported", a.dif_order);
-    return PFDTD_ERR_INVALID;
-  }
+  if (a.wide) return dispatch_interp_order<T, HAS_D3, true, 0>(a, m, chunk, occ);
+  if (a.dif_order > 0) return dispatch_interp_order<T, HAS_D3, false, 0>(a, m, chunk, occ);
   switch (tile) {
     case 0: case 3: return launch_interp_t<T, HAS_D3, 8, 4, 0>(a, m, chunk, occ);
     case 2: case 1: case 4: return launch_interp_t<T, HAS_D3, 16, 4, 0>(a, m, chunk, occ);

@@ -100,13 +100,15 @@ struct Partition {
   cudaEvent_t ev_src = nullptr, ev_int = nullptr, ev_edge = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   bool use_tma = false;
   TmaMaps maps[2];                      // maps[c]: current field = P[c], overwritten field = P[1-c]
+  TmaMaps maps_tail[2];                 // the same for the tile shape of the launches with a tail (edge planes, fused sources / receivers)
+  TmaConfig cfg_tail_full{0, 1, 0};     // full slab on that shape (fused launches)
   TmaConfig cfg_full{0, 1, 0}, cfg_int{0, 1, 0}, cfg_edge{0, 1, 0};
   int* d_step = nullptr;                // [0] step counter, [1] first recordable step, [2] last step of the current enqueue
   // sources / receivers handled by the update launch itself (single slab; tma_common.cuh fused_srcrec)
   bool fused = false;
+  FusedParams fused_params{};           // item coordinates, passed to the launch by value
   void* d_fused = nullptr;              // FusedSrcRec<T>
-  FusedItem* d_fused_items = nullptr;   // sources, then receivers
-  unsigned int* d_fused_done = nullptr;
+  int* d_item_step = nullptr;           // [n_src + n_rec] per-item step counters
   // sources / receivers that live in this partition
   int n_src = 0, n_rec = 0;
   int64_t* d_src_elem = nullptr; int32_t* d_src_type = nullptr; int32_t* d_src_slot = nullptr;
@@ -224,7 +226,7 @@ static int free_partitions(pfdtd_solver* s) {
     cudaFree(p.dif_state); cudaFree(p.dif_rowbase); cudaFree(p.dif_table);
     cudaFree(p.d_wide_keys); cudaFree(p.wide_class_table); cudaFree(p.wide_dif_table);
     cudaFree(p.P[0]); cudaFree(p.P[1]); cudaFree(p.materials); cudaFree(p.d_step);
-    cudaFree(p.d_fused); cudaFree(p.d_fused_items); cudaFree(p.d_fused_done);
+    cudaFree(p.d_fused); cudaFree(p.d_item_step);
     cudaFree(p.d_src_elem); cudaFree(p.d_src_type); cudaFree(p.d_src_slot); cudaFree(p.d_rec_elem); cudaFree(p.d_rec_slot);
     cudaFree(p.d_src_samples); cudaFree(p.d_rec_out);
     if (p.s_main) cudaStreamDestroy(p.s_main);
@@ -258,36 +260,43 @@ static int upload_new(void** d, const void* h, size_t bytes) {
 static int build_fused(pfdtd_solver* s) {
   for (auto& p : s->parts) {
     p.fused = false;
-    cudaFree(p.d_fused); cudaFree(p.d_fused_items); cudaFree(p.d_fused_done);
-    p.d_fused = nullptr; p.d_fused_items = nullptr; p.d_fused_done = nullptr;
+    p.fused_params = FusedParams{};
+    cudaFree(p.d_fused); cudaFree(p.d_item_step);
+    p.d_fused = nullptr; p.d_item_step = nullptr;
   }
   if (s->parts.size() != 1 || s->comm || !s->opt_fuse_srcrec) return PFDTD_OK;
   Partition& p = s->parts[0];
-  if (!p.use_tma || s->n_src > 64 || s->n_rec > 4096 || s->n_src + s->n_rec == 0) return PFDTD_OK;
+  if (!p.use_tma || s->n_src + s->n_rec > PFDTD_FUSED_MAX || s->n_src + s->n_rec == 0) return PFDTD_OK;
+  // Worth it where the step is launch-bound: a second launch costs a few microseconds per step, the tail costs every CTA
+  // a few hundred cycles -- small slabs only (option value 2 forces it for any size); frequency-independent, narrow classes.
+  if (s->opt_dif_order != 0 || s->wide) return PFDTD_OK;
+  if (s->opt_fuse_srcrec < 2 && (uint64_t)s->X * s->Y * (uint64_t)p.size > (1ull << 24)) return PFDTD_OK;
   const int64_t zoff = s->opt_global_z_first;
-  std::vector<FusedItem> items;
+  FusedParams fp{};
+  FusedSrcRec<void> h{};
+  int k = 0;
   for (int pass = 0; pass < 2; pass++) {
     const uint32_t n = pass == 0 ? s->n_src : s->n_rec;
     const std::vector<int32_t>& xyz = pass == 0 ? s->src_xyz : s->rec_xyz;
-    for (uint32_t i = 0; i < n; i++) {
+    for (uint32_t i = 0; i < n; i++, k++) {
       const int64_t z = (int64_t)xyz[3 * i + 2] - zoff - p.first;
       if (z < 1 || z > p.size - 2) return PFDTD_OK;             // a plane this slab never updates: separate launch
-      items.push_back(FusedItem{xyz[3 * i], xyz[3 * i + 1], (int)z, (int)i, pass == 0 ? s->src_type[i] : 0});
+      fp.xyz[k][0] = xyz[3 * i]; fp.xyz[k][1] = xyz[3 * i + 1]; fp.xyz[k][2] = (int)z;
+      h.slot[k] = (int)i;
+      h.type[k] = pass == 0 ? s->src_type[i] : 0;
     }
   }
+  fp.n_src = (int)s->n_src; fp.n_rec = (int)s->n_rec;
   PF_CUDA(cudaSetDevice(p.device));
-  PF_CUDA(cudaMalloc(&p.d_fused_items, items.size() * sizeof(FusedItem)));
-  PF_CUDA(cudaMemcpy(p.d_fused_items, items.data(), items.size() * sizeof(FusedItem), cudaMemcpyHostToDevice));
-  PF_CUDA(cudaMalloc(&p.d_fused_done, sizeof(unsigned int)));
-  PF_CUDA(cudaMemset(p.d_fused_done, 0, sizeof(unsigned int)));
-  FusedSrcRec<void> h{};
-  h.n_src = (int)s->n_src; h.n_rec = (int)s->n_rec; h.soft_accumulate = (int)s->opt_soft_accumulate;
+  PF_CUDA(cudaMalloc(&p.d_item_step, PFDTD_FUSED_MAX * sizeof(int)));
+  PF_CUDA(cudaMemset(p.d_item_step, 0, PFDTD_FUSED_MAX * sizeof(int)));
+  h.soft_accumulate = (int)s->opt_soft_accumulate;
   h.rec_stride = p.rec_cap_alloc; h.src_stride = s->src_steps;
   h.rec_out = p.d_rec_out; h.src_samples = p.d_src_samples;
-  h.d_step = p.d_step; h.done = p.d_fused_done;
-  h.src = p.d_fused_items; h.rec = p.d_fused_items + s->n_src;
+  h.d_step = p.d_step; h.item_step = p.d_item_step;
   PF_CUDA(cudaMalloc(&p.d_fused, sizeof(h)));
   PF_CUDA(cudaMemcpy(p.d_fused, &h, sizeof(h), cudaMemcpyHostToDevice));
+  p.fused_params = fp;
   p.fused = true;
   return PFDTD_OK;
 }
@@ -390,7 +399,9 @@ static UpdateArgs make_update_args(pfdtd_solver* s, Partition& p, int z_begin, i
   a.tma_hints = (int)s->opt_tma_hints;
   a.peer_plane = nullptr;
   a.sig_local = nullptr; a.sig_remote = nullptr; a.sig_side = 0;
+  a.tail = 0;
   a.fused_srcrec = nullptr;
+  a.fused_params = FusedParams{};
   a.dif_order = p.dif_rowbase ? (int)s->opt_dif_order : 0;
   a.dif_state = p.dif_state;
   a.dif_rowbase = p.dif_rowbase;
@@ -439,7 +450,11 @@ static int launch_update(pfdtd_solver* s, Partition& p, int z_begin, int z_end, 
                          bool timed, void* peer_plane = nullptr, int* sig_remote = nullptr, int sig_side = 0, bool fused = false) {
   if (z_end <= z_begin) return PFDTD_OK;
   UpdateArgs a = make_update_args(s, p, z_begin, z_end, st);
-  a.fused_srcrec = fused ? p.d_fused : nullptr;
+  if (fused) { a.fused_srcrec = p.d_fused; a.fused_params = p.fused_params; a.tail = 2; }
+  else if (peer_plane != nullptr && z_end - z_begin == 1 && p.use_tma) a.tail = 1;
+  const TmaMaps& maps = a.tail ? p.maps_tail[s->cur] : p.maps[s->cur];
+  TmaConfig cfg_used = cfg;
+  if (a.tail == 1) cfg_used.tile = tma_tail_tile(s->dtype, s->scheme);
   a.peer_plane = peer_plane;
   a.sig_local = s->d_halo_flags;
   a.sig_remote = sig_remote;
@@ -454,9 +469,9 @@ static int launch_update(pfdtd_solver* s, Partition& p, int z_begin, int z_end, 
     PF_CUDA(cudaEventRecord(e0, st));
   }
   if (s->scheme == SCH_INTERP) {
-    if (p.use_tma) PF_TRY(launch_update_interp_tma(a, p.maps[s->cur], cfg, nullptr));
+    if (p.use_tma) PF_TRY(launch_update_interp_tma(a, maps, cfg_used, nullptr));
     else PF_TRY(launch_update_interp_plain(a));
-  } else if (p.use_tma) PF_TRY(launch_update_tma(a, p.maps[s->cur], cfg));
+  } else if (p.use_tma) PF_TRY(launch_update_tma(a, maps, cfg_used));
   else PF_TRY(launch_update_plain(a));
   if (timed) PF_CUDA(cudaEventRecord(e1, st));
   s->launch_count++;
@@ -548,7 +563,7 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
     PF_CUDA(cudaSetDevice(p.device));
     // fused: the update launch records this step's receivers, injects the next step's sources and advances the step
     if (!p.fused) PF_TRY(launch_srcrec_for(s, p, p.s_main, 1, 1, 1));
-    PF_TRY(launch_update(s, p, 1, (int)p.size - 1, p.cfg_full, p.s_main, timed, nullptr, nullptr, 0, p.fused));
+    PF_TRY(launch_update(s, p, 1, (int)p.size - 1, p.fused ? p.cfg_tail_full : p.cfg_full, p.s_main, timed, nullptr, nullptr, 0, p.fused));
     s->cur = 1 - c;
     return PFDTD_OK;
   }
@@ -635,6 +650,11 @@ static int set_step_counters(pfdtd_solver* s, int step, int first_recordable, in
     PF_CUDA(cudaSetDevice(p.device));
     cudaStream_t st = (s->parts.size() == 1 && !s->comm) ? p.s_main : p.s_edge;
     PF_CUDA(cudaMemcpyAsync(p.d_step, h, sizeof(h), cudaMemcpyHostToDevice, st));
+    if (p.d_item_step) {
+      int items[PFDTD_FUSED_MAX];
+      for (int& v : items) v = step;
+      PF_CUDA(cudaMemcpyAsync(p.d_item_step, items, sizeof(items), cudaMemcpyHostToDevice, st));
+    }
   }
   return PFDTD_OK;
 }
@@ -1250,8 +1270,13 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->opt_dif_order, s->wide, (int)s->X, (int)s->Y, std::max(1, nplanes - 2), p.device,
                              p.cfg_full.tile + 1, s->opt_tma_chunk, &p.cfg_int));
       p.cfg_edge = TmaConfig{p.cfg_full.tile, 1, p.cfg_full.occupancy};
-      for (int c = 0; c < 2; c++)
+      const int tail_tile = tma_tail_tile(s->dtype, s->scheme);
+      PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->opt_dif_order, s->wide, (int)s->X, (int)s->Y, nplanes, p.device, tail_tile + 1,
+                             s->opt_tma_chunk, &p.cfg_tail_full));
+      for (int c = 0; c < 2; c++) {
         PF_TRY(tma_encode_maps(&p.maps[c], s->dtype, p.cfg_full.tile, p.P[c], p.P[1 - c], p.cls, (int)s->X, (int)s->Y, (int)p.size));
+        PF_TRY(tma_encode_maps(&p.maps_tail[c], s->dtype, tail_tile, p.P[c], p.P[1 - c], p.cls, (int)s->X, (int)s->Y, (int)p.size));
+      }
     }
   }
   if (s->d_pos0) {   // free the staging volumes (cudaMesh.h:704-707)

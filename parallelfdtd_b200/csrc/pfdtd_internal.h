@@ -58,6 +58,26 @@ int launch_assign_classes(const uint8_t* d_pos, const uint8_t* d_mat, uint64_t n
                           uint32_t X, uint32_t Y, uint32_t Z, const uint32_t* d_table, const uint8_t* d_ids, uint32_t cap,
                           uint8_t* d_cls, cudaStream_t stream);
 
+// ---- sources / receivers handled inside the update launch (tma_common.cuh fused_srcrec) ------------------------------
+// The voxel coordinates travel as a kernel parameter (constant bank): "does my tile own one of them" costs a CTA a few
+// compares and no memory access; only the owning CTAs touch the descriptor in device memory.
+#define PFDTD_FUSED_MAX 16
+struct FusedParams {
+  int n_src, n_rec;                 // items [0, n_src) are sources, [n_src, n_src + n_rec) receivers; 0 / 0 = off
+  int xyz[PFDTD_FUSED_MAX][3];      // voxel coordinates local to the slab
+};
+template <typename T>
+struct FusedSrcRec {                // device memory, read by owning CTAs only
+  int soft_accumulate, pad;
+  long long rec_stride, src_stride;
+  T* rec_out;                       // [n_rec_total][rec_stride]
+  const T* src_samples;             // [n_src_total][src_stride]
+  const int* d_step;                // [1] first recordable step, [2] last step of the enqueue
+  int* item_step;                   // [n_src + n_rec] step each item is at (advanced by its owner CTA)
+  int slot[PFDTD_FUSED_MAX];        // row in src_samples / rec_out
+  int type[PFDTD_FUSED_MAX];        // source type
+};
+
 // ---- update kernels (update_kernels.cu) ---------------------------------------------------------
 struct TmaMaps {           // tensor maps of one partition for one (cur,new) buffer assignment
   CUtensorMap p_halo;      // P (current field), box with x/y halo
@@ -102,8 +122,11 @@ struct UpdateArgs {
   int* sig_local;          // this process's flag block
   int* sig_remote;         // the neighbour's flag word this launch publishes to (null: neighbour is in this process)
   int sig_side;            // 0: towards the lower neighbour, 1: towards the upper one
-  // single slab: device FusedSrcRec<T> (tma_common.cuh) -- receivers recorded / next sources injected by this launch; or null
-  const void* fused_srcrec;
+  // what the CTAs do after their march: 0 nothing, 1 edge launch (peer_plane / sig_*), 2 fused sources / receivers.
+  // Launches with a tail run on the tile shape of tma_tail_tile() and need tensor maps encoded for it.
+  int tail;
+  FusedParams fused_params;
+  const void* fused_srcrec;     // device FusedSrcRec<T>
   cudaStream_t stream;
 };
 
@@ -133,6 +156,7 @@ int launch_update_plain(const UpdateArgs& a);
 int launch_update_interp_tma(const UpdateArgs& a, const TmaMaps& maps, const TmaConfig& cfg, int* occupancy_out);
 int launch_update_interp_plain(const UpdateArgs& a);
 const char* tma_tile_name(int dtype, int tile);
+int tma_tail_tile(int dtype, int scheme);
 
 // ---- capture kernel (capture_kernels.cu): planes [z_lo, z_lo+nz) of a partition, orientation 1 (xz) or 2 (yz)
 int launch_capture_slice(int dtype, const void* P, const uint8_t* pos, void* out_p, uint8_t* out_pos, uint32_t X, uint32_t Y,
@@ -143,20 +167,6 @@ int launch_capture_slice(int dtype, const void* P, const uint8_t* pos, void* out
 int voxelize_to_device(int device, const float* h_vertices, uint32_t n_vertices, const uint32_t* h_indices, uint32_t n_triangles,
                        const uint8_t* h_tri_material, float dx, uint8_t** d_bid_out, uint8_t** d_mat_out, uint32_t* vx_out, uint32_t* vy_out,
                        uint32_t* vz_out, uint64_t* launches);
-
-// ---- sources / receivers handled inside the update launch (tma_common.cuh fused_srcrec); lives in device memory ----
-struct FusedItem { int x, y, z, slot, type; };   // voxel coordinates local to the slab
-template <typename T>
-struct FusedSrcRec {
-  int n_src, n_rec, soft_accumulate, pad;
-  long long rec_stride, src_stride;
-  T* rec_out;                    // [n_rec_total][rec_stride]
-  const T* src_samples;          // [n_src_total][src_stride]
-  int* d_step;                   // [0] step of the launch, [1] first recordable step, [2] last step of the enqueue
-  unsigned int* done;            // CTA counter
-  const FusedItem* src;
-  const FusedItem* rec;
-};
 
 // ---- source / receiver kernel (srcrec_kernels.cu) -------------------------------------------------
 struct SrcRecArgs {

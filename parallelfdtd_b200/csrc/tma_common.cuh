@@ -162,48 +162,6 @@ __device__ __forceinline__ void halo_publish(int* __restrict__ local, int* __res
   }
 }
 
-// ---- sources and receivers inside the update launch (single slab) ---------------------------------------------------
-// The reference's step is source(n) -> update -> receiver(n) (kernels3d.cu:93-104,164-173); receiver(n) and
-// source(n+1) both act on the field the update has just written.  So the CTA that computed a receiver's voxel records
-// it, and the CTA that computed a source's voxel overwrites (or adds to) what it stored with the next step's sample:
-// no second launch per step.  Lists live in device memory (built by the host: voxel coordinates, not linear indices, so
-// that "is it in my tile" is six compares).  d_step: [0] step n of this launch, [1] first recordable step, [2] last
-// step of the enqueue (its sources for n+1 are left to the next enqueue: the field a caller sees is the same as with
-// the separate launch).  The last CTA to finish advances the step.
-template <typename T>
-__device__ __forceinline__ void fused_srcrec(const FusedSrcRec<T>* __restrict__ sr, T* __restrict__ Pn, int X, int64_t XY, int x0, int y0, int ty,
-                                             int z_lo, int z_hi, int warp, int lane, int consumer_threads) {
-  asm volatile("bar.sync 1, %0;" ::"r"(consumer_threads) : "memory");   // every store of this CTA's tile has been issued
-  if (warp != 0) return;
-  const int n = sr->d_step[0];
-  const int n_rec = sr->n_rec, n_src = sr->n_src;
-  if (n >= sr->d_step[1] && (long long)n < sr->rec_stride)
-    for (int i = lane; i < n_rec; i += 32) {
-      const FusedItem it = sr->rec[i];
-      if (it.x >= x0 && it.x < x0 + TX && it.y >= y0 && it.y < y0 + ty && it.z >= z_lo && it.z < z_hi)
-        sr->rec_out[(long long)it.slot * sr->rec_stride + n] = Pn[(int64_t)it.z * XY + (int64_t)it.y * X + it.x];
-    }
-  __syncwarp();
-  if (lane == 0) {
-    if (n < sr->d_step[2] && (long long)(n + 1) < sr->src_stride)
-      for (int i = 0; i < n_src; i++) {      // in source order: a later source at the same voxel wins, like the reference's loop
-        const FusedItem it = sr->src[i];
-        if (it.x >= x0 && it.x < x0 + TX && it.y >= y0 && it.y < y0 + ty && it.z >= z_lo && it.z < z_hi) {
-          T* q = Pn + (int64_t)it.z * XY + (int64_t)it.y * X + it.x;
-          const T v = sr->src_samples[(long long)it.slot * sr->src_stride + n + 1];
-          if (it.type == 0 /* PFDTD_SRC_HARD */ || !sr->soft_accumulate) *q = v;
-          else *q += v;
-        }
-      }
-    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-    __threadfence();
-    if (atomicAdd(sr->done, 1u) == total - 1) {     // every CTA has read d_step[0] and finished: advance
-      *sr->done = 0u;
-      sr->d_step[0] = n + 1;
-    }
-  }
-}
-
 // CTA -> (tile row, z chunk).  Natural order, or (hint bit 2) the first and last tile rows of every chunk first: in a
 // room those hold the rows that lie in the y walls, whose warps pay a state round trip per plane -- started first,
 // they finish inside the launch instead of forming its tail.  blockIdx.x (the tile column) is never remapped.
@@ -217,6 +175,52 @@ __device__ __forceinline__ void cta_tile(int heavy_first, int& by, int& bz) {
   if (t < n_heavy) { by = (t & 1) ? gy - 1 : 0; bz = t >> 1; }
   else { t -= n_heavy; by = 1 + t % (gy - 2); bz = t / (gy - 2); }
   (void)gx;
+}
+
+// ---- sources and receivers inside the update launch (single slab) ---------------------------------------------------
+// The reference's step is source(n) -> update -> receiver(n) (kernels3d.cu:93-104,164-173); receiver(n) and
+// source(n+1) both act on the field the update has just written.  So the CTA that computed a receiver's voxel records
+// it, and the CTA that computed a source's voxel overwrites (or adds to) what it stored with the next step's sample:
+// no second launch per step.  Every CTA compares its tile with the item coordinates in the kernel parameters (no memory
+// access); the few owners do the rest.  Each item carries its own step counter, advanced by its owner, so there is no
+// grid-wide hand-over.  Out of line and fed only by kernel parameters: the tile is recomputed here instead of being
+// kept alive across the march (every value that lives across the plane loop costs a register the loop does not have).
+template <typename T>
+__device__ __noinline__ void fused_srcrec(const FusedParams& fp, const FusedSrcRec<T>* __restrict__ sr, T* __restrict__ Pn, int X, int Y,
+                                          int ty, int z_begin, int z_end, int chunk, int hints, int consumer_threads) {
+  int cby, cbz;
+  cta_tile(hints & 4, cby, cbz);
+  const int x0 = blockIdx.x * TX, y0 = cby * ty;
+  const int z_lo = z_begin + cbz * chunk, z_hi = min(z_lo + chunk, z_end);
+  const int n_items = fp.n_src + fp.n_rec;
+  unsigned mine = 0u;                                 // CTA-uniform: bit i = item i lies in this CTA's tile
+  for (int i = 0; i < n_items; i++) {
+    const int x = fp.xyz[i][0], y = fp.xyz[i][1], z = fp.xyz[i][2];
+    if (x >= x0 && x < x0 + TX && y >= y0 && y < y0 + ty && z >= z_lo && z < z_hi) mine |= 1u << i;
+  }
+  if (mine == 0u) return;
+  asm volatile("bar.sync 1, %0;" ::"r"(consumer_threads) : "memory");   // every store of this CTA's tile has been issued
+  if (threadIdx.x != 0) return;
+  const int64_t XY = (int64_t)X * Y;
+  const int first_recordable = sr->d_step[1], last = sr->d_step[2];
+  for (int i = fp.n_src; i < n_items; i++)            // receivers first: they see the field before the next injection
+    if (mine & (1u << i)) {
+      const int n = sr->item_step[i];
+      if (n >= first_recordable && (long long)n < sr->rec_stride)
+        sr->rec_out[(long long)sr->slot[i] * sr->rec_stride + n] = Pn[(int64_t)fp.xyz[i][2] * XY + (int64_t)fp.xyz[i][1] * X + fp.xyz[i][0]];
+      sr->item_step[i] = n + 1;
+    }
+  for (int i = 0; i < fp.n_src; i++)                  // in source order: a later source at the same voxel wins, like the reference's loop
+    if (mine & (1u << i)) {
+      const int n = sr->item_step[i];
+      if (n < last && (long long)(n + 1) < sr->src_stride) {
+        T* q = Pn + (int64_t)fp.xyz[i][2] * XY + (int64_t)fp.xyz[i][1] * X + fp.xyz[i][0];
+        const T v = sr->src_samples[(long long)sr->slot[i] * sr->src_stride + n + 1];
+        if (sr->type[i] == 0 /* PFDTD_SRC_HARD */ || !sr->soft_accumulate) *q = v;
+        else *q += v;
+      }
+      sr->item_step[i] = n + 1;
+    }
 }
 
 constexpr int align128(int x) { return (x + 127) & ~127; }

@@ -86,13 +86,16 @@ constexpr int tma_max_regs(size_t esize, int scheme, int ty, int rpw, int nst, i
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: (TY/RPW + 1) warps (last warp = TMA producer)
 // DIF = 0: frequency-independent boundaries; 1..4: digital impedance filters of that order
 // (one-row-per-warp 128x8 tile: three resident CTAs per SM in fp32, two in fp64)
-template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF, bool WIDE>
+// TAIL: what a CTA does after its march -- 0 nothing (the bulk launches), 1 edge launch of a slab (store the plane into the
+// neighbour's halo plane and publish the step), 2 record receivers / inject the next sources (single small slab)
+template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF, bool WIDE, int TAIL>
 __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(sizeof(T), SCHEME, TY, RPW, NST, DIF))
     fdtd_update_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                     const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                     T* __restrict__ Pn, T lam2, T a_air, int X, int Y, int z_begin, int z_end, int chunk, int hints,
                     const DifArgs<T> dif, const WideArgs<T> wide, T* __restrict__ peer, int* __restrict__ sig_local,
-                    int* __restrict__ sig_remote, int sig_side, const FusedSrcRec<T>* __restrict__ fused) {
+                    int* __restrict__ sig_remote, int sig_side, const __grid_constant__ FusedParams fused_p,
+                    const FusedSrcRec<T>* __restrict__ fused) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY / RPW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
           }
         }
         if (DIF) drow.apply(j, res.v, old[k].v, pw[k], active, lane, dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0),
-                            (out - Pn) + (int64_t)k * X);
+                            out + (int64_t)k * X, Pn);
         if (active) stg4(out + (int64_t)k * X, res);
       }
       out += XY;
@@ -277,18 +280,18 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
         mbar_arrive_a(be + 8 * ((u + 1) % NST));
         if (j == 0) mbar_arrive_a(be);   // plane z_lo-1, read in the prologue
       }
-      if (DIF) drow.next(dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0), Pn + (int64_t)(y0 + r0) * X + x0, XY, j, n, z_lo, z_hi, y0 + r0, Y, lane);
+      if (DIF) drow.next(dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0), out - xl, XY, j, n, z_lo, z_hi, y0 + r0, Y, lane);
 #pragma unroll
       for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
     }
   }
   // single slab: receivers of this step and sources of the next one, by the CTA that owns their voxel (tma_common.cuh)
-  if (fused != nullptr) fused_srcrec<T>(fused, Pn, X, XY, x0, y0, TY, z_lo, z_hi, warp, lane, NW * 32);
+  if (TAIL == 2) fused_srcrec<T>(fused_p, fused, Pn, X, Y, TY, z_begin, z_end, chunk, hints, NW * 32);
   // Edge launch of a slab (one plane): the plane is the neighbour slab's halo for the next step.  Every lane sends the
   // four voxels it has just written (read back from L2) straight into the neighbour's halo plane -- a peer-mapped
   // store over NVLink when the neighbour lives on another GPU -- so compute and halo transfer are one launch and the
   // tiles that finish first travel while the others are still being computed.
-  if (peer != nullptr && n == 1) {
+  if (TAIL == 1 && peer != nullptr && n == 1) {
 #pragma unroll
     for (int k = 0; k < RPW; k++)
       if (x_ok && (y0 + r0 + k) < Y) {
@@ -366,9 +369,9 @@ constexpr int kNumTiles = (int)(sizeof(kTiles) / sizeof(kTiles[0]));
 template <typename T, int TY>
 constexpr int stage_bytes() { return TileGeom<T, TY>::STAGE_BYTES; }
 
-template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF = 0, bool WIDE = false>
+template <typename T, int SCHEME, int TY, int RPW, int NST, int DIF = 0, bool WIDE = false, int TAIL = 0>
 int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupancy_out) {
-  auto kern = fdtd_update_tma<T, SCHEME, TY, RPW, NST, DIF, WIDE>;
+  auto kern = fdtd_update_tma<T, SCHEME, TY, RPW, NST, DIF, WIDE, TAIL>;
   const int smem = NST * stage_bytes<T, TY>();
   static bool attr_set[64] = {false};   // per device
   int dev = 0;
@@ -389,38 +392,38 @@ int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupanc
                                           c.lam2, c.a_air, a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints, make_dif<T>(a), make_wide<T>(a),
                                           (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr, a.sig_local,
                                           (a.z_end - a.z_begin == 1 && a.peer_plane) ? a.sig_remote : nullptr, a.sig_side,
-                                          (const FusedSrcRec<T>*)a.fused_srcrec);
+                                          a.fused_params, (const FusedSrcRec<T>*)a.fused_srcrec);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
 }
 
+// filter boundaries: one kernel per order on one shape per dtype -- fp32: 128x8 with six stages (72 registers, three
+// CTAs per SM); fp64: 128x7 with five (eight warps per CTA leave 128 registers).  Wide meshes (position classes x
+// material table) and the launches with a tail (edge planes, fused sources / receivers) run on the same shapes.
+template <typename T, int SCHEME, bool WIDE, int TAIL>
+int dispatch_order(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occ) {
+  constexpr int DTY = sizeof(T) == 4 ? 8 : 7, DNST = sizeof(T) == 4 ? 6 : 5;
+  switch (a.dif_order) {
+    case 0: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 0, WIDE, TAIL>(a, m, chunk, occ);
+    case 1: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 1, WIDE, TAIL>(a, m, chunk, occ);
+    case 2: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 2, WIDE, TAIL>(a, m, chunk, occ);
+    case 3: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 3, WIDE, TAIL>(a, m, chunk, occ);
+    case 4: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 4, WIDE, TAIL>(a, m, chunk, occ);
+  }
+  set_error("filter order %d is not supported", a.dif_order);
+  return PFDTD_ERR_INVALID;
+}
+
 template <typename T, int SCHEME>
 int dispatch_tile(const UpdateArgs& a, const TmaMaps& m, int tile, int chunk, int* occ) {
-  // filter boundaries: one kernel per order on the shape tma_pick_config selects for them -- fp32: 128x8 with six
-  // stages (72 registers, three CTAs per SM); fp64: 128x7 with five (eight warps per CTA leave 128 registers).
-  // Wide meshes (position classes x material table) run on the same shapes, with and without filters.
   constexpr int DTY = sizeof(T) == 4 ? 8 : 7, DNST = sizeof(T) == 4 ? 6 : 5;
-  if (a.wide) {
-    switch (a.dif_order) {
-      case 0: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 0, true>(a, m, chunk, occ);
-      case 1: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 1, true>(a, m, chunk, occ);
-      case 2: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 2, true>(a, m, chunk, occ);
-      case 3: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 3, true>(a, m, chunk, occ);
-      case 4: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 4, true>(a, m, chunk, occ);
-    }
-    set_error("filter order %d is not supported", a.dif_order);
-    return PFDTD_ERR_INVALID;
+  if (a.tail == 1) return a.wide ? dispatch_order<T, SCHEME, true, 1>(a, m, chunk, occ) : dispatch_order<T, SCHEME, false, 1>(a, m, chunk, occ);
+  if (a.tail == 2) {
+    PF_CHECK(a.dif_order == 0 && !a.wide, PFDTD_ERR_INVALID, "fused sources / receivers are built for the frequency-independent kernels");
+    return launch_tma_t<T, SCHEME, DTY, 1, DNST, 0, false, 2>(a, m, chunk, occ);
   }
-  if (a.dif_order > 0) {
-    switch (a.dif_order) {
-      case 1: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 1>(a, m, chunk, occ);
-      case 2: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 2>(a, m, chunk, occ);
-      case 3: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 3>(a, m, chunk, occ);
-      case 4: return launch_tma_t<T, SCHEME, DTY, 1, DNST, 4>(a, m, chunk, occ);
-    }
-    set_error("filter order %d is not supported", a.dif_order);
-    return PFDTD_ERR_INVALID;
-  }
+  if (a.wide) return dispatch_order<T, SCHEME, true, 0>(a, m, chunk, occ);
+  if (a.dif_order > 0) return dispatch_order<T, SCHEME, false, 0>(a, m, chunk, occ);
   switch (tile) {
     case 0: return launch_tma_t<T, SCHEME, 8, 1, 4>(a, m, chunk, occ);
     case 1: return launch_tma_t<T, SCHEME, 16, 2, 4>(a, m, chunk, occ);
@@ -452,6 +455,9 @@ bool tma_supported(int X, int Y, int dtype) {
   return X % 16 == 0 && X >= 16 && Y >= 1 && get_encode_fn() != nullptr;
 }
 
+// the one tile shape per dtype / scheme that the filter kernels, wide meshes and launches with a tail are built for
+int tma_tail_tile(int dtype, int scheme) { return dtype == PFDTD_F64 ? 6 : (scheme == SCH_INTERP ? 7 : 3); }
+
 const char* tma_tile_name(int dtype, int tile) {
   (void)dtype;
   return (tile >= 0 && tile < kNumTiles) ? kTiles[tile].name : "?";
@@ -475,7 +481,7 @@ int tma_pick_config(int dtype, int scheme, int dif_order, bool wide, int X, int 
   // over the four sub-partitions, which leaves 64 (fp32, four CTAs per SM) / 128 (fp64, two) registers per thread
   // and room for a fifth or sixth stage.  The filter kernels have one shape per dtype (dispatch_tile).
   int tile;
-  if (dif_order > 0 || wide) tile = dtype == PFDTD_F64 ? 6 : (scheme == SCH_INTERP ? 7 : 3);
+  if (dif_order > 0 || wide) tile = tma_tail_tile(dtype, scheme);
   else if (opt_tile > 0 && opt_tile <= kNumTiles) tile = (int)opt_tile - 1;
   else tile = (dtype == PFDTD_F32 && scheme == SCH_FORWARD) ? 7 : 6;
   if (Y <= 8 && kTiles[tile].ty > 8) tile = 0;
@@ -484,6 +490,7 @@ int tma_pick_config(int dtype, int scheme, int dif_order, bool wide, int X, int 
   probe.scheme = scheme;
   probe.dif_order = dif_order;
   probe.wide = wide;
+  probe.tail = 0;
   TmaMaps dummy{};
   int occ = 0;
   if (scheme == SCH_INTERP) {
@@ -512,7 +519,7 @@ int tma_pick_config(int dtype, int scheme, int dif_order, bool wide, int X, int 
     for (int gz = 1; gz <= nplanes; gz++) {
       int ch = (nplanes + gz - 1) / gz;
       if (deep && ch > hi) continue;
-      if (ch < (deep ? lo : 8) && gz > 1) break;
+      if (ch < (deep ? lo : 2) && gz > 1) break;   // a launch of less than a wave is latency-bound: short chunks fill the machine
       int gz_eff = (nplanes + ch - 1) / ch;
       int64_t total = tiles * gz_eff;
       int64_t waves = (total + resident - 1) / resident;

@@ -158,8 +158,10 @@ __device__ __forceinline__ ClassEntry<T> class_entry(const ClassEntry<T>* __rest
 #define PFDTD_DIF_MAX_ORDER 4
 // how single-voxel planes are evaluated (DifRow): 0 = by the voxel's lane at the plane's turn, 1 = stashed in shared
 // memory and evaluated 32 planes at a time, 2 = the same with the stash in the registers of lane (plane & 31)
+// Measured on B200 (profiles/r02_dif_ab.md): 0 is the fastest for every scheme and dtype; 1 and 2 trade the one-lane filter
+// evaluation for a flush call and lose more to register pressure than they save in issue slots.
 #ifndef PFDTD_DIF_STASH
-#define PFDTD_DIF_STASH 1
+#define PFDTD_DIF_STASH 0
 #endif
 template <typename T>
 struct DifEntry {
@@ -307,12 +309,12 @@ struct alignas(16) DifStash {
 };
 
 // The deferred filter evaluation of a block's single-voxel planes (DifRow below): lane l holds the entry and the
-// states of plane z_blk + l.  `row` = address of (x = tile origin, the warp's row, plane 0) of the field being
+// states of plane z_blk + l.  `row` = address of (x = tile origin, the warp's row, plane z_blk) of the field being
 // written.  Out of line, arguments by value: it runs once per 32 planes and its registers stay out of the march.
 template <typename T, int ORD, bool WIDE>
 __device__ __noinline__ void dif_flush(uint2 ent, DifArr<T, ORD> sv, DifStash<T> mine, const DifArgs<T>& d,
                                        const DifEntry<T>* __restrict__ s_dif, const DifStash<T>* __restrict__ stash, T* __restrict__ row,
-                                       int64_t XY, int z_blk, int lane) {
+                                       int64_t XY, int lane) {
   constexpr int P = dif_pad(ORD);
   __syncwarp();                                     // the stash entries and the march's stores of these planes
   if (ent.y & DIF_SINGLE) {
@@ -327,7 +329,7 @@ __device__ __noinline__ void dif_flush(uint2 ent, DifArr<T, ORD> sv, DifStash<T>
     T ns[ORD], p_new;
     dif_filter<T, ORD>(e, sv.v, st.val0, st.p_old, p_new, ns);
     dif_st<T, ORD>(d.state + (size_t)ent.x * P, ns);
-    row[(int64_t)(z_blk + lane) * XY + (ent.y & 127u)] = p_new;
+    row[(int64_t)lane * XY + (ent.y & 127u)] = p_new;
   }
   __syncwarp();
 }
@@ -380,11 +382,12 @@ struct DifRow {
     load_block(d, z_lo, z_hi, gy, Y, lane);
   }
 
-  // end of plane j (of n): flush the block that ends here, then fetch the next block of entries
+  // end of plane j (of n): flush the block that ends here, then fetch the next block of entries.  row_next = address of
+  // (x = tile origin, the warp's row, plane j + 1) of the field being written (derived from the march's store pointer)
   __device__ __forceinline__ void next(const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif, const DifStash<T>* __restrict__ stash,
-                                       T* __restrict__ row, int64_t XY, int j, int n, int z_lo, int z_hi, int gy, int Y, int lane) {
+                                       T* __restrict__ row_next, int64_t XY, int j, int n, int z_lo, int z_hi, int gy, int Y, int lane) {
 #if PFDTD_DIF_STASH == 0
-    (void)s_dif; (void)stash; (void)row; (void)XY;
+    (void)s_dif; (void)stash; (void)row_next; (void)XY;
     if (((j + 1) & 31) == 0 && j + 1 < n) load_block(d, z_lo + j + 1, z_hi, gy, Y, lane);
 #else
     if (((j + 1) & 31) == 0 || j + 1 == n) {
@@ -395,9 +398,9 @@ struct DifRow {
 #if PFDTD_DIF_STASH == 2
         DifStash<T> mine;
         mine.val0 = r_val0; mine.p_old = r_old; mine.cls = r_cls; mine.pad = 0u;
-        dif_flush<T, ORD, WIDE>(ent, sv, mine, d, s_dif, stash, row, XY, z_lo + (j & ~31), lane);
+        dif_flush<T, ORD, WIDE>(ent, sv, mine, d, s_dif, stash, row_next - (int64_t)((j & 31) + 1) * XY, XY, lane);
 #else
-        dif_flush<T, ORD, WIDE>(ent, sv, DifStash<T>{}, d, s_dif, stash, row, XY, z_lo + (j & ~31), lane);
+        dif_flush<T, ORD, WIDE>(ent, sv, DifStash<T>{}, d, s_dif, stash, row_next - (int64_t)((j & 31) + 1) * XY, XY, lane);
 #endif
       }
       if (j + 1 < n) load_block(d, z_lo + j + 1, z_hi, gy, Y, lane);
@@ -408,8 +411,10 @@ struct DifRow {
   // Warp-convergent, plane j of the chunk.  res = the frequency-independent results of this lane's four voxels
   // (updated in place for runs / general segments; single voxels are patched by flush), pw = their class bytes.
   __device__ __forceinline__ void apply(int j, T (&res)[4], const T (&old)[4], uint32_t pw, bool active, int lane, const DifArgs<T>& d,
-                                        const DifEntry<T>* __restrict__ s_dif, DifStash<T>* __restrict__ stash, int64_t vox0) {
+                                        const DifEntry<T>* __restrict__ s_dif, DifStash<T>* __restrict__ stash, const T* vox_ptr, const T* field) {
     if (!(ent.y & DIF_ANY)) return;   // the same in every lane
+    // voxel index of this lane's voxel 0 (wide meshes look the material byte up with it): only formed where it is used
+    const int64_t vox0 = WIDE ? (int64_t)(vox_ptr - field) : 0;
     const uint32_t fl = __shfl_sync(0xffffffffu, ent.y, j & 31);
     if (!(fl & DIF_HAS)) return;
     if (fl & DIF_SINGLE) {

@@ -51,7 +51,11 @@ def test_fused_sources_and_receivers_equal_the_separate_launch(capi, gpu, name):
         got = _run(capi, case, 1, graph, blocks)
         assert np.array_equal(got[0], base[0]), (name, graph, blocks)
         assert np.array_equal(got[1], base[1]) and np.array_equal(got[2], base[2]), (name, graph, blocks)
-    assert _run(capi, case, 1, 0, [])[3] < base[3]        # one launch per step instead of two
+    fused_launches = _run(capi, case, 1, 0, [])[3]
+    if case.get("dif_order"):                             # the filter kernels keep the separate launch
+        assert fused_launches == base[3]
+    else:
+        assert fused_launches < base[3]                   # one launch per step instead of two
 
 
 def test_fused_soft_sources_accumulate_once(capi, gpu):

@@ -8,4 +8,6 @@ for lib in $LIBS; do for h in $HINTS; do
     echo -n "lib=$lib hints=$h $dt ut=$ut dif2: "; run --dtype $dt --update-type $ut --dif-order 2 --tma-hints $h
   done
   echo -n "lib=$lib hints=$h f32 ut=0 dif2 keep=0: "; PFDTD_DEBUG_DIF_KEEP=0 run --dif-order 2 --tma-hints $h
+  echo -n "lib=$lib hints=$h f32 ut=0 dif0: "; run --dif-order 0 --tma-hints $h
+  echo -n "lib=$lib hints=$h f64 ut=0 dif0: "; run --dtype f64 --dif-order 0 --tma-hints $h
 done; done
