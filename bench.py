@@ -181,7 +181,7 @@ def receiver_positions(gdims):
 
 # ---------------------------------------------------------------------------------------------------
 REPEATS = 5          # the K-step block is timed this many times; the median block is the reported one
-E2E_REPEATS = 3
+E2E_REPEATS = 5
 
 
 class Ctx:
@@ -312,7 +312,9 @@ def measure(ctx, dtype, update_type, dif_order, K, W, with_e2e=True, sampler=Non
         dif_addon = {"filter_voxels": int(n_bnd), "state_bytes_read_plus_written": int(2 * n_bnd * pad * np.dtype(npdt).itemsize),
                      "row_segment_entries_bytes": int(8 * ctx.nz * Y * ((X + 127) // 128))}
     ss.close()
+    clocks = sampler.stop(t_first, t_last) if (sampler is not None and ctx.rank == 0) else None   # the timed region only
     out = {
+        "clocks": clocks,
         "value": nvox_global * K / (step_ms * 1e-3) / 1e6, "ms_per_step": step_ms / K, "step_ms_blocks": [b / K for b in blocks],
         "wall_ms_per_step": walls[med] / K, "launches": int(launches), "kernel": kname, "halo": transport,
         "padded": (X, Y), "nvox_global": nvox_global, "responses": resp, "t_window": (t_first, t_last),
@@ -361,7 +363,7 @@ def measure_e2e(ctx, dtype, update_type, dif_order, K, src_tab, nvox_global):
     return {"value": nvox_global * K / mid["seconds"] / 1e6, "unit": "Mvox/s", "h2d_bytes_per_step": h2d * ctx.world / K,
             "d2h_bytes_per_step": d2h / K, "seconds": mid["seconds"], "setup_seconds": mid["setup_seconds"],
             "run_seconds": mid["run_seconds"], "srcrec_seconds": mid["srcrec_seconds"], "connect_seconds": mid["connect_seconds"],
-            "all_seconds": [r["seconds"] for r in runs], "repeats": E2E_REPEATS,
+            "all_seconds": [r["seconds"] for r in runs], "all_setup_seconds": [r["setup_seconds"] for r in runs], "repeats": E2E_REPEATS,
             "what": "median of %d: pfdtd_setup_mesh(host bid+mat, pinned) + make_partition [setup_seconds] + set_sources/receivers "
                     "+ pfdtd_run(K) incl. response D2H [run_seconds]" % E2E_REPEATS
                     + ("; the job's NCCL communicator already exists (created once per process)" if ctx.world > 1 else "")}
@@ -461,7 +463,7 @@ def run_ours(args):
 
     sampler = ClockSampler(local_rank)
     head = measure(ctx, args.dtype, args.update_type, args.dif_order, K, W, with_e2e=not args.no_e2e, sampler=sampler)
-    clocks = sampler.stop(*head["t_window"]) if rank == 0 else None
+    clocks = head["clocks"]
     resp = head["responses"]
     resp_ok = bool(np.isfinite(resp).all() and np.abs(resp).max() > 0)
 

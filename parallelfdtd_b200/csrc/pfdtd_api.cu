@@ -190,6 +190,19 @@ namespace pfdtd {
 
 static size_t esize(const pfdtd_solver* s) { return s->dtype == PFDTD_F32 ? 4 : 8; }
 
+// PFDTD_TRACE_SETUP=1: wall-clock of the set-up phases on stderr (device-synchronised at every mark)
+struct PhaseTrace {
+  bool on = getenv("PFDTD_TRACE_SETUP") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void mark(const char* what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pfdtd setup] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 static void partition_indexing(uint32_t dim, uint32_t n, std::vector<int64_t>& first, std::vector<int64_t>& size) {
   // CudaMesh::getPartitionIndexing, src/kernels/cudaMesh.h:280-307
   first.resize(n);
@@ -970,14 +983,18 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
   PF_CUDA(cudaMalloc(&d_counts, 2 * sizeof(unsigned long long)));
   scratch.ptrs.push_back(d_counts);
   PF_CUDA(cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), 0));
+  PhaseTrace tr;
+  tr.mark("alloc node volumes");
   const int skip_z0 = (s->opt_global_z_first == 0);   // only the global z=0 plane is dropped by the reference's copy
   PF_TRY(launch_prepare_nodes(d_bid, d_mat, np, nm, vx, vy, vz, nx, ny, nz, skip_z0, s->scheme == SCH_CENTRED, d_counts, 0));
   s->launch_count += (nx % 16 == 0) ? 1 : 3;
   unsigned long long h_counts[2] = {0, 0};
   PF_CUDA(cudaMemcpy(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost));
+  tr.mark("pad + translate + count");
   scratch.keep(d_bid); scratch.keep(d_mat);
   PF_CUDA(cudaFree(d_bid));   // adopted, like the reference (cudaMesh.cu:290-291)
   PF_CUDA(cudaFree(d_mat));
+  tr.mark("free input volumes");
   // node classes: distinct node keys (position byte, material byte [, K12, K8]) -> one class byte per voxel
   {
     const uint32_t air_code = s->scheme == SCH_CENTRED ? 0x80u : 0x86u;
@@ -1008,6 +1025,7 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
       PF_CUDA(cudaMemset(d_count, 0, sizeof(uint32_t)));
       PF_TRY(launch_mark_classes(np, key_mat, n_new, air_key, air_code, interp, nx, ny, nz, d_table, cap, d_count, 0));
       s->launch_count++;
+      tr.mark("mark classes");
       std::vector<uint32_t> table(cap);
       uint32_t count = 0;
       PF_CUDA(cudaMemcpy(table.data(), d_table, cap * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -1032,12 +1050,14 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
       PF_TRY(launch_assign_classes(np, key_mat, n_new, air_key, air_code, interp, nx, ny, nz, d_table, d_ids, cap, s->d_cls0, 0));
       PF_CUDA(cudaDeviceSynchronize());
       s->launch_count++;
+      tr.mark("assign classes");
       for (uint32_t k : found) s->class_keys.push_back(k);
       s->dif_lo = 2 + n_lossless;
       s->n_lossy = n_lossy;
       s->wide = attempt == 1;
     }
   }
+  tr.mark("class tables (host)");
   scratch.keep(np); scratch.keep(nm); scratch.keep(s->d_cls0);   // what the solver keeps; the rest goes with `scratch`
   s->d_pos0 = np; s->d_mat0 = nm;
   s->stage_device = device;
@@ -1076,8 +1096,10 @@ int pfdtd_setup_mesh(pfdtd_solver* s, const uint8_t* h_bid, const uint8_t* h_mat
   uint8_t *db = nullptr, *dm = nullptr;
   PF_CUDA(cudaMalloc(&db, n));
   PF_CUDA(cudaMalloc(&dm, n));
+  PhaseTrace tr;
   PF_CUDA(cudaMemcpy(db, h_bid, n, cudaMemcpyHostToDevice));
   PF_CUDA(cudaMemcpy(dm, h_mat, n, cudaMemcpyHostToDevice));
+  tr.mark("H2D bid + mat");
   return pfdtd_setup_mesh_device(s, device, db, dm, vx, vy, vz, block_x, block_y, block_z, element_type, dtype, params,
                                  material_coefs, n_unique_materials);
 }
@@ -1134,6 +1156,7 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
   PF_TRY(pfdtd_device_count(&ndev));
   std::vector<int64_t> first, size;
   partition_indexing(s->Z, n_partitions, first, size);
+  PhaseTrace tr;
   const size_t XY = (size_t)s->X * s->Y;
   const size_t es = esize(s);
   s->parts.resize(n_partitions);
@@ -1207,6 +1230,7 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       PF_CUDA(cudaMalloc(&p.P[b], nelem * es));
       PF_CUDA(cudaMemset(p.P[b], 0, nelem * es));
     }
+    tr.mark("partition: nodes + fields");
     PF_CUDA(cudaMalloc(&p.materials, s->materials_host.size()));
     PF_CUDA(cudaMemcpy(p.materials, s->materials_host.data(), s->materials_host.size(), cudaMemcpyHostToDevice));
     PF_CUDA(cudaMalloc(&p.d_step, 4 * sizeof(int)));
@@ -1263,6 +1287,7 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       PF_CUDA(cudaMalloc(&p.dif_table, std::max<uint32_t>(s->n_lossy, 1) * dif_entry_bytes(s->dtype)));
       s->launch_count++;
     }
+    tr.mark("partition: streams, filters");
     if (p.use_tma) {
       int64_t want_tile = s->opt_tma_tile;
       PF_TRY(tma_pick_config(s->dtype, s->scheme, (int)s->opt_dif_order, s->wide, (int)s->X, (int)s->Y, nplanes, p.device, want_tile, s->opt_tma_chunk,
@@ -1279,6 +1304,7 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       }
     }
   }
+  tr.mark("partition: tile config + maps");
   if (s->d_pos0) {   // free the staging volumes (cudaMesh.h:704-707)
     PF_CUDA(cudaSetDevice(s->stage_device));
     PF_CUDA(cudaFree(s->d_pos0));
