@@ -69,7 +69,6 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
   __shared__ __align__(8) uint64_t bar_empty[NST];
   __shared__ ClassEntry<T> s_table[256];
   __shared__ DifEntry<T> s_dif[DIF ? 64 : 1];
-  __shared__ DifStash<T> s_stash[(DIF && PFDTD_DIF_STASH == 1) ? NW * 32 : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -165,27 +164,24 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
       }
     }
     T* const vox_ptr = Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx;     // this lane's four voxels of plane z
-    if (DIF) drow.apply(j, res.v, old.v, pw, active, lane, dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0), vox_ptr, Pn);
-    if (active) stg4(vox_ptr, res);
+    if (DIF) drow.apply(j, res.v, old.v, pw, active, lane, dif, s_dif, vox_ptr, Pn);
+    if (active) {
+      stg4(vox_ptr, res);
+      if (TAIL == 1 && peer != nullptr) stg4(peer + (int64_t)gy * X + gx, res);   // edge launch: the neighbour slab's halo plane (update_kernels.cu)
+    }
     // the store above consumed everything read from stage s2 (and, at j == 0, from the two prologue stages)
     __syncwarp();
     if (lane == 0) {
       mbar_arrive(&bar_empty[s2]);
       if (j == 0) { mbar_arrive(&bar_empty[0]); mbar_arrive(&bar_empty[1 % NST]); }
     }
-    if (DIF) drow.next(dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0), vox_ptr + XY - 4 * lane, XY, j, n, z_lo, z_hi, gy, Y, lane);
+    if (DIF) drow.next(dif, j, n, z_lo, z_hi, gy, Y, lane);
     pm = pc;
     pc = pp;
   }
   if (TAIL == 2) fused_srcrec<T>(fused_p, fused, Pn, X, Y, TY, z_begin, z_end, chunk, hints, NW * 32);
   // edge launch of a slab (one plane): send the plane into the neighbour slab's halo plane (update_kernels.cu)
   if (TAIL == 1 && peer != nullptr && n == 1) {
-    if (active) {
-      const int64_t row = (int64_t)gy * X + gx;
-      V4<T> v;
-      ldg4(Pn + (int64_t)z_lo * XY + row, v);
-      stg4(peer + row, v);
-    }
     if (sig_remote != nullptr) halo_publish(sig_local, sig_remote, sig_side, NW * 32);
   }
 }

@@ -103,7 +103,6 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
   __shared__ __align__(8) uint64_t bar_empty[NST];
   __shared__ ClassEntry<T> s_table[256];
   __shared__ DifEntry<T> s_dif[DIF ? 64 : 1];
-  __shared__ DifStash<T> s_stash[(DIF && PFDTD_DIF_STASH == 1) ? NW * 32 : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -269,9 +268,14 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
             }
           }
         }
-        if (DIF) drow.apply(j, res.v, old[k].v, pw[k], active, lane, dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0),
-                            out + (int64_t)k * X, Pn);
-        if (active) stg4(out + (int64_t)k * X, res);
+        if (DIF) drow.apply(j, res.v, old[k].v, pw[k], active, lane, dif, s_dif, out + (int64_t)k * X, Pn);
+        if (active) {
+          stg4(out + (int64_t)k * X, res);
+          // edge launch (one plane): the same registers go straight into the neighbour slab's halo plane -- a peer-mapped
+          // store over NVLink when the neighbour lives on another GPU -- so compute and halo transfer are one launch and the
+          // tiles that finish first travel while the others are still being computed
+          if (TAIL == 1 && peer != nullptr) stg4(peer + (int64_t)(y0 + r0 + k) * X + gx, res);
+        }
       }
       out += XY;
       // every read of stage s1 (plane z tile, plus P_old/node bytes of plane z-1 read last iteration) is done
@@ -280,26 +284,14 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
         mbar_arrive_a(be + 8 * ((u + 1) % NST));
         if (j == 0) mbar_arrive_a(be);   // plane z_lo-1, read in the prologue
       }
-      if (DIF) drow.next(dif, s_dif, s_stash + (PFDTD_DIF_STASH == 1 ? warp * 32 : 0), out - xl, XY, j, n, z_lo, z_hi, y0 + r0, Y, lane);
+      if (DIF) drow.next(dif, j, n, z_lo, z_hi, y0 + r0, Y, lane);
 #pragma unroll
       for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
     }
   }
   // single slab: receivers of this step and sources of the next one, by the CTA that owns their voxel (tma_common.cuh)
   if (TAIL == 2) fused_srcrec<T>(fused_p, fused, Pn, X, Y, TY, z_begin, z_end, chunk, hints, NW * 32);
-  // Edge launch of a slab (one plane): the plane is the neighbour slab's halo for the next step.  Every lane sends the
-  // four voxels it has just written (read back from L2) straight into the neighbour's halo plane -- a peer-mapped
-  // store over NVLink when the neighbour lives on another GPU -- so compute and halo transfer are one launch and the
-  // tiles that finish first travel while the others are still being computed.
   if (TAIL == 1 && peer != nullptr && n == 1) {
-#pragma unroll
-    for (int k = 0; k < RPW; k++)
-      if (x_ok && (y0 + r0 + k) < Y) {
-        const int64_t row = (int64_t)(y0 + r0 + k) * X + gx;
-        V4<T> v;
-        ldg4(Pn + (int64_t)z_lo * XY + row, v);
-        stg4(peer + row, v);
-      }
     // neighbour in another process: tell it that this step's plane has arrived (tma_common.cuh)
     if (sig_remote != nullptr) halo_publish(sig_local, sig_remote, sig_side, NW * 32);
   }

@@ -156,13 +156,6 @@ __device__ __forceinline__ ClassEntry<T> class_entry(const ClassEntry<T>* __rest
 // c3 = kappa * sw/(1+beta0), kappa = 0.5*(6-K)*lam (forward / interpolated) or lam*(dir_x+dir_y+dir_z) (centred).
 // Order 0 leaves p_new = val0: exactly the reference's locally-reacting boundary.
 #define PFDTD_DIF_MAX_ORDER 4
-// how single-voxel planes are evaluated (DifRow): 0 = by the voxel's lane at the plane's turn, 1 = stashed in shared
-// memory and evaluated 32 planes at a time, 2 = the same with the stash in the registers of lane (plane & 31)
-// Measured on B200 (profiles/r02_dif_ab.md): 0 is the fastest for every scheme and dtype; 1 and 2 trade the one-lane filter
-// evaluation for a flush call and lose more to register pressure than they save in issue slots.
-#ifndef PFDTD_DIF_STASH
-#define PFDTD_DIF_STASH 0
-#endif
 template <typename T>
 struct DifEntry {
   T c3, b0;
@@ -299,41 +292,6 @@ __device__ __noinline__ Quad<T> dif_apply_multi(Quad<T> res_q, const Quad<T> old
   return res_q;
 }
 
-// What the march leaves behind for a single-voxel plane: the frequency-independent result of the voxel, the value
-// it overwrites and its class.  The filter itself runs once per 32 planes, on 32 voxels at a time (DifRow::flush).
-template <typename T, int N> struct DifArr { T v[N]; };
-template <typename T>
-struct alignas(16) DifStash {
-  T val0, p_old;
-  uint32_t cls, pad;
-};
-
-// The deferred filter evaluation of a block's single-voxel planes (DifRow below): lane l holds the entry and the
-// states of plane z_blk + l.  `row` = address of (x = tile origin, the warp's row, plane z_blk) of the field being
-// written.  Out of line, arguments by value: it runs once per 32 planes and its registers stay out of the march.
-template <typename T, int ORD, bool WIDE>
-__device__ __noinline__ void dif_flush(uint2 ent, DifArr<T, ORD> sv, DifStash<T> mine, const DifArgs<T>& d,
-                                       const DifEntry<T>* __restrict__ s_dif, const DifStash<T>* __restrict__ stash, T* __restrict__ row,
-                                       int64_t XY, int lane) {
-  constexpr int P = dif_pad(ORD);
-  __syncwarp();                                     // the stash entries and the march's stores of these planes
-  if (ent.y & DIF_SINGLE) {
-#if PFDTD_DIF_STASH == 2
-    const DifStash<T> st = mine;
-    (void)stash;
-#else
-    const DifStash<T> st = stash[lane];
-    (void)mine;
-#endif
-    const DifEntry<T>& e = dif_entry<T, WIDE>(d, s_dif, st.cls & 0xffu, st.cls >> 8);
-    T ns[ORD], p_new;
-    dif_filter<T, ORD>(e, sv.v, st.val0, st.p_old, p_new, ns);
-    dif_st<T, ORD>(d.state + (size_t)ent.x * P, ns);
-    row[(int64_t)lane * XY + (ent.y & 127u)] = p_new;
-  }
-  __syncwarp();
-}
-
 // Filter-boundary bookkeeping of one consumer warp (one tile row, 128 voxels, marching in z).  ORD = the filter
 // order the kernel is compiled for.  The filter states are the only dependent global loads of the march, and an
 // L2 round trip is longer than a plane's worth of work:
@@ -341,11 +299,11 @@ __device__ __noinline__ void dif_flush(uint2 ent, DifArr<T, ORD> sv, DifStash<T>
 //     DIF_ANY says whether the block has a filter voxel in this row segment at all -- segments in open air skip
 //     everything with one test per plane.
 //   * single-voxel planes (a wall crossing the rows: half of all row segments of a shoebox): lane l also loads the
-//     states of plane 32*b + l's voxel right away (filter voxels are numbered z-fastest within a row segment, so this
-//     is one coalesced access).  At the plane's turn the voxel's lane only stashes (val0, p_old, class) in shared
-//     memory -- one predicated store instead of a one-lane-wide filter evaluation per plane.  After the block's last
-//     plane, flush() runs the filter for all 32 planes at once, lane l for plane 32*b + l: full-width arithmetic,
-//     one coalesced state store, and a 4-byte patch of the value the march had stored for the voxel.
+//     states of plane 32*b + l's voxel right away, up to a whole block ahead (filter voxels are numbered z-fastest
+//     within a row segment, so this is one coalesced access); the plane's turn hands them to the voxel's lane by
+//     shuffle.  (Tried on B200 and dropped, profiles/r02_dif_ab.md: stashing (val0, p_old, class) per plane and running
+//     the filter for 32 planes at once, from shared memory or from registers -- the one-lane evaluation it saves costs
+//     less than the register pressure of the deferred pass.)
 //   * runs (rows lying in a wall): every lane loads the states of its own (up to four) voxels when the plane's turn
 //     comes -- one exposed round trip per plane, in the few warps that own such rows.
 //   * anything else: ranked by ballots, one pass per voxel of the busiest lane.
@@ -356,10 +314,6 @@ struct DifRow {
   static constexpr int P = dif_pad(ORD);
   uint2 ent;            // lane l: entry of plane 32*b + l; DIF_ANY is set in every lane's flags when any plane of the block has voxels
   T st_blk[ORD];        // lane l: states of the single filter voxel of plane 32*b + l
-#if PFDTD_DIF_STASH == 2
-  T r_val0, r_old;      // lane l: what the march left behind for plane 32*b + l
-  uint32_t r_cls;
-#endif
 
   __device__ __forceinline__ void load_block(const DifArgs<T>& d, int z_first, int z_end, int gy, int Y, int lane) {
     const int z = z_first + lane;
@@ -374,51 +328,26 @@ struct DifRow {
     if (__ballot_sync(0xffffffffu, (ent.y & DIF_HAS) != 0u)) ent.y |= DIF_ANY;
   }
   __device__ __forceinline__ void start(const DifArgs<T>& d, int z_lo, int z_hi, int gy, int Y, int lane) {
-#if PFDTD_DIF_STASH == 2
-    r_val0 = (T)0; r_old = (T)0; r_cls = 0u;
-#endif
 #pragma unroll
     for (int i = 0; i < ORD; i++) st_blk[i] = (T)0;
     load_block(d, z_lo, z_hi, gy, Y, lane);
   }
 
-  // end of plane j (of n): flush the block that ends here, then fetch the next block of entries.  row_next = address of
-  // (x = tile origin, the warp's row, plane j + 1) of the field being written (derived from the march's store pointer)
-  __device__ __forceinline__ void next(const DifArgs<T>& d, const DifEntry<T>* __restrict__ s_dif, const DifStash<T>* __restrict__ stash,
-                                       T* __restrict__ row_next, int64_t XY, int j, int n, int z_lo, int z_hi, int gy, int Y, int lane) {
-#if PFDTD_DIF_STASH == 0
-    (void)s_dif; (void)stash; (void)row_next; (void)XY;
+  // end of plane j (of n): the next block of entries is due
+  __device__ __forceinline__ void next(const DifArgs<T>& d, int j, int n, int z_lo, int z_hi, int gy, int Y, int lane) {
     if (((j + 1) & 31) == 0 && j + 1 < n) load_block(d, z_lo + j + 1, z_hi, gy, Y, lane);
-#else
-    if (((j + 1) & 31) == 0 || j + 1 == n) {
-      if (ent.y & DIF_ANY) {
-        DifArr<T, ORD> sv;
-#pragma unroll
-        for (int i = 0; i < ORD; i++) sv.v[i] = st_blk[i];
-#if PFDTD_DIF_STASH == 2
-        DifStash<T> mine;
-        mine.val0 = r_val0; mine.p_old = r_old; mine.cls = r_cls; mine.pad = 0u;
-        dif_flush<T, ORD, WIDE>(ent, sv, mine, d, s_dif, stash, row_next - (int64_t)((j & 31) + 1) * XY, XY, lane);
-#else
-        dif_flush<T, ORD, WIDE>(ent, sv, DifStash<T>{}, d, s_dif, stash, row_next - (int64_t)((j & 31) + 1) * XY, XY, lane);
-#endif
-      }
-      if (j + 1 < n) load_block(d, z_lo + j + 1, z_hi, gy, Y, lane);
-    }
-#endif
   }
 
   // Warp-convergent, plane j of the chunk.  res = the frequency-independent results of this lane's four voxels
-  // (updated in place for runs / general segments; single voxels are patched by flush), pw = their class bytes.
+  // (updated in place), pw = their class bytes.
   __device__ __forceinline__ void apply(int j, T (&res)[4], const T (&old)[4], uint32_t pw, bool active, int lane, const DifArgs<T>& d,
-                                        const DifEntry<T>* __restrict__ s_dif, DifStash<T>* __restrict__ stash, const T* vox_ptr, const T* field) {
+                                        const DifEntry<T>* __restrict__ s_dif, const T* vox_ptr, const T* field) {
     if (!(ent.y & DIF_ANY)) return;   // the same in every lane
     // voxel index of this lane's voxel 0 (wide meshes look the material byte up with it): only formed where it is used
     const int64_t vox0 = WIDE ? (int64_t)(vox_ptr - field) : 0;
     const uint32_t fl = __shfl_sync(0xffffffffu, ent.y, j & 31);
     if (!(fl & DIF_HAS)) return;
     if (fl & DIF_SINGLE) {
-#if PFDTD_DIF_STASH == 0
       T s[ORD];
 #pragma unroll
       for (int i = 0; i < ORD; i++) s[i] = __shfl_sync(0xffffffffu, st_blk[i], j & 31);
@@ -431,27 +360,6 @@ struct DifRow {
         dif_st<T, ORD>(d.state + (size_t)base * P, ns);
         put4<T>(res, q, p_new);
       }
-#elif PFDTD_DIF_STASH == 1
-      if ((uint32_t)lane == ((fl & 127u) >> 2)) {
-        const int q = (int)(fl & 3u);
-        DifStash<T> st;
-        st.val0 = sel4<T>(res, q);
-        st.p_old = sel4<T>(old, q);
-        st.cls = ((pw >> (8 * q)) & 0xffu) | (dif_mat<T, WIDE>(d, vox0 + q) << 8);
-        st.pad = 0u;
-        stash[j & 31] = st;
-      }
-#else
-      {   // q and the source lane are warp-uniform: every lane selects, the voxel's lane's values go to lane (j & 31)
-        const int q = (int)(fl & 3u), src = (int)((fl & 127u) >> 2);
-        const T v0 = __shfl_sync(0xffffffffu, sel4<T>(res, q), src);
-        const T po = __shfl_sync(0xffffffffu, sel4<T>(old, q), src);
-        uint32_t c = (pw >> (8 * q)) & 0xffu;
-        if (WIDE && lane == src) c |= dif_mat<T, WIDE>(d, vox0 + q) << 8;
-        c = __shfl_sync(0xffffffffu, c, src);
-        if (lane == (j & 31)) { r_val0 = v0; r_old = po; r_cls = c; }
-      }
-#endif
       return;
     }
     // rows lying in a wall and everything else: out of line, so that their register needs stay out of the march
