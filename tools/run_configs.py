@@ -27,6 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", nargs="+", default=["c3", "c5"])
     ap.add_argument("--steps", type=int, default=300, help="steps per run (c5: per source; BASELINE says 4000, see --full)")
+    ap.add_argument("--c3-steps", type=int, default=900, help="c3 runs longer so that the seating grid is reached")
     ap.add_argument("--full", action="store_true", help="c5 with the 4000 steps per source BASELINE.json names")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every dimension (smoke runs)")
     args = ap.parse_args()
@@ -70,12 +71,14 @@ def main():
             gen = lambda a, b: synth.banded_shoebox(dims, n_mat, a, b)
             X, Y, Z = dims
             rng = np.random.default_rng(5)
-            sources = [[int(rng.integers(X // 4, 3 * X // 4)), int(rng.integers(Y // 4, 3 * Y // 4)), int(rng.integers(Z // 8, 7 * Z // 8))] for _ in range(10)]
-            rec = [[X // 2, Y // 2, Z // 2], [X // 5, int(Y * 0.8), int(Z * 0.9)]]
+            reach = max(8, int(0.3 * args.steps))                    # the wave front travels ~0.87 voxels per step
+            sources = [[int(X // 2 + rng.integers(-reach, reach)), int(Y // 2 + rng.integers(-reach, reach)), int(Z // 2 + rng.integers(-reach, reach))]
+                       for _ in range(10)]
+            rec = [[X // 2, Y // 2, Z // 2], [X // 5, int(Y * 0.8), int(Z * 0.9)]]     # one every run reaches, one far away
             what = "fp64 IISO, 20 materials in z-bands, 10 source positions as separate runs"
         else:
             raise SystemExit(f"unknown config {cfg}")
-        steps = 4000 if (cfg == "c5" and args.full) else args.steps
+        steps = 4000 if (cfg == "c5" and args.full) else (args.c3_steps if cfg == "c3" else args.steps)
         lam = float(np.sqrt(3.0) / 2)
         prm = np.array([lam, lam * lam, 1.0 / 3.0, 0.0], dtype=npdt)
         tab = synth.material_table(list(np.linspace(0.99, 0.5, n_mat))).astype(npdt)
