@@ -59,8 +59,7 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
     fdtd_update_interp_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                            const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                            T* __restrict__ Pn, T d1, T d2, T d3, T d4, int X, int Y, int z_begin, int z_end, int chunk, int hints,
-                           const DifArgs<T> dif, const WideArgs<T> wide, T* __restrict__ peer, int* __restrict__ sig_local,
-                           int* __restrict__ sig_remote, int sig_side, const __grid_constant__ FusedParams fused_p,
+                           const DifArgs<T> dif, const WideArgs<T> wide, T* __restrict__ peer, const __grid_constant__ FusedParams fused_p,
                     const FusedSrcRec<T>* __restrict__ fused) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY;
@@ -181,9 +180,6 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
   }
   if (TAIL == 2) fused_srcrec<T>(fused_p, fused, Pn, X, Y, TY, z_begin, z_end, chunk, hints, NW * 32);
   // edge launch of a slab (one plane): send the plane into the neighbour slab's halo plane (update_kernels.cu)
-  if (TAIL == 1 && peer != nullptr && n == 1) {
-    if (sig_remote != nullptr) halo_publish(sig_local, sig_remote, sig_side, NW * 32);
-  }
 }
 
 // one thread per voxel; same arithmetic (fallback for dimensions the TMA path does not take, cross-check)
@@ -236,8 +232,7 @@ int launch_interp_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occup
   const UpdConst<T> c = make_const<T>(a);
   kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.cls, (const ClassEntry<T>*)a.class_table, a.n_classes, (T*)a.Pn, c.d[0],
                                           c.d[1], c.d[2], c.d[3], a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints, make_dif<T>(a), make_wide<T>(a),
-                                          (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr, a.sig_local,
-                                          (a.z_end - a.z_begin == 1 && a.peer_plane) ? a.sig_remote : nullptr, a.sig_side,
+                                          (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr,
                                           a.fused_params, (const FusedSrcRec<T>*)a.fused_srcrec);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;

@@ -411,7 +411,6 @@ static UpdateArgs make_update_args(pfdtd_solver* s, Partition& p, int z_begin, i
   a.n_classes = (int)s->class_keys.size();
   a.tma_hints = (int)s->opt_tma_hints;
   a.peer_plane = nullptr;
-  a.sig_local = nullptr; a.sig_remote = nullptr; a.sig_side = 0;
   a.tail = 0;
   a.fused_srcrec = nullptr;
   a.fused_params = FusedParams{};
@@ -460,7 +459,7 @@ static int ensure_class_tables(pfdtd_solver* s) {
 }
 
 static int launch_update(pfdtd_solver* s, Partition& p, int z_begin, int z_end, const TmaConfig& cfg, cudaStream_t st,
-                         bool timed, void* peer_plane = nullptr, int* sig_remote = nullptr, int sig_side = 0, bool fused = false) {
+                         bool timed, void* peer_plane = nullptr, bool fused = false) {
   if (z_end <= z_begin) return PFDTD_OK;
   UpdateArgs a = make_update_args(s, p, z_begin, z_end, st);
   if (fused) { a.fused_srcrec = p.d_fused; a.fused_params = p.fused_params; a.tail = 2; }
@@ -469,9 +468,6 @@ static int launch_update(pfdtd_solver* s, Partition& p, int z_begin, int z_end, 
   TmaConfig cfg_used = cfg;
   if (a.tail == 1) cfg_used.tile = tma_tail_tile(s->dtype, s->scheme);
   a.peer_plane = peer_plane;
-  a.sig_local = s->d_halo_flags;
-  a.sig_remote = sig_remote;
-  a.sig_side = sig_side;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed) {
     PF_CUDA(cudaEventCreate(&e0));
@@ -576,7 +572,7 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
     PF_CUDA(cudaSetDevice(p.device));
     // fused: the update launch records this step's receivers, injects the next step's sources and advances the step
     if (!p.fused) PF_TRY(launch_srcrec_for(s, p, p.s_main, 1, 1, 1));
-    PF_TRY(launch_update(s, p, 1, (int)p.size - 1, p.fused ? p.cfg_tail_full : p.cfg_full, p.s_main, timed, nullptr, nullptr, 0, p.fused));
+    PF_TRY(launch_update(s, p, 1, (int)p.size - 1, p.fused ? p.cfg_tail_full : p.cfg_full, p.s_main, timed, nullptr, p.fused));
     s->cur = 1 - c;
     return PFDTD_OK;
   }
@@ -584,16 +580,18 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
   s->halo_sent_up.assign(np, 0);      // interface k|k+1: partition k's top plane already stored into k+1's plane 0
   s->halo_sent_down.assign(np, 0);    //                  partition k+1's plane 1 already stored into k's last plane
   bool ext_sent_lo = false, ext_sent_hi = false;   // process boundaries served by the edge launches (CUDA IPC mapping)
-  // phase 1: sources/receivers + edge planes on the edge stream
+  // phase 1: sources / receivers on the MAIN stream, right behind the previous interior launch: the critical path of a
+  // step is interior -> sources/receivers -> interior on one stream, the edge planes and the halo traffic hang off it.
   for (size_t k = 0; k < np; k++) {
     Partition& p = s->parts[k];
     PF_CUDA(cudaSetDevice(p.device));
-    // wait for last step's interior of this partition and the neighbours' edge work (halo arrival + WAR)
-    PF_CUDA(cudaStreamWaitEvent(p.s_edge, p.ev_int, 0));
-    if (k > 0) PF_CUDA(cudaStreamWaitEvent(p.s_edge, s->parts[k - 1].ev_edge, 0));
-    if (k + 1 < np) PF_CUDA(cudaStreamWaitEvent(p.s_edge, s->parts[k + 1].ev_edge, 0));
-    PF_TRY(launch_srcrec_for(s, p, p.s_edge, 1, 1, 1));
-    PF_CUDA(cudaEventRecord(p.ev_src, p.s_edge));
+    // everything this step reads has arrived: own edge planes and halo traffic of the previous step, and the
+    // neighbours' edge work (they wrote this slab's halo planes; across processes the flag wait in srcrec does this)
+    PF_CUDA(cudaStreamWaitEvent(p.s_main, p.ev_edge, 0));
+    if (k > 0) PF_CUDA(cudaStreamWaitEvent(p.s_main, s->parts[k - 1].ev_edge, 0));
+    if (k + 1 < np) PF_CUDA(cudaStreamWaitEvent(p.s_main, s->parts[k + 1].ev_edge, 0));
+    PF_TRY(launch_srcrec_for(s, p, p.s_main, 1, 1, 1));
+    PF_CUDA(cudaEventRecord(p.ev_src, p.s_main));
   }
   for (size_t k = 0; k < np; k++) {
     Partition& p = s->parts[k];
@@ -617,7 +615,7 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
         peer_hi = s->parts[k + 1].P[1 - c];
         s->halo_sent_up[k] = 1;
       }
-      // neighbour PROCESSES whose slab is mapped here: same stores, plus the flag hand-over instead of a stream event
+      // neighbour PROCESSES whose slab is mapped here: same stores, then the flag hand-over instead of a stream event
       int *sig_lo = nullptr, *sig_hi = nullptr;
       if (p.use_tma && k == 0 && ipc_side(s, 0)) {
         peer_lo = (char*)s->link[0].nb_P[1 - c] + (size_t)(s->link[0].nb_size - 1) * plane_bytes;
@@ -629,15 +627,18 @@ static int enqueue_one_step(pfdtd_solver* s, bool timed, bool time_halo) {
         sig_hi = s->link[1].nb_flags + 0 /* HALO_FROM_LO */;
         ext_sent_hi = true;
       }
-      if (lo_nb) { PF_TRY(launch_update(s, p, zb, zb + 1, p.cfg_edge, p.s_edge, timed, peer_lo, sig_lo, 0)); ib = zb + 1; }
-      if (hi_nb) { PF_TRY(launch_update(s, p, ze - 1, ze, p.cfg_edge, p.s_edge, timed, peer_hi, sig_hi, 1)); ie = ze - 1; }
-      // interior on the main stream, concurrently with the halo traffic below
-      PF_CUDA(cudaStreamWaitEvent(p.s_main, p.ev_src, 0));
+      // edge planes on the edge stream (it waits for the sources, and through them for the previous interior launch)
+      PF_CUDA(cudaStreamWaitEvent(p.s_edge, p.ev_src, 0));
+      if (lo_nb) { PF_TRY(launch_update(s, p, zb, zb + 1, p.cfg_edge, p.s_edge, timed, peer_lo)); ib = zb + 1; }
+      if (hi_nb) { PF_TRY(launch_update(s, p, ze - 1, ze, p.cfg_edge, p.s_edge, timed, peer_hi)); ie = ze - 1; }
+      if (sig_lo || sig_hi) { PF_TRY(launch_halo_publish(s->d_halo_flags, sig_lo, sig_hi, p.s_edge)); s->launch_count++; }
+      // interior on the main stream, concurrently with the edge launches and the halo traffic below
       PF_TRY(launch_update(s, p, ib, ie, p.cfg_int, p.s_main, timed));
       PF_CUDA(cudaEventRecord(p.ev_int, p.s_main));
     } else {
-      PF_TRY(launch_update(s, p, zb, ze, p.cfg_full, p.s_edge, timed));
-      PF_CUDA(cudaEventRecord(p.ev_int, p.s_edge));
+      PF_TRY(launch_update(s, p, zb, ze, p.cfg_full, p.s_main, timed));
+      PF_CUDA(cudaEventRecord(p.ev_int, p.s_main));
+      PF_CUDA(cudaStreamWaitEvent(p.s_edge, p.ev_int, 0));   // the halo traffic below reads what this launch wrote
     }
   }
   // phase 2: halo traffic of the new field (index 1-c) on the edge streams
@@ -661,7 +662,7 @@ static int set_step_counters(pfdtd_solver* s, int step, int first_recordable, in
   int h[3] = {step, first_recordable, last_step};
   for (auto& p : s->parts) {
     PF_CUDA(cudaSetDevice(p.device));
-    cudaStream_t st = (s->parts.size() == 1 && !s->comm) ? p.s_main : p.s_edge;
+    cudaStream_t st = p.s_main;   // the stream the source / receiver launches run on
     PF_CUDA(cudaMemcpyAsync(p.d_step, h, sizeof(h), cudaMemcpyHostToDevice, st));
     if (p.d_item_step) {
       int items[PFDTD_FUSED_MAX];
@@ -1636,8 +1637,7 @@ int pfdtd_enqueue_steps(pfdtd_solver* s, uint32_t first_step, uint32_t n_steps) 
   PF_TRY(set_step_counters(s, (int)first_step, (int)first_step, (int)(first_step + n_steps) - 1));
   for (auto& p : s->parts) {
     PF_CUDA(cudaSetDevice(p.device));
-    cudaStream_t lead = single ? p.s_main : p.s_edge;
-    PF_CUDA(cudaEventRecord(p.ev_t0, lead));
+    PF_CUDA(cudaEventRecord(p.ev_t0, p.s_main));
   }
   uint32_t done = 0;
   const bool fused = single && s->parts[0].fused;
@@ -1678,13 +1678,13 @@ int pfdtd_enqueue_steps(pfdtd_solver* s, uint32_t first_step, uint32_t n_steps) 
       if (!fused) PF_TRY(launch_srcrec_for(s, p, p.s_main, 1, 0, 0));   // fused: the last update launch has recorded them
       PF_CUDA(cudaEventRecord(p.ev_t1, p.s_main));
     } else {
-      // the last step's interior, and the neighbours' halo copies into this partition's end planes
-      PF_CUDA(cudaStreamWaitEvent(p.s_edge, p.ev_int, 0));
+      // the last step's edge planes and halo traffic, and the neighbours' halo copies into this partition's end planes
+      PF_CUDA(cudaStreamWaitEvent(p.s_main, p.ev_edge, 0));
       const size_t k = (size_t)(&p - &s->parts[0]);
-      if (k > 0) PF_CUDA(cudaStreamWaitEvent(p.s_edge, s->parts[k - 1].ev_edge, 0));
-      if (k + 1 < s->parts.size()) PF_CUDA(cudaStreamWaitEvent(p.s_edge, s->parts[k + 1].ev_edge, 0));
-      PF_TRY(launch_srcrec_for(s, p, p.s_edge, 1, 0, 0));
-      PF_CUDA(cudaEventRecord(p.ev_t1, p.s_edge));
+      if (k > 0) PF_CUDA(cudaStreamWaitEvent(p.s_main, s->parts[k - 1].ev_edge, 0));
+      if (k + 1 < s->parts.size()) PF_CUDA(cudaStreamWaitEvent(p.s_main, s->parts[k + 1].ev_edge, 0));
+      PF_TRY(launch_srcrec_for(s, p, p.s_main, 1, 0, 0));
+      PF_CUDA(cudaEventRecord(p.ev_t1, p.s_main));
     }
   }
   return PFDTD_OK;
@@ -1860,7 +1860,7 @@ int pfdtd_step(pfdtd_solver* s, uint32_t step, int direction, void* h_response, 
   const bool single = (s->parts.size() == 1 && !s->comm);
   for (auto& p : s->parts) {
     PF_CUDA(cudaSetDevice(p.device));
-    cudaStream_t st = single ? p.s_main : p.s_edge;
+    cudaStream_t st = p.s_main;
     PF_TRY(launch_srcrec_for(s, p, st, 0, 1, 0));
     PF_TRY(launch_update(s, p, 1, (int)p.size - 1, p.cfg_full, st, false));
   }

@@ -118,11 +118,7 @@ struct UpdateArgs {
   // edge launches of a slab (exactly one plane): the freshly computed plane is also stored into this plane of the
   // neighbour slab -- its halo plane, on another GPU over NVLink when peer access exists -- by the same kernel
   void* peer_plane;
-  // ... and, when that neighbour lives in another process, the flag words of the hand-over (tma_common.cuh halo_publish)
-  int* sig_local;          // this process's flag block
-  int* sig_remote;         // the neighbour's flag word this launch publishes to (null: neighbour is in this process)
-  int sig_side;            // 0: towards the lower neighbour, 1: towards the upper one
-  // what the CTAs do after their march: 0 nothing, 1 edge launch (peer_plane / sig_*), 2 fused sources / receivers.
+  // what the CTAs do after their march: 0 nothing, 1 edge launch (peer_plane), 2 fused sources / receivers.
   // Launches with a tail run on the tile shape of tma_tail_tile() and need tensor maps encoded for it.
   int tail;
   FusedParams fused_params;
@@ -182,5 +178,8 @@ struct SrcRecArgs {
   cudaStream_t stream;
 };
 int launch_srcrec(const SrcRecArgs& a);
+// After the edge launches of a step (same stream): tell the neighbour PROCESSES that their halo planes hold this step
+// (tma_common.cuh: flag block layout).  remote_lo / remote_hi: the neighbours' flag words, either may be null.
+int launch_halo_publish(int* local_flags, int* remote_lo, int* remote_hi, cudaStream_t stream);
 
 }  // namespace pfdtd

@@ -61,6 +61,29 @@ __global__ void srcrec_kernel(T* __restrict__ P, int n_rec, const int64_t* __res
   }
 }
 
+// The stores of the edge launches into the neighbours' halo planes are complete when those launches are (stream order);
+// this one-thread launch right behind them publishes the step: own counter first, then the neighbour's flag word with
+// system-scope release.
+__global__ void halo_publish_kernel(int* __restrict__ local, int* __restrict__ remote_lo, int* __restrict__ remote_hi) {
+  __threadfence_system();
+  if (remote_lo != nullptr) {
+    const int seq = local[HALO_SEQ + 0] + 1;
+    local[HALO_SEQ + 0] = seq;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote_lo), "r"(seq) : "memory");
+  }
+  if (remote_hi != nullptr) {
+    const int seq = local[HALO_SEQ + 1] + 1;
+    local[HALO_SEQ + 1] = seq;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote_hi), "r"(seq) : "memory");
+  }
+}
+
+int launch_halo_publish(int* local_flags, int* remote_lo, int* remote_hi, cudaStream_t stream) {
+  halo_publish_kernel<<<1, 1, 0, stream>>>(local_flags, remote_lo, remote_hi);
+  PF_CUDA(cudaGetLastError());
+  return PFDTD_OK;
+}
+
 int launch_srcrec(const SrcRecArgs& a) {
   int threads = a.n_rec > 32 ? (a.n_rec > 256 ? 256 : ((a.n_rec + 31) / 32) * 32) : 32;
   if (a.dtype == PFDTD_F32)

@@ -136,31 +136,12 @@ __device__ __forceinline__ void stg4(double* p, const V4<double>& o) {
 // ---- halo hand-over between processes (one process per GPU) ------------------------------------------------------
 // The edge launch of a slab stores its plane into the neighbour process's halo plane through a CUDA-IPC mapping
 // (NVLink).  Ordering between the two processes goes through one word per direction in the RECEIVER's memory:
-// the sender publishes "step q done" after its last CTA has stored, the receiver's next step waits for it
-// (srcrec_kernels.cu).  Flag block of a process (ints): [0] published by the lower neighbour, [1] by the upper one,
-// [2] / [3] steps this process has published towards the lower / upper neighbour, [4] / [5] CTA counters of its two
-// edge launches, [6] set when a wait timed out.
+// the sender publishes "step q done" with a one-thread launch right behind its edge launches, the receiver's next
+// step waits for it (both in srcrec_kernels.cu).  Flag block of a process (ints): [0] published by the lower
+// neighbour, [1] by the upper one, [2] / [3] steps this process has published towards the lower / upper neighbour,
+// [6] set when a wait timed out.  (A first version published from inside the edge launch -- last CTA done -> flag; its
+// system-scope fence per CTA kept every edge CTA resident for a link round trip and tripled the edge launches' time.)
 enum : int { HALO_FROM_LO = 0, HALO_FROM_HI = 1, HALO_SEQ = 2, HALO_CTR = 4, HALO_ERR = 6, HALO_FLAG_INTS = 8 };
-
-// Called by every consumer thread of an edge launch after its peer stores.  `side`: 0 = towards the lower neighbour.
-// One system-scope fence per CTA (by thread 0, after the CTA barrier: the barrier orders the other threads' stores
-// before it, the fence is cumulative over them) -- a fence per thread costs a link round trip per warp.
-__device__ __forceinline__ void halo_publish(int* __restrict__ local, int* __restrict__ remote_slot, int side, int consumer_threads) {
-  asm volatile("bar.sync 1, %0;" ::"r"(consumer_threads) : "memory");   // consumer warps only: the producer warp has exited
-  if (threadIdx.x == 0) {
-    __threadfence_system();                                           // the CTA's peer stores, system-wide
-    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-    unsigned prev;
-    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(local + HALO_CTR + side) : "memory");
-    if (prev == total - 1) {                                          // every CTA of the plane has stored
-      local[HALO_CTR + side] = 0;
-      const int seq = local[HALO_SEQ + side] + 1;
-      local[HALO_SEQ + side] = seq;
-      __threadfence_system();
-      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote_slot), "r"(seq) : "memory");
-    }
-  }
-}
 
 // CTA -> (tile row, z chunk).  Natural order, or (hint bit 2) the first and last tile rows of every chunk first: in a
 // room those hold the rows that lie in the y walls, whose warps pay a state round trip per plane -- started first,

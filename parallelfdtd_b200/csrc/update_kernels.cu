@@ -93,8 +93,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
     fdtd_update_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_old,
                     const __grid_constant__ CUtensorMap tm_cls, const ClassEntry<T>* __restrict__ g_table, int n_classes,
                     T* __restrict__ Pn, T lam2, T a_air, int X, int Y, int z_begin, int z_end, int chunk, int hints,
-                    const DifArgs<T> dif, const WideArgs<T> wide, T* __restrict__ peer, int* __restrict__ sig_local,
-                    int* __restrict__ sig_remote, int sig_side, const __grid_constant__ FusedParams fused_p,
+                    const DifArgs<T> dif, const WideArgs<T> wide, T* __restrict__ peer, const __grid_constant__ FusedParams fused_p,
                     const FusedSrcRec<T>* __restrict__ fused) {
   using G = TileGeom<T, TY>;
   constexpr int NW = TY / RPW;
@@ -291,10 +290,6 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
   }
   // single slab: receivers of this step and sources of the next one, by the CTA that owns their voxel (tma_common.cuh)
   if (TAIL == 2) fused_srcrec<T>(fused_p, fused, Pn, X, Y, TY, z_begin, z_end, chunk, hints, NW * 32);
-  if (TAIL == 1 && peer != nullptr && n == 1) {
-    // neighbour in another process: tell it that this step's plane has arrived (tma_common.cuh)
-    if (sig_remote != nullptr) halo_publish(sig_local, sig_remote, sig_side, NW * 32);
-  }
 }
 
 // builds the per-class table with the device arithmetic of update_math.cuh (one thread per class)
@@ -382,8 +377,7 @@ int launch_tma_t(const UpdateArgs& a, const TmaMaps& m, int chunk, int* occupanc
   const UpdConst<T> c = make_const<T>(a);
   kern<<<grid, threads, smem, a.stream>>>(m.p_halo, m.p_old, m.cls, (const ClassEntry<T>*)a.class_table, a.n_classes, (T*)a.Pn,
                                           c.lam2, c.a_air, a.X, a.Y, a.z_begin, a.z_end, chunk, a.tma_hints, make_dif<T>(a), make_wide<T>(a),
-                                          (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr, a.sig_local,
-                                          (a.z_end - a.z_begin == 1 && a.peer_plane) ? a.sig_remote : nullptr, a.sig_side,
+                                          (a.z_end - a.z_begin == 1) ? (T*)a.peer_plane : nullptr,
                                           a.fused_params, (const FusedSrcRec<T>*)a.fused_srcrec);
   PF_CUDA(cudaGetLastError());
   return PFDTD_OK;
