@@ -162,9 +162,11 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
         }
       }
     }
-    T* const vox_ptr = Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx;     // this lane's four voxels of plane z
-    if (DIF) drow.apply(j, res.v, old.v, pw, active, lane, dif, s_dif, vox_ptr, Pn);
+    // (the voxel address is formed after the filter pass in narrow mode: the pass is the register-pressure peak of the loop)
+    if (DIF) drow.apply(j, res.v, old.v, pw, active, lane, dif, s_dif,
+                        WIDE ? Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx : (const T*)nullptr, Pn);
     if (active) {
+      T* const vox_ptr = Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx;     // this lane's four voxels of plane z
       stg4(vox_ptr, res);
       if (TAIL == 1 && peer != nullptr) stg4(peer + (int64_t)gy * X + gx, res);   // edge launch: the neighbour slab's halo plane (update_kernels.cu)
     }

@@ -1821,23 +1821,34 @@ int pfdtd_run(pfdtd_solver* s, uint32_t n_steps, void* h_response, pfdtd_interru
   PF_CHECK(s && !s->parts.empty(), PFDTD_ERR_INVALID, "make_partition must be called before run");
   auto t0 = std::chrono::steady_clock::now();
   PF_TRY(pfdtd_reserve_steps(s, n_steps));
-  // steps are enqueued in blocks of PROGRESS_MOD (kernels3d.h:36) so the callbacks keep their cadence
-  // without a device synchronisation per step
-  const uint32_t block = 100;
+  // Steps are enqueued in blocks that end on multiples of PROGRESS_MOD (kernels3d.h:36), so the progress callback keeps
+  // its cadence without a device synchronisation per step.  The reference polls the interrupt callback every step
+  // (kernels3d.cu:86-89); here, with a callback installed, a block is cut so that it holds about 25 ms of device work
+  // (measured on the previous block) and the queue is drained before the next poll: cancelling takes tens of
+  // milliseconds whatever the mesh size, at the price of one synchronisation per block.
+  const uint32_t cadence = 100;
   uint32_t done = 0;
   bool interrupted = false;
   auto tb = t0;
+  double ms_per_step = 0.0;
   while (done < n_steps) {
     if (interrupt && interrupt()) { interrupted = true; break; }
-    uint32_t nb = std::min(block, n_steps - done);
+    uint32_t nb = std::min(cadence - done % cadence, n_steps - done);
+    if (interrupt && ms_per_step > 0.0) nb = std::min<uint32_t>(nb, (uint32_t)std::max(1.0, 25.0 / ms_per_step));
+    else if (interrupt && done == 0) nb = std::min<uint32_t>(nb, 8);        // a first short block to learn the step time
     PF_TRY(pfdtd_enqueue_steps(s, done, nb));
-    if (progress) {
-      PF_TRY(sync_all(s));
-      auto tn = std::chrono::steady_clock::now();
-      progress((int)done, (int)n_steps, (float)(std::chrono::duration<double>(tn - tb).count() / nb));
-      tb = tn;
+    if (interrupt) {
+      PF_TRY(pfdtd_sync(s));
+      ms_per_step = s->last_total_ms / (double)nb;
     }
     done += nb;
+    if (progress && (done % cadence == 0 || done == n_steps)) {
+      PF_TRY(sync_all(s));
+      auto tn = std::chrono::steady_clock::now();
+      const uint32_t since = done % cadence == 0 ? cadence : done % cadence;
+      progress((int)(done - since), (int)n_steps, (float)(std::chrono::duration<double>(tn - tb).count() / since));
+      tb = tn;
+    }
   }
   PF_TRY(pfdtd_sync(s));
   if (h_response && s->n_rec) PF_TRY(pfdtd_fetch_responses(s, h_response, n_steps));

@@ -183,6 +183,25 @@ def test_run_in_blocks_and_interrupt(capi, gpu):
     r, _ = s.run(50, interrupt=lambda: 1)
     assert not r.any()
     s.close()
+    # an installed callback that never fires changes nothing (the run is cut into ~25 ms blocks, drained before each poll);
+    # one that fires at its 4th poll stops the run early: the steps before it are there, the rest is not
+    for fire_at in (None, 4):
+        s = capi.Solver()
+        s.setup_mesh(case["bid"], case["mat"], case["block"], 0, capi.F32, oracle.params(fc.LAM, 0), case["materials"])
+        s.make_partition(1, [0])
+        s.set_sources([[32, 32, 32]], [0], fc.source_table(case))
+        s.set_receivers(case["receivers"])
+        polls, seen = [], []
+        try:
+            r, _ = s.run(500, interrupt=lambda: (polls.append(1), int(fire_at is not None and len(polls) >= fire_at))[1],
+                         progress=lambda step, mx, t: seen.append(step))
+        finally:
+            s.close()
+        if fire_at is None:
+            assert np.array_equal(r, r_or) and seen == [0, 100, 200, 300, 400] and len(polls) >= 6
+        else:
+            done = 8 + 92 + 100                                       # blocks before the 4th poll: 8, 92, 100
+            assert len(polls) == 4 and np.array_equal(r[:, :done], r_or[:, :done]) and not r[:, done + 1:].any()
 
 
 @pytest.mark.parametrize("name", ["shoebox_48x40x49_ctr_f64_6mat_5parts", "hall_96x128x64_fwd_f32_5mat_oct1"])
