@@ -83,6 +83,21 @@ constexpr int tma_max_regs(size_t esize, int scheme, int ty, int rpw, int nst, i
   return fit > 255 ? 255 : fit;
 }
 
+// Unroll factor of the plane loop (see the loop).  Full unrolling over the stages everywhere except the fp32 centred
+// filter kernel, whose six-fold body (4344 SASS instructions) misses the instruction cache (ncu: `no_instruction` 2.1
+// stalls per issue, profiles/r02_ncu_f32_centred_dif2_512.json).
+#ifndef PFDTD_UNR_CENTRED_DIF
+#define PFDTD_UNR_CENTRED_DIF 0
+#endif
+#ifndef PFDTD_UNR_FORWARD_DIF
+#define PFDTD_UNR_FORWARD_DIF 0
+#endif
+__host__ __device__ constexpr int tma_unroll(size_t esize, int scheme, int dif, int nst) {
+  if (dif > 0 && esize == 4 && scheme == SCH_CENTRED && PFDTD_UNR_CENTRED_DIF > 0) return PFDTD_UNR_CENTRED_DIF;
+  if (dif > 0 && esize == 4 && scheme == SCH_FORWARD && PFDTD_UNR_FORWARD_DIF > 0) return PFDTD_UNR_FORWARD_DIF;
+  return nst;
+}
+
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: (TY/RPW + 1) warps (last warp = TMA producer)
 // DIF = 0: frequency-independent boundaries; 1..4: digital impedance filters of that order
 // (one-row-per-warp 128x8 tile: three resident CTAs per SM in fp32, two in fp64)
@@ -201,17 +216,26 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
 
   constexpr uint32_t AIR4 = CLS_AIR * 0x01010101u;
   T* out = Pn + (int64_t)z_lo * XY + (int64_t)(y0 + r0) * X + gx;   // this lane's four voxels of the warp's first row
-  uint32_t par = 0;                                                    // parity of the round that starts at plane jb
+  // The plane loop is unrolled UNR times.  UNR == NST (the default): every stage offset and barrier parity is a
+  // compile-time constant or one XOR.  UNR < NST: the stage of plane jb (`base_rt`) is carried in a register and the
+  // offsets cost a compare-and-subtract each -- a few integer instructions per plane for a loop body UNR / NST the size,
+  // which matters where the unrolled body outgrows the instruction cache (tma_unroll()).
+  constexpr int UNR = tma_unroll(sizeof(T), SCHEME, DIF, NST);
+  uint32_t par = 0;                                                    // parity of the round plane jb belongs to
+  uint32_t base_rt = 0;                                                // stage index of plane jb (UNR < NST only)
 
-  for (int jb = 0; jb < n; jb += NST, par ^= 1u) {
+  for (int jb = 0; jb < n; jb += UNR) {
 #pragma unroll
-    for (int u = 0; u < NST; u++) {
+    for (int u = 0; u < UNR; u++) {
       const int j = jb + u;
       if (j >= n) break;
-      constexpr int dummy = 0; (void)dummy;
-      const uint32_t s2 = (uint32_t)((u + 2) % NST) * G::STAGE_BYTES;   // stage of plane z+1 (and P_old / classes of z)
-      const uint32_t s1 = (uint32_t)((u + 1) % NST) * G::STAGE_BYTES;   // stage of plane z
-      mbar_wait_a(bf + 8 * ((u + 2) % NST), par ^ ((u + 2) >= NST ? 1u : 0u));
+      const uint32_t base = (UNR == NST) ? 0u : base_rt;
+      const uint32_t t1 = base + (uint32_t)(u + 1), t2 = base + (uint32_t)(u + 2);
+      const uint32_t i1 = t1 >= (uint32_t)NST ? t1 - NST : t1;           // stage of plane z
+      const uint32_t w2 = t2 >= (uint32_t)NST ? 1u : 0u;
+      const uint32_t i2 = w2 ? t2 - NST : t2;                            // stage of plane z+1 (and P_old / classes of z)
+      const uint32_t s2 = i2 * G::STAGE_BYTES, s1 = i1 * G::STAGE_BYTES;
+      mbar_wait_a(bf + 8 * i2, par ^ w2);
 
       V4<T> old[RPW];
       uint32_t pw[RPW];
@@ -280,12 +304,17 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
       // every read of stage s1 (plane z tile, plus P_old/node bytes of plane z-1 read last iteration) is done
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive_a(be + 8 * ((u + 1) % NST));
+        mbar_arrive_a(be + 8 * i1);
         if (j == 0) mbar_arrive_a(be);   // plane z_lo-1, read in the prologue
       }
       if (DIF) drow.next(dif, j, n, z_lo, z_hi, y0 + r0, Y, lane);
 #pragma unroll
       for (int k = 0; k < RPW; k++) { down[k] = cur[k]; cur[k] = up[k]; }
+    }
+    if (UNR == NST) par ^= 1u;
+    else {
+      base_rt += UNR;
+      if (base_rt >= (uint32_t)NST) { base_rt -= NST; par ^= 1u; }
     }
   }
   // single slab: receivers of this step and sources of the next one, by the CTA that owns their voxel (tma_common.cuh)

@@ -86,3 +86,32 @@ def test_committed_bench_lines_are_well_formed():
         assert d["e2e"] is None or {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
         bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
         assert not bad, (f, bad)
+
+
+def test_round2_bench_lines_carry_the_new_blocks():
+    """profiles/r02_*: median-of-blocks timing, the like-for-like block with its own roofline and e2e, the config-4 block,
+    and -- at N > 1 -- the single-GPU invariance check and the halo figures."""
+    def load(rel):
+        return json.loads(open(os.path.join(ROOT, "profiles", rel)).read().strip().splitlines()[-1])
+    n1, n2, n8 = load("r02_bench_n1.json"), load("r02_bench_n2_peer_stores.json"), load(os.path.join("r02_n8", "bench_n8_auto.json"))
+    for d in (n1, n2, n8):
+        assert len(d["step_ms_blocks"]) == 5 and sorted(d["step_ms_blocks"])[2] == d["ms_per_step"]
+        l = d["like_for_like"]
+        assert l["value"] > d["value"] and l["roofline"]["frac"] > 0.9 and l["e2e"]["value"] > 0
+        assert "frequency-independent" in l["config"]["boundaries"] and "frequency-dependent" in d["config"]["boundaries"]
+        assert d["e2e"]["setup_seconds"] > 0 and d["e2e"]["run_seconds"] > 0 and len(d["e2e"]["all_seconds"]) >= 3
+        assert d["roofline"]["kernel_ms_per_launch"] <= d["ms_per_step"] * 1.01        # a launch never takes longer than the step
+        assert not d["clocks"]["reasons"] or d["clocks"]["reasons"] == ["sw_power_cap"]
+        assert d["c4"]["overlap"]["value"] > 0 and "1024x1024x960" in d["c4"]["workload"]
+    assert n1["roofline"]["frac"] > 0.9 and n1["gpu_launches"] >= 21
+    for d in (n2, n8):
+        assert d["slab_invariance"] is True and d["slab_invariance_detail"]["headline"]["max_abs_diff"] == 0.0
+        assert "peer-mapped stores" in d["config"]["halo"] and d["halo_ms_per_exchange_alone"] > 0
+    # weak scaling at the stated size: config 4, 1.007e9 voxels per GPU, 8.05e9 at N = 8
+    eff = n8["c4"]["overlap"]["value"] / (8 * n1["c4"]["overlap"]["value"])
+    assert "8.05e9" in n8["c4"]["workload"] and eff > 0.85, eff
+    # configs 3 and 5 at their stated size on 8 GPUs
+    c3 = json.loads(open(os.path.join(ROOT, "profiles", "r02_n8", "configs_c3_n8_final.jsonl")).read().strip().splitlines()[0])
+    assert c3["voxels"] == 1536 * 1024 * 960 and c3["n_gpus"] == 8 and c3["receivers_reached"] == [16] and c3["same_responses_with_nccl_transport"]
+    c5 = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "r02_n8", "configs_c3_c5_n8.jsonl")).read().strip().splitlines()][-1]
+    assert c5["config"] == "c5" and c5["voxels"] == 2048 * 1024 * 1920 and c5["dtype"] == "f64" and c5["distinct_responses"] == 10
