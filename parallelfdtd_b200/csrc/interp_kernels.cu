@@ -138,10 +138,15 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
 
   // stage and barrier parity of plane z+1 are carried along instead of being derived from the plane index (a division per
   // plane in a kernel that is issue-bound: ncu, 72 % of the issue slots busy with filters on); the voxel address likewise
-  int s2 = 2 % NST;
-  uint32_t par2 = (uint32_t)((2 / NST) & 1);
-  T* vox_ptr = Pn + (int64_t)z_lo * XY + (int64_t)gy * X + gx;       // this lane's four voxels of plane z
+  int s2c = 2 % NST;
+  uint32_t par2c = (uint32_t)((2 / NST) & 1);
+  // (fp64 derives all three from the plane index instead: at its 128-register budget every value carried across the
+  // filter pass spills, and the carried form is 9 % slower there)
+  constexpr bool CARRY_PTR = sizeof(T) == 4;
+  T* vox_carry = Pn + (int64_t)z_lo * XY + (int64_t)gy * X + gx;     // this lane's four voxels of plane z
   for (int j = 0; j < n; j++) {
+    const int s2 = CARRY_PTR ? s2c : (j + 2) % NST;
+    const uint32_t par2 = CARRY_PTR ? par2c : (uint32_t)(((j + 2) / NST) & 1);
     mbar_wait(&bar_full[s2], par2);
     const unsigned char* st2 = smem_raw + (size_t)s2 * G::STAGE_BYTES;
     load_plane<T, TY, HAS_D3>(reinterpret_cast<const T*>(st2 + G::PT_OFF), r, lane, pp);
@@ -158,15 +163,18 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
       } else {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const ClassEntry<T> ce = class_entry<T, WIDE>(s_table, wide, (pw >> (8 * q)) & 0xffu, WIDE ? (int64_t)(vox_ptr - Pn) + q : 0);
+          const ClassEntry<T> ce = class_entry<T, WIDE>(s_table, wide, (pw >> (8 * q)) & 0xffu,
+                                                        WIDE ? (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx + q : 0);
           res.v[q] = voxel_interp<T, HAS_D3>(ce.c0, ce.c1, ce.c2, pc.c[q], pc.a4[q], pc.g4[q], pm.c[q], pm.a4[q], pm.g4[q], pp.c[q],
                                              pp.a4[q], pp.g4[q], old.v[q], d1, d2, d3);
         }
       }
     }
     // (the voxel address is formed after the filter pass in narrow mode: the pass is the register-pressure peak of the loop)
-    if (DIF) drow.apply(j, res.v, old.v, pw, active, lane, dif, s_dif, vox_ptr, Pn);
+    if (DIF) drow.apply(j, res.v, old.v, pw, active, lane, dif, s_dif,
+                        (CARRY_PTR || !WIDE) ? (const T*)vox_carry : (const T*)(Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx), Pn);
     if (active) {
+      T* const vox_ptr = CARRY_PTR ? vox_carry : Pn + (int64_t)(z_lo + j) * XY + (int64_t)gy * X + gx;
       stg4(vox_ptr, res);
       if (TAIL == 1 && peer != nullptr) stg4(peer + (int64_t)gy * X + gx, res);   // edge launch: the neighbour slab's halo plane (update_kernels.cu)
     }
@@ -179,8 +187,8 @@ __global__ void __launch_bounds__((TY + 1) * 32) __maxnreg__(sizeof(T) == 4 ? (T
     if (DIF) drow.next(dif, j, n, z_lo, z_hi, gy, Y, lane);
     pm = pc;
     pc = pp;
-    vox_ptr += XY;
-    if (++s2 == NST) { s2 = 0; par2 ^= 1u; }
+    if (CARRY_PTR) vox_carry += XY;
+    if (CARRY_PTR && ++s2c == NST) { s2c = 0; par2c ^= 1u; }
   }
   if (TAIL == 2) fused_srcrec<T>(fused_p, fused, Pn, X, Y, TY, z_begin, z_end, chunk, hints, NW * 32);
   // edge launch of a slab (one plane): send the plane into the neighbour slab's halo plane (update_kernels.cu)

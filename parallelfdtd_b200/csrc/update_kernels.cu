@@ -83,19 +83,24 @@ constexpr int tma_max_regs(size_t esize, int scheme, int ty, int rpw, int nst, i
   return fit > 255 ? 255 : fit;
 }
 
-// Unroll factor of the plane loop (see the loop).  Full unrolling over the stages everywhere except the fp32 centred
-// filter kernel, whose six-fold body (4344 SASS instructions) misses the instruction cache (ncu: `no_instruction` 2.1
-// stalls per issue, profiles/r02_ncu_f32_centred_dif2_512.json).
-#ifndef PFDTD_UNR_CENTRED_DIF
-#define PFDTD_UNR_CENTRED_DIF 0
+// Unroll factor of the plane loop (see the loop).  The frequency-independent kernels unroll over all stages (they run at
+// the copy bandwidth that way).  The filter kernels do NOT unroll: their six-fold body (3584 / 4344 SASS instructions
+// forward / centred) misses the instruction cache -- ncu `no_instruction` 0.5 / 2.1 stalls per issue
+// (profiles/r02_ncu_f32_centred_dif2_512.json) -- and the rolled loop is 3 % / 14 % faster at 512^3 in fp32, 4 % / 7 % in
+// fp64; for the frequency-independent kernels it changes nothing (profiles/r02_dif_ab.md).  0 = all stages.
+#ifndef PFDTD_UNR_DIF_F32
+#define PFDTD_UNR_DIF_F32 1
 #endif
-#ifndef PFDTD_UNR_FORWARD_DIF
-#define PFDTD_UNR_FORWARD_DIF 0
+#ifndef PFDTD_UNR_DIF_F64
+#define PFDTD_UNR_DIF_F64 1
+#endif
+#ifndef PFDTD_UNR_NODIF
+#define PFDTD_UNR_NODIF 0
 #endif
 __host__ __device__ constexpr int tma_unroll(size_t esize, int scheme, int dif, int nst) {
-  if (dif > 0 && esize == 4 && scheme == SCH_CENTRED && PFDTD_UNR_CENTRED_DIF > 0) return PFDTD_UNR_CENTRED_DIF;
-  if (dif > 0 && esize == 4 && scheme == SCH_FORWARD && PFDTD_UNR_FORWARD_DIF > 0) return PFDTD_UNR_FORWARD_DIF;
-  return nst;
+  (void)scheme;
+  const int want = dif > 0 ? (esize == 4 ? PFDTD_UNR_DIF_F32 : PFDTD_UNR_DIF_F64) : PFDTD_UNR_NODIF;
+  return want > 0 ? want : nst;
 }
 
 // grid: (ceil(X/128), ceil(Y/TY), n_chunks); block: (TY/RPW + 1) warps (last warp = TMA producer)
