@@ -325,7 +325,12 @@ def measure(ctx, dtype, update_type, dif_order, K, W, with_e2e=True, sampler=Non
                      "what": "the full-slab launch (N=1) / the interior launch of a slab with neighbours (N>1); the one-plane edge "
                              "launches run concurrently on their own stream and are listed separately",
                      "edge_kernel_ms_per_step": (edge_ms / K2) if n_edge else 0.0, "edge_launches_per_step": n_edge / K2,
-                     "how": f"CUDA events around every update launch over {K2} steps right after the timed blocks",
+                     "how": f"CUDA events around every update launch over {K2} steps right after the timed blocks (per-step launches: the "
+                            "dispatch latency of a launch falls inside its bracket; the timed blocks replay a CUDA graph)",
+                     # N = 1: one bulk launch per step, so the graph-replayed step time (which also holds the source / receiver
+                     # work) bounds the kernel's bandwidth from below without any event in between
+                     "achieved_from_step_time": (X * Y * (ctx.nz - 2) * ALGO_BYTES[dtype] / (step_ms / K * 1e-3) / 1e9) if ctx.world == 1 else None,
+                     "frac_from_step_time": (X * Y * (ctx.nz - 2) * ALGO_BYTES[dtype] / (step_ms / K * 1e-3) / 1e9 / peak) if ctx.world == 1 else None,
                      "addon_bytes_per_step_not_in_achieved": dif_addon},
         "halo_ms_per_exchange_alone": halo_clean_ms,
     }
@@ -576,7 +581,8 @@ def run_variants(args):
             d = json.loads(r.stdout.strip().splitlines()[-1])
             out.append({"variant": name, "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
                         "kernel": d["config"]["kernel"], "roofline_achieved_gbs": d["roofline"]["achieved"],
-                        "roofline_frac": d["roofline"]["frac"], "bytes_per_voxel_update": d["roofline"]["bytes_per_voxel_update"],
+                        "roofline_frac": d["roofline"]["frac"], "roofline_frac_from_step_time": d["roofline"].get("frac_from_step_time"),
+                        "bytes_per_voxel_update": d["roofline"]["bytes_per_voxel_update"],
                         "gpu_launches": d["gpu_launches"]})
         except Exception as e:  # noqa: BLE001
             out.append({"variant": name, "error": repr(e)[:200]})
