@@ -181,9 +181,10 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
   }
 
   // --------------------------------- consumers ---------------------------------------------------
-  // Shared memory is addressed through 32-bit window addresses kept in registers, and the plane loop is unrolled
-  // over the NST stages so that every stage offset and barrier parity is a compile-time constant or one XOR:
-  // the per-plane instruction count is what bounds this kernel once the boundary filters are switched on.
+  // Shared memory is addressed through 32-bit window addresses kept in registers.  The frequency-independent kernels
+  // unroll the plane loop over the NST stages so that every stage offset and barrier parity is a compile-time constant or
+  // one XOR; the filter kernels run it rolled, because their unrolled body does not fit the instruction cache
+  // (tma_unroll above).
   const int r0 = warp * RPW;                 // first tile row of this warp
   const int xl = 4 * lane;                   // x offset inside the tile
   const int gx = x0 + xl;
