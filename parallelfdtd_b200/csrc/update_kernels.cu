@@ -86,7 +86,7 @@ constexpr int tma_max_regs(size_t esize, int scheme, int ty, int rpw, int nst, i
 // Unroll factor of the plane loop (see the loop).  The frequency-independent kernels unroll over all stages (they run at
 // the copy bandwidth that way).  The filter kernels do NOT unroll: their six-fold body (3584 / 4344 SASS instructions
 // forward / centred) misses the instruction cache -- ncu `no_instruction` 0.5 / 2.1 stalls per issue
-// (profiles/r02_ncu_f32_centred_dif2_512.json) -- and the rolled loop is 3 % / 14 % faster at 512^3 in fp32, 4 % / 7 % in
+// (profiles/r02_ncu_f32_centred_dif2_512_unrolled.json) -- and the rolled loop is 3 % / 14 % faster at 512^3 in fp32, 4 % / 7 % in
 // fp64; for the frequency-independent kernels it changes nothing (profiles/r02_dif_ab.md).  0 = all stages.
 #ifndef PFDTD_UNR_DIF_F32
 #define PFDTD_UNR_DIF_F32 1
