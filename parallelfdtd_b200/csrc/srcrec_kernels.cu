@@ -23,7 +23,7 @@ __device__ __forceinline__ void halo_wait(int* __restrict__ flags, int from_slot
   for (;;) {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + from_slot) : "memory");
     if (v >= want) return;
-    if (clock64() - t0 > (6LL << 30)) { flags[HALO_ERR] = 1; return; }   // ~3 s
+    if (clock64() - t0 > (60LL << 30)) { flags[HALO_ERR] = 1; return; }   // ~30 s: ranks may start a run seconds apart
     __nanosleep(64);
   }
 }
