@@ -89,9 +89,7 @@ enum {
   /* single slab: record the receivers and inject the next step's sources inside the update launch instead of a
    * separate launch per step (the reference does both with per-element memcpys, kernels3d.cu:93-104,164-173).
    * 1 (default): where the step is launch-bound (slabs up to 2^24 voxels, frequency-independent boundaries, at most 16
-   * sources + receivers); 2: for any slab size; 0: always the separate launch.  Same results either way.
-   * (Also bit 2 of PFDTD_OPT_TMA_HINTS: CTAs of the first / last tile row -- rows lying in the y walls -- are
-   * scheduled first.) */
+   * sources + receivers); 2: for any slab size; 0: always the separate launch.  Same results either way. */
   PFDTD_OPT_FUSE_SRCREC = 15
 };
 

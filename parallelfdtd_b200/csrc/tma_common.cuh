@@ -143,19 +143,12 @@ __device__ __forceinline__ void stg4(double* p, const V4<double>& o) {
 // system-scope fence per CTA kept every edge CTA resident for a link round trip and tripled the edge launches' time.)
 enum : int { HALO_FROM_LO = 0, HALO_FROM_HI = 1, HALO_SEQ = 2, HALO_CTR = 4, HALO_ERR = 6, HALO_FLAG_INTS = 8 };
 
-// CTA -> (tile row, z chunk).  Natural order, or (hint bit 2) the first and last tile rows of every chunk first: in a
-// room those hold the rows that lie in the y walls, whose warps pay a state round trip per plane -- started first,
-// they finish inside the launch instead of forming its tail.  blockIdx.x (the tile column) is never remapped.
-__device__ __forceinline__ void cta_tile(int heavy_first, int& by, int& bz) {
+// CTA -> (tile row, z chunk): the natural order.  (A remapped order -- the first / last tile rows of every chunk, whose warps
+// pay a filter-state round trip per plane, launched first -- bought nothing, 0 ... -1.5 %, and the two remapped values kept
+// alive across the plane loop cost fp64 IISO + DIF 2 a spill and 8 % at its 128-register budget: profiles/r02_dif_ab.md.)
+__device__ __forceinline__ void cta_tile(int& by, int& bz) {
   by = blockIdx.y;
   bz = blockIdx.z;
-  const int gx = gridDim.x, gy = gridDim.y;
-  if (!heavy_first || gy < 3) return;
-  int t = by + gy * bz;                    // launch order within a tile column
-  const int n_heavy = 2 * gridDim.z;
-  if (t < n_heavy) { by = (t & 1) ? gy - 1 : 0; bz = t >> 1; }
-  else { t -= n_heavy; by = 1 + t % (gy - 2); bz = t / (gy - 2); }
-  (void)gx;
 }
 
 // ---- sources and receivers inside the update launch (single slab) ---------------------------------------------------
@@ -170,7 +163,7 @@ template <typename T>
 __device__ __noinline__ void fused_srcrec(const FusedParams& fp, const FusedSrcRec<T>* __restrict__ sr, T* __restrict__ Pn, int X, int Y,
                                           int ty, int z_begin, int z_end, int chunk, int hints, int consumer_threads) {
   int cby, cbz;
-  cta_tile(hints & 4, cby, cbz);
+  cta_tile(cby, cbz);
   const int x0 = blockIdx.x * TX, y0 = cby * ty;
   const int z_lo = z_begin + cbz * chunk, z_hi = min(z_lo + chunk, z_end);
   const int n_items = fp.n_src + fp.n_rec;

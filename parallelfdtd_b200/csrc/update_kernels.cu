@@ -126,7 +126,7 @@ __global__ void __launch_bounds__((TY / RPW + 1) * 32) __maxnreg__(tma_max_regs(
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   int cby, cbz;
-  cta_tile(hints & 4, cby, cbz);
+  cta_tile(cby, cbz);
   const int x0 = blockIdx.x * TX;
   const int y0 = cby * TY;
   const int z_lo = z_begin + cbz * chunk;
