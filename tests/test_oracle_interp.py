@@ -107,3 +107,36 @@ def test_weights_follow_the_published_family_and_land_on_the_right_neighbours(ut
         else:
             want = {0: d[3], 1: d[0], 2: d[1], 3: d[2]}[n_off]
         assert v == want, ((dx, dy, dz), v, want)
+
+
+@pytest.mark.parametrize("ut,a,b", [(3, 1.0 / 6.0, 0.0), (4, 1.0 / 4.0, 1.0 / 16.0)])
+@pytest.mark.parametrize("k", [(0.31, 0.0, 0.0), (0.4, 0.4, 0.0), (0.23, -0.37, 0.52), (1.1, 0.9, 1.3)])
+def test_plane_waves_follow_the_published_dispersion_relation(ut, a, b, k):
+    """Second literature anchor, independent of how the weights are written: the numerical dispersion relation of the compact
+    explicit family (Kowalczyk & van Walstijn 2011),
+        sin^2(w T / 2) = lam^2 [ (sx + sy + sz) - 4 a (sx sy + sx sz + sy sz) + 16 b sx sy sz ],   s_i = sin^2(k_i h / 2).
+    A sampled plane wave cos(w n T - k.x) with that w must be carried one step forward exactly by the oracle's update in
+    open air (k in radians per voxel; the last case is close to the grid's Nyquist limit)."""
+    lam = oracle.interp_lambda(ut)
+    l2 = lam * lam
+    sx, sy, sz = (np.sin(0.5 * q) ** 2 for q in k)
+    s2 = l2 * ((sx + sy + sz) - 4 * a * (sx * sy + sx * sz + sy * sz) + 16 * b * sx * sy * sz)
+    assert 0.0 <= s2 <= 1.0                                    # inside the stability limit
+    wT = 2.0 * np.arcsin(np.sqrt(s2))
+
+    X, Y, nz = 24, 20, 12
+    bid, mat = synth.shoebox((X, Y, nz + 8), 1)
+    pos, m, _, _ = oracle.setup_mesh(bid, mat, (4, 2, 1), 0, True)
+    pos, m = pos[4:4 + nz], m[4:4 + nz]                        # an all-air run of planes (walls only in x and y)
+    assert pos.shape == (nz, Y, X)
+    zz, yy, xx = np.meshgrid(np.arange(nz), np.arange(Y), np.arange(X), indexing="ij")
+    phase = k[0] * xx + k[1] * yy + k[2] * zz
+    p8 = oracle.params_interp(lam, 0, oracle.interp_coefficients(ut, l2), True)
+    new = oracle.step_slab(pos, m, 3, p8, np.zeros((1, 20)), np.cos(phase), np.cos(wT + phase))
+    want = np.cos(wT - phase)
+    inner = (slice(1, nz - 1), slice(3, Y - 3), slice(3, X - 3))   # away from the walls; planes 0 / nz-1 are halos
+    assert np.abs(new[inner] - want[inner]).max() < 1e-13
+    # and the relation discriminates: the leapfrog frequency of the 7-point scheme (a = b = 0) is measurably off
+    wT7 = 2.0 * np.arcsin(np.sqrt(min(1.0, l2 * (sx + sy + sz))))
+    if abs(wT7 - wT) > 1e-6:
+        assert np.abs(new[inner] - np.cos(wT7 - phase)[inner]).max() > 1e-8
