@@ -370,7 +370,9 @@ def measure_e2e(ctx, dtype, update_type, dif_order, K, src_tab, nvox_global):
             "run_seconds": mid["run_seconds"], "srcrec_seconds": mid["srcrec_seconds"], "connect_seconds": mid["connect_seconds"],
             "all_seconds": [r["seconds"] for r in runs], "all_setup_seconds": [r["setup_seconds"] for r in runs], "repeats": E2E_REPEATS,
             "what": "median of %d: pfdtd_setup_mesh(host bid+mat, pinned) + make_partition [setup_seconds] + set_sources/receivers "
-                    "+ pfdtd_run(K) incl. response D2H [run_seconds]" % E2E_REPEATS
+                    "+ pfdtd_run(K) incl. response D2H [run_seconds]; a repeat builds its solver out of the device blocks the library "
+                    "kept from the solvers destroyed before it (pfdtd_release_cached_memory), as every job after the first of a "
+                    "session does" % E2E_REPEATS
                     + ("; the job's NCCL communicator already exists (created once per process)" if ctx.world > 1 else "")}
 
 

@@ -116,6 +116,12 @@ int pfdtd_device_fill(int device, void* d_ptr, size_t count, size_t elem_size, c
 int pfdtd_device_upload(int device, void* d_dst, const void* h_src, size_t bytes);
 int pfdtd_device_download(int device, void* h_dst, const void* d_src, size_t bytes);
 int pfdtd_device_free(int device, void* d_ptr);
+/* The library keeps the large device blocks of a solver it has destroyed (node volumes, pressure fields, filter states; at most
+ * PFDTD_CACHE_MB megabytes per device, default 16384, 0 = keep nothing) and builds the next solver of the same size out of them
+ * instead of going through cudaFree / cudaMalloc again.  pfdtd_device_mem_mb counts them as free; an allocation that does
+ * not fit gives them back by itself.  This call returns them to the driver now (`device` -1: every device) -- what is left
+ * of the reference's cudaDeviceReset before a run (matlab/device_reset.cpp:5-17, App::resetDevices src/App.cpp:114-120). */
+int pfdtd_release_cached_memory(int device);
 
 /* ---- solver lifetime ----------------------------------------------------- */
 int pfdtd_create(pfdtd_solver** out);

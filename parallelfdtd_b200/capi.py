@@ -76,6 +76,11 @@ def device_count() -> int:
     return n.value if rc == 0 else 0
 
 
+def release_cached_memory(device: int = -1) -> None:
+    """Give the device blocks the library keeps for the next solver back to the driver (pfdtd_release_cached_memory)."""
+    _check(lib().pfdtd_release_cached_memory(C.c_int(device)))
+
+
 def voxelize(vertices, indices, dx, triangle_material=None):
     """voxelizeGeometry (reference src/kernels/voxelizationUtils.cu:47-146) on the device: closed triangle mesh ->
     voxelizer-style ``bid`` and material volumes ``[vz][vy][vx]``."""

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <list>
 #include <map>
 #include <mutex>
 
@@ -26,6 +27,135 @@ void set_error(const char* fmt, ...) {
   vsnprintf(buf, sizeof(buf), fmt, ap);
   va_end(ap);
   g_last_error = buf;
+}
+
+// ---- device block cache (pfdtd_internal.h) ---------------------------------------------------------
+namespace {
+constexpr size_t kCacheMinBytes = (size_t)1 << 20;
+constexpr int kCacheMaxDevices = 64;
+struct DevCache {
+  struct Block { void* p; size_t bytes; int dev; };
+  std::mutex mu;
+  std::map<void*, std::pair<size_t, int>> live;   // blocks handed out by dev_alloc: size, device
+  std::list<Block> idle;                          // cached blocks, least recently returned first
+  size_t idle_bytes[kCacheMaxDevices] = {};
+  size_t cap = (size_t)16384 << 20;
+  DevCache() {
+    if (const char* e = getenv("PFDTD_CACHE_MB")) cap = (size_t)std::max<long long>(0, atoll(e)) << 20;
+  }
+};
+DevCache& dev_cache() {
+  static DevCache* c = new DevCache();   // never destroyed: the CUDA context may be gone by the time statics are
+  return *c;
+}
+}  // namespace
+
+void dev_cache_release(int device) {
+  DevCache& c = dev_cache();
+  std::vector<void*> drop;
+  {
+    std::lock_guard<std::mutex> g(c.mu);
+    for (auto it = c.idle.begin(); it != c.idle.end();) {
+      if (device < 0 || it->dev == device) {
+        drop.push_back(it->p);
+        c.idle_bytes[it->dev] -= it->bytes;
+        it = c.idle.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+  for (void* q : drop) cudaFree(q);
+}
+
+size_t dev_cache_bytes(int device) {
+  DevCache& c = dev_cache();
+  std::lock_guard<std::mutex> g(c.mu);
+  return (device >= 0 && device < kCacheMaxDevices) ? c.idle_bytes[device] : 0;
+}
+
+int dev_alloc(void** d_ptr, size_t bytes) {
+  *d_ptr = nullptr;
+  DevCache& c = dev_cache();
+  size_t want = bytes ? bytes : 1;
+  int dev = 0;
+  PF_CUDA(cudaGetDevice(&dev));
+  const bool cached = c.cap > 0 && want >= kCacheMinBytes && dev < kCacheMaxDevices;
+  if (cached) {
+    want = (want + 511) & ~(size_t)511;
+    void* hit = nullptr;
+    {
+      std::lock_guard<std::mutex> g(c.mu);
+      for (auto it = c.idle.end(); it != c.idle.begin();) {   // most recently returned first
+        --it;
+        if (it->dev == dev && it->bytes == want) {
+          hit = it->p;
+          c.idle_bytes[dev] -= want;
+          c.idle.erase(it);
+          c.live[hit] = {want, dev};
+          break;
+        }
+      }
+    }
+    if (hit) {
+      // what the block held belongs to a solver that is gone: hand it out zero-filled, and finished
+      cudaError_t e = cudaMemsetAsync(hit, 0, want, 0);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+      if (e != cudaSuccess) { dev_free(hit); PF_CUDA(e); }
+      *d_ptr = hit;
+      return PFDTD_OK;
+    }
+  }
+  cudaError_t e = cudaMalloc(d_ptr, want);
+  if (e == cudaErrorMemoryAllocation) {   // the cache may be what is in the way
+    cudaGetLastError();
+    dev_cache_release(-1);
+    e = cudaMalloc(d_ptr, want);
+  }
+  if (e != cudaSuccess) *d_ptr = nullptr;
+  PF_CUDA(e);
+  if (cached) {
+    std::lock_guard<std::mutex> g(c.mu);
+    c.live[*d_ptr] = {want, dev};
+  }
+  return PFDTD_OK;
+}
+
+void dev_free(void* d_ptr) {
+  if (!d_ptr) return;
+  DevCache& c = dev_cache();
+  size_t bytes = 0;
+  int dev = 0;
+  {
+    std::lock_guard<std::mutex> g(c.mu);
+    auto it = c.live.find(d_ptr);
+    if (it == c.live.end()) bytes = 0;
+    else { bytes = it->second.first; dev = it->second.second; c.live.erase(it); }
+  }
+  if (bytes == 0 || bytes > c.cap) { cudaFree(d_ptr); return; }   // not ours (a caller's cudaMalloc), or larger than the cache
+  // cudaFree waits for the device; whoever frees a block and allocates the next one relies on that
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != dev) cudaSetDevice(dev);
+  const cudaError_t se = cudaDeviceSynchronize();
+  if (cur != dev) cudaSetDevice(cur);
+  if (se != cudaSuccess) { cudaFree(d_ptr); return; }             // a failed context: nothing to keep
+  std::vector<void*> drop;
+  {
+    std::lock_guard<std::mutex> g(c.mu);
+    for (auto it = c.idle.begin(); it != c.idle.end() && c.idle_bytes[dev] + bytes > c.cap;) {
+      if (it->dev == dev) {
+        drop.push_back(it->p);
+        c.idle_bytes[dev] -= it->bytes;
+        it = c.idle.erase(it);
+      } else {
+        ++it;
+      }
+    }
+    c.idle.push_back({d_ptr, bytes, dev});
+    c.idle_bytes[dev] += bytes;
+  }
+  for (void* q : drop) cudaFree(q);
 }
 
 // ---- NCCL, loaded lazily so that single-GPU use has no NCCL dependency ---------------------------
@@ -234,11 +364,11 @@ static int free_partitions(pfdtd_solver* s) {
     cudaSetDevice(p.device);
     if (p.s_main) cudaStreamSynchronize(p.s_main);
     if (p.s_edge) cudaStreamSynchronize(p.s_edge);
-    if (p.owns_nodes) { cudaFree(p.pos); cudaFree(p.mat); cudaFree(p.cls); }
+    if (p.owns_nodes) { dev_free(p.pos); dev_free(p.mat); dev_free(p.cls); }
     cudaFree(p.class_table); cudaFree(p.d_class_keys);
-    cudaFree(p.dif_state); cudaFree(p.dif_rowbase); cudaFree(p.dif_table);
+    dev_free(p.dif_state); dev_free(p.dif_rowbase); cudaFree(p.dif_table);
     cudaFree(p.d_wide_keys); cudaFree(p.wide_class_table); cudaFree(p.wide_dif_table);
-    cudaFree(p.P[0]); cudaFree(p.P[1]); cudaFree(p.materials); cudaFree(p.d_step);
+    dev_free(p.P[0]); dev_free(p.P[1]); cudaFree(p.materials); cudaFree(p.d_step);
     cudaFree(p.d_fused); cudaFree(p.d_item_step);
     cudaFree(p.d_src_elem); cudaFree(p.d_src_type); cudaFree(p.d_src_slot); cudaFree(p.d_rec_elem); cudaFree(p.d_rec_slot);
     cudaFree(p.d_src_samples); cudaFree(p.d_rec_out);
@@ -806,6 +936,7 @@ int pfdtd_device_mem_mb(int device, int* out_total_mb, int* out_free_mb) {
   PF_CUDA(cudaSetDevice(device));
   size_t f = 0, t = 0;
   PF_CUDA(cudaMemGetInfo(&f, &t));
+  f += dev_cache_bytes(device);   // blocks the library holds for reuse are given up when an allocation needs them
   if (out_total_mb) *out_total_mb = (int)(t >> 20);
   if (out_free_mb) *out_free_mb = (int)(f >> 20);
   return PFDTD_OK;
@@ -822,8 +953,7 @@ int pfdtd_device_alloc(int device, size_t bytes, void** d_ptr) {
   PF_CHECK(d_ptr != nullptr, PFDTD_ERR_INVALID, "null out pointer");
   *d_ptr = nullptr;
   PF_TRY(select_device(device));
-  PF_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 1));
-  return PFDTD_OK;
+  return dev_alloc(d_ptr, bytes);
 }
 
 int pfdtd_device_fill(int device, void* d_ptr, size_t count, size_t elem_size, const void* value) {
@@ -866,7 +996,13 @@ int pfdtd_device_download(int device, void* h_dst, const void* d_src, size_t byt
 int pfdtd_device_free(int device, void* d_ptr) {
   if (!d_ptr) return PFDTD_OK;
   PF_TRY(select_device(device));
-  PF_CUDA(cudaFree(d_ptr));
+  dev_free(d_ptr);
+  return PFDTD_OK;
+}
+
+int pfdtd_release_cached_memory(int device) {
+  PF_CHECK(device >= -1, PFDTD_ERR_INVALID, "device %d", device);
+  dev_cache_release(device);   // no CUDA call unless something is cached
   return PFDTD_OK;
 }
 
@@ -883,7 +1019,7 @@ int pfdtd_destroy(pfdtd_solver* s) {
   if (!s) return PFDTD_OK;
   if (!s->parts.empty()) sync_all(s);
   free_partitions(s);
-  if (s->d_pos0) { cudaSetDevice(s->stage_device); cudaFree(s->d_pos0); cudaFree(s->d_mat0); cudaFree(s->d_cls0); }
+  if (s->d_pos0) { cudaSetDevice(s->stage_device); dev_free(s->d_pos0); dev_free(s->d_mat0); dev_free(s->d_cls0); }
   // s->comm is owned by the process-wide communicator cache (pfdtd_comm_init)
   if (s->ev_h0) cudaEventDestroy(s->ev_h0);
   if (s->ev_h1) cudaEventDestroy(s->ev_h1);
@@ -955,7 +1091,7 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
   free_partitions(s);
   if (device < 0) PF_CUDA(cudaGetDevice(&device));
   PF_CUDA(cudaSetDevice(device));
-  if (s->d_pos0) { cudaFree(s->d_pos0); cudaFree(s->d_mat0); cudaFree(s->d_cls0); s->d_pos0 = s->d_mat0 = s->d_cls0 = nullptr; }
+  if (s->d_pos0) { dev_free(s->d_pos0); dev_free(s->d_mat0); dev_free(s->d_cls0); s->d_pos0 = s->d_mat0 = s->d_cls0 = nullptr; }
   s->dtype = dtype;
   s->element_type = (int)element_type;
   // scheme choice as in setupMesh: types 0,1,(3) -> Bilbao/forward, else Kowalczyk/centred (cudaMesh.cu:70-73,134-137)
@@ -970,16 +1106,16 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
   // (the reference frees them inside padWithZeros, cudaMesh.cu:290-291)
   struct Scratch {
     std::vector<void*> ptrs;
-    ~Scratch() { for (void* q : ptrs) cudaFree(q); }
+    ~Scratch() { for (void* q : ptrs) dev_free(q); }
     void keep(void* q) { ptrs.erase(std::remove(ptrs.begin(), ptrs.end(), q), ptrs.end()); }
   } scratch;
   scratch.ptrs.push_back(d_bid);
   scratch.ptrs.push_back(d_mat);
   uint8_t *np = nullptr, *nm = nullptr;
   unsigned long long* d_counts = nullptr;
-  PF_CUDA(cudaMalloc(&np, n_new));
+  PF_TRY(dev_alloc((void**)&np, n_new));
   scratch.ptrs.push_back(np);
-  PF_CUDA(cudaMalloc(&nm, n_new));
+  PF_TRY(dev_alloc((void**)&nm, n_new));
   scratch.ptrs.push_back(nm);
   PF_CUDA(cudaMalloc(&d_counts, 2 * sizeof(unsigned long long)));
   scratch.ptrs.push_back(d_counts);
@@ -993,8 +1129,8 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
   PF_CUDA(cudaMemcpy(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost));
   tr.mark("pad + translate + count");
   scratch.keep(d_bid); scratch.keep(d_mat);
-  PF_CUDA(cudaFree(d_bid));   // adopted, like the reference (cudaMesh.cu:290-291)
-  PF_CUDA(cudaFree(d_mat));
+  dev_free(d_bid);   // adopted, like the reference (cudaMesh.cu:290-291)
+  dev_free(d_mat);
   tr.mark("free input volumes");
   // node classes: distinct node keys (position byte, material byte [, K12, K8]) -> one class byte per voxel
   {
@@ -1046,7 +1182,7 @@ int pfdtd_setup_mesh_device(pfdtd_solver* s, int device, uint8_t* d_bid, uint8_t
         if (table[slot] != 0xffffffffu)
           ids[slot] = (uint8_t)(2 + (std::find(found.begin(), found.end(), table[slot]) - found.begin()));
       PF_CUDA(cudaMemcpy(d_ids, ids.data(), cap, cudaMemcpyHostToDevice));
-      PF_CUDA(cudaMalloc(&s->d_cls0, n_new));
+      PF_TRY(dev_alloc((void**)&s->d_cls0, n_new));
       scratch.ptrs.push_back(s->d_cls0);
       PF_TRY(launch_assign_classes(np, key_mat, n_new, air_key, air_code, interp, nx, ny, nz, d_table, d_ids, cap, s->d_cls0, 0));
       PF_CUDA(cudaDeviceSynchronize());
@@ -1095,11 +1231,16 @@ int pfdtd_setup_mesh(pfdtd_solver* s, const uint8_t* h_bid, const uint8_t* h_mat
   PF_CUDA(cudaGetDevice(&device));
   const size_t n = (size_t)vx * vy * vz;
   uint8_t *db = nullptr, *dm = nullptr;
-  PF_CUDA(cudaMalloc(&db, n));
-  PF_CUDA(cudaMalloc(&dm, n));
   PhaseTrace tr;
-  PF_CUDA(cudaMemcpy(db, h_bid, n, cudaMemcpyHostToDevice));
-  PF_CUDA(cudaMemcpy(dm, h_mat, n, cudaMemcpyHostToDevice));
+  int rc = dev_alloc((void**)&db, n);
+  if (rc == PFDTD_OK) rc = dev_alloc((void**)&dm, n);
+  tr.mark("alloc input volumes");
+  if (rc == PFDTD_OK) {
+    cudaError_t e = cudaMemcpy(db, h_bid, n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dm, h_mat, n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("pfdtd_setup_mesh: H2D of the node volumes failed: %s", cudaGetErrorString(e)); rc = PFDTD_ERR_CUDA; }
+  }
+  if (rc != PFDTD_OK) { dev_free(db); dev_free(dm); return rc; }
   tr.mark("H2D bid + mat");
   return pfdtd_setup_mesh_device(s, device, db, dm, vx, vy, vz, block_x, block_y, block_z, element_type, dtype, params,
                                  material_coefs, n_unique_materials);
@@ -1203,12 +1344,12 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       p.pos = s->d_pos0; p.mat = s->d_mat0; p.cls = s->d_cls0; p.owns_nodes = true;   // adopt (cudaMesh.h:697-700)
       s->d_pos0 = s->d_mat0 = s->d_cls0 = nullptr;
     } else {
-      PF_CUDA(cudaMalloc(&p.pos, nelem));
-      PF_CUDA(cudaMalloc(&p.mat, nelem));
+      PF_TRY(dev_alloc((void**)&p.pos, nelem));
+      PF_TRY(dev_alloc((void**)&p.mat, nelem));
       PF_CUDA(cudaMemcpyPeer(p.pos, p.device, s->d_pos0 + (size_t)p.first * XY, s->stage_device, nelem));
       PF_CUDA(cudaMemcpyPeer(p.mat, p.device, s->d_mat0 + (size_t)p.first * XY, s->stage_device, nelem));
       if (s->d_cls0) {
-        PF_CUDA(cudaMalloc(&p.cls, nelem));
+        PF_TRY(dev_alloc((void**)&p.cls, nelem));
         PF_CUDA(cudaMemcpyPeer(p.cls, p.device, s->d_cls0 + (size_t)p.first * XY, s->stage_device, nelem));
       }
     }
@@ -1228,7 +1369,7 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       }
     }
     for (int b = 0; b < 2; b++) {
-      PF_CUDA(cudaMalloc(&p.P[b], nelem * es));
+      PF_TRY(dev_alloc(&p.P[b], nelem * es));
       PF_CUDA(cudaMemset(p.P[b], 0, nelem * es));
     }
     tr.mark("partition: nodes + fields");
@@ -1268,22 +1409,22 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
       uint32_t* d_counts = nullptr;
       uint32_t* d_cols = nullptr;
       unsigned long long* d_nb = nullptr;
-      PF_CUDA(cudaMalloc(&p.dif_rowbase, n_seg * 2 * sizeof(uint32_t)));
-      PF_CUDA(cudaMalloc(&d_counts, n_seg * sizeof(uint32_t)));
+      PF_TRY(dev_alloc((void**)&p.dif_rowbase, n_seg * 2 * sizeof(uint32_t)));
+      PF_TRY(dev_alloc((void**)&d_counts, n_seg * sizeof(uint32_t)));
       PF_CUDA(cudaMalloc(&d_cols, (size_t)n_cols * sizeof(uint32_t)));
       PF_CUDA(cudaMalloc(&d_nb, sizeof(unsigned long long)));
       PF_TRY(launch_count_dif_segments(p.cls, (int)s->X, (int)s->Y, (int)p.size, s->dif_lo, d_counts, 0));
       PF_TRY(launch_build_dif_entries(d_counts, n_cols, (int)p.size, d_cols, d_nb, p.dif_rowbase, 0));
       unsigned long long run = 0;
       PF_CUDA(cudaMemcpy(&run, d_nb, sizeof(run), cudaMemcpyDeviceToHost));
-      PF_CUDA(cudaFree(d_counts));
+      dev_free(d_counts);
       PF_CUDA(cudaFree(d_cols));
       PF_CUDA(cudaFree(d_nb));
       PF_CHECK(run < 0x7fffffffull, PFDTD_ERR_INVALID, "too many boundary voxels in one slab");
       p.dif_nb = (uint32_t)run;
       s->launch_count += 3;
       const size_t sb = (size_t)std::max<uint32_t>(p.dif_nb, 1) * dif_state_pad((int)s->opt_dif_order) * es;
-      PF_CUDA(cudaMalloc(&p.dif_state, sb));
+      PF_TRY(dev_alloc(&p.dif_state, sb));
       PF_CUDA(cudaMemset(p.dif_state, 0, sb));
       PF_CUDA(cudaMalloc(&p.dif_table, std::max<uint32_t>(s->n_lossy, 1) * dif_entry_bytes(s->dtype)));
       s->launch_count++;
@@ -1308,9 +1449,9 @@ int pfdtd_make_partition(pfdtd_solver* s, uint32_t n_partitions, const uint32_t*
   tr.mark("partition: tile config + maps");
   if (s->d_pos0) {   // free the staging volumes (cudaMesh.h:704-707)
     PF_CUDA(cudaSetDevice(s->stage_device));
-    PF_CUDA(cudaFree(s->d_pos0));
-    PF_CUDA(cudaFree(s->d_mat0));
-    PF_CUDA(cudaFree(s->d_cls0));
+    dev_free(s->d_pos0);
+    dev_free(s->d_mat0);
+    dev_free(s->d_cls0);
     s->d_pos0 = s->d_mat0 = s->d_cls0 = nullptr;
   }
   s->tables_dirty = true;

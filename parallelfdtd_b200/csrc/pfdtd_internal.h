@@ -40,6 +40,20 @@ enum : int { SCH_FORWARD = 0, SCH_CENTRED = 2, SCH_INTERP = 3 };
     if (rc__ != PFDTD_OK) return rc__; \
   } while (0)
 
+// ---- device block cache (pfdtd_api.cu) -----------------------------------------------------------
+// The large device arrays of a solver (node volumes, pressure fields, filter states) are taken from / returned to a
+// per-device cache of blocks of exactly the sizes seen before, so that a process that runs one simulation after another
+// (a MATLAB or Python session) pays the driver's cudaMalloc / cudaFree -- milliseconds to tens of milliseconds per
+// 512 MB block on a busy host, profiles/r02_final_setup_trace.log -- once.  Semantics of the driver calls are kept:
+// dev_free synchronises the block's device before the block can be handed out again (cudaFree's implicit
+// synchronisation), a reused block is zero-filled, and an allocation that fails empties the cache and retries.
+// Blocks under 1 MiB, and pointers that did not come from dev_alloc (volumes a caller adopts out to the library), go
+// straight to the driver.  PFDTD_CACHE_MB = most cached megabytes per device (default 16384; 0 = no cache).
+int dev_alloc(void** d_ptr, size_t bytes);      // on the calling thread's current device
+void dev_free(void* d_ptr);                     // nullptr is fine
+void dev_cache_release(int device);             // cudaFree everything cached for `device` (-1: every device)
+size_t dev_cache_bytes(int device);
+
 // ---- mesh preparation kernels (mesh_kernels.cu) ------------------------------------------------
 // padWithZeros + toBilbao/toKowalczyk + calcBoundaries of the reference, on `stream`.
 int launch_pad_with_zeros(const uint8_t* d_old, uint8_t* d_new, uint32_t dx, uint32_t dy, uint32_t dz,

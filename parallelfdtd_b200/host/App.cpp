@@ -44,8 +44,12 @@ void App::queryDevices() {
   best_device_ = best;
 }
 // the reference calls cudaDeviceReset on every device here; resetting would also tear down other users of the
-// process' CUDA context (torch, MATLAB's GPU arrays), so this build only releases its own partitions
-void App::resetDevices() { m_mesh.destroyPartitions(); }
+// process' CUDA context (torch, MATLAB's GPU arrays), so this build only releases its own partitions and the device
+// blocks the library keeps for the next mesh
+void App::resetDevices() {
+  m_mesh.destroyPartitions();
+  pfdtd_release_cached_memory(-1);
+}
 void App::initializeDevices() {
   queryDevices();
   if (number_of_devices_ < 1) { c_log_msg(LOG_ERROR, "App::initializeDevices - no CUDA device"); throw(-1); }
