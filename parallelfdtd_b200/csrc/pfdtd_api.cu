@@ -68,6 +68,12 @@ void dev_cache_release(int device) {
   for (void* q : drop) cudaFree(q);
 }
 
+void dev_cache_forget(void* d_ptr) {
+  DevCache& c = dev_cache();
+  std::lock_guard<std::mutex> g(c.mu);
+  c.live.erase(d_ptr);
+}
+
 size_t dev_cache_bytes(int device) {
   DevCache& c = dev_cache();
   std::lock_guard<std::mutex> g(c.mu);
@@ -846,6 +852,9 @@ static int exchange_links(pfdtd_solver* s) {
   bool exportable = cudaIpcGetMemHandle(&mine.p0, p.P[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.p1, p.P[1]) == cudaSuccess &&
                     cudaIpcGetMemHandle(&mine.flags, s->d_halo_flags) == cudaSuccess;
   if (!exportable) cudaGetLastError();
+  // a field another process maps stays out of the block cache: it goes back to the driver with its solver, as it
+  // always did, instead of turning up inside a later solver while a neighbour may still hold the old mapping
+  if (exportable) { dev_cache_forget(p.P[0]); dev_cache_forget(p.P[1]); }
   mine.size = p.size;
   mine.can_peer = (exportable && p.use_tma && (int)p.size - 2 >= 4) ? 1 : 0;
   LinkHello* d_hello = nullptr;     // [0] mine, [1] from the lower neighbour, [2] from the upper one

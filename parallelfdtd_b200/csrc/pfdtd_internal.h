@@ -51,6 +51,7 @@ enum : int { SCH_FORWARD = 0, SCH_CENTRED = 2, SCH_INTERP = 3 };
 // straight to the driver.  PFDTD_CACHE_MB = most cached megabytes per device (default 16384; 0 = no cache).
 int dev_alloc(void** d_ptr, size_t bytes);      // on the calling thread's current device
 void dev_free(void* d_ptr);                     // nullptr is fine
+void dev_cache_forget(void* d_ptr);             // this block is not to be recycled: dev_free will hand it to cudaFree
 void dev_cache_release(int device);             // cudaFree everything cached for `device` (-1: every device)
 size_t dev_cache_bytes(int device);
 
