@@ -60,7 +60,7 @@ def test_recycled_blocks_give_the_answers_of_fresh_memory(capi, gpu, dif, double
         assert np.array_equal(again, fresh)                   # ... and the next solver is built out of them
     held = _free_mb(capi) - _free_mb(capi, raw=True)
     capi.release_cached_memory(0)
-    assert _free_mb(capi) - _free_mb(capi, raw=True) <= 1 and held >= 20
+    assert _free_mb(capi) - _free_mb(capi, raw=True) <= 4 and held >= 20
 
 
 def test_cached_blocks_count_as_free_memory_and_repeats_do_not_grow(capi, gpu):
@@ -110,7 +110,7 @@ def test_cache_can_be_switched_off(gpu):
             "assert lib.pfdtd_device_free(0, p) == 0\n"
             "b = torch.cuda.mem_get_info(0)[0]\n"
             "print((b - a) >> 20)\n")
-    for mb, lo, hi in (("0", 60, 70), ("1024", -2, 2)):
+    for mb, lo, hi in (("0", 56, 72), ("1024", -8, 8)):
         r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env={**os.environ, "PFDTD_CACHE_MB": mb}, capture_output=True, text=True,
                            timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
