@@ -135,8 +135,12 @@ void dev_free(void* d_ptr) {
   {
     std::lock_guard<std::mutex> g(c.mu);
     auto it = c.live.find(d_ptr);
-    if (it == c.live.end()) bytes = 0;
-    else { bytes = it->second.first; dev = it->second.second; c.live.erase(it); }
+    if (it == c.live.end()) {
+      for (const auto& b : c.idle) if (b.p == d_ptr) return;   // returned already: the block stays where it is
+      bytes = 0;
+    } else {
+      bytes = it->second.first; dev = it->second.second; c.live.erase(it);
+    }
   }
   if (bytes == 0 || bytes > c.cap) { cudaFree(d_ptr); return; }   // not ours (a caller's cudaMalloc), or larger than the cache
   // cudaFree waits for the device; whoever frees a block and allocates the next one relies on that
